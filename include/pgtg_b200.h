@@ -235,7 +235,19 @@ int pgtg_step_host(pgtg_env* env, const int32_t* actions, int8_t* obs_map, int32
                    int32_t* obs_velocity, double* reward, uint8_t* terminated, uint8_t* truncated,
                    void* stream);
 
+/* Recompute the observation buffers from the current state without ticking (the second half of
+ * set_to_state, environment.py:1342). */
+int pgtg_observe(pgtg_env* env, void* stream);
+
+/* add_traffic_rule / remove_traffic_rule (environment.py:569-575): replace the rule table. */
+int pgtg_update_rules(pgtg_env* env, const pgtg_rule* rules, int num_rules);
+
 int pgtg_get_buffers(pgtg_env* env, pgtg_buffers* out);
+/* DLPack export of one buffer of pgtg_buffers by field name ("obs_map", "reward", ...): *out
+ * receives a DLManagedTensor* (DLPack v0 ABI) that the caller wraps in a PyCapsule named
+ * "dltensor" (or hands to any DLPack consumer). The memory stays owned by the handle; the
+ * deleter only frees the descriptor. */
+int pgtg_dlpack(pgtg_env* env, const char* name, void** out_managed_tensor);
 int pgtg_get_state(pgtg_env* env, pgtg_state* out);
 /* set_to_state (environment.py:1301-1342): agent, flat_tire and cars only (quirk A.3-10). */
 int pgtg_set_state(pgtg_env* env, const pgtg_state* in);

@@ -1,0 +1,558 @@
+// pgtg_api_impl.hpp -- implementation of the C ABI (include/pgtg_b200.h) over a small memory /
+// launch backend. Included exactly once by
+//   pgtg_b200/csrc/pgtg_kernels.cu   backend = CUDA runtime on sm_100a (the product), and
+//   tests/emu/pgtg_emu.cpp           backend = host memory + loops (CPU test-suite only).
+// The including file defines, before the #include:
+//   void* bk_alloc(size_t);  void bk_free(void*);  int bk_set_device(int);
+//   int bk_h2d(void* dst, const void* src, size_t n, void* stream);   (async on stream)
+//   int bk_d2h(void* dst, const void* src, size_t n, void* stream);   (async on stream)
+//   int bk_memset(void* dst, int v, size_t n);  int bk_sync(void* stream);
+//   int bk_pick_block(const DevCfg&, int* block, size_t* smem);
+//   int bk_launch(pgtg_env*, int mode, const uint8_t* mask_dev, const int64_t* seeds_dev,
+//                 const void* actions_dev, int action_bytes, void* stream);
+//   const char* bk_error();
+#pragma once
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "pgtg_phases.cuh"
+
+using namespace pgtg;
+
+enum { MODE_STEP = 0, MODE_RESET = 1 };
+
+struct pgtg_env {
+  pgtg_config cfg;
+  DevCfg dc;
+  DevPtrs dp;
+  int device;
+  int block;
+  size_t smem;
+  int64_t launches;
+  std::vector<void*> allocs;
+  bool have_fixed, have_tape, did_reset;
+  int tape_mode;
+  // device scratch for reset arguments and host-buffer steps
+  uint8_t* mask_dev;
+  int64_t* seeds_dev;
+  int32_t* actions_dev;
+  // host tables kept for get_state / introspection
+  std::vector<uint16_t> edge_tab, edge_rev, border_slots;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+extern "C" const char* pgtg_last_error(void) { return g_err.c_str(); }
+extern "C" int pgtg_abi_version(void) { return PGTG_ABI_VERSION; }
+
+template <typename T>
+static T* dev_alloc(pgtg_env* e, size_t count, bool zero = true) {
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  void* ptr = bk_alloc(bytes);
+  if (!ptr) return nullptr;
+  e->allocs.push_back(ptr);
+  if (zero) bk_memset(ptr, 0, bytes);
+  return (T*)ptr;
+}
+
+// removable_edges order = graph-theory Graph.edges() after the add_edge calls of
+// generate_map_graph (map_generator.py:218-227): nodes in first-mention order, each node's
+// successors in insertion order. Node = tile index y * W + x.
+static void build_edge_tables(int W, int H, std::vector<uint16_t>& tab, std::vector<uint16_t>& rev) {
+  int T = W * H;
+  std::vector<int> order;
+  std::vector<char> known(T, 0);
+  std::vector<std::vector<int>> nbr(T);
+  auto add = [&](int a, int b) {
+    if (!known[a]) { known[a] = 1; order.push_back(a); }
+    if (!known[b]) { known[b] = 1; order.push_back(b); }
+    nbr[a].push_back(b);
+    nbr[b].push_back(a);  // bidirectional=True: reverse edge right after the forward one
+  };
+  for (int x = 0; x < W; x++)
+    for (int y = 0; y < H; y++) {
+      if (x < W - 1) add(y * W + x, y * W + x + 1);
+      if (y < H - 1) add(y * W + x, (y + 1) * W + x);
+    }
+  tab.clear();
+  for (int a : order) for (int b : nbr[a]) tab.push_back((uint16_t)(a | b << 8));
+  rev.assign(tab.size(), 0);
+  for (size_t i = 0; i < tab.size(); i++)
+    for (size_t j = 0; j < tab.size(); j++)
+      if ((tab[j] & 255) == (tab[i] >> 8) && (tab[j] >> 8) == (tab[i] & 255)) rev[i] = (uint16_t)j;
+}
+
+// possible_connections_to_borders (map_generator.py:350-360): rows (tile_y, tile_x, dir), with the
+// DEFAULT start and goal slots removed whatever the actual start/goal are
+static void build_border_slots(int W, int H, std::vector<uint16_t>& slots) {
+  struct Row { int y, x, d; };
+  std::vector<Row> rows;
+  for (int x = 0; x < W; x++) rows.push_back({0, x, 0});
+  for (int y = 0; y < H; y++) rows.push_back({y, W - 1, 1});
+  for (int x = 0; x < W; x++) rows.push_back({H - 1, x, 2});
+  for (int y = 0; y < H; y++) rows.push_back({y, 0, 3});
+  auto remove_first = [&](int y, int x, int d) {
+    for (size_t i = 0; i < rows.size(); i++)
+      if (rows[i].y == y && rows[i].x == x && rows[i].d == d) { rows.erase(rows.begin() + i); return; }
+  };
+  remove_first(H - 1, 0, 3);
+  remove_first(0, W - 1, 1);
+  slots.clear();
+  for (auto& r : rows) slots.push_back((uint16_t)((r.y * W + r.x) | r.d << 8));
+}
+
+// direction table evaluated with the host libm (the CPython `math` module calls the same atan2);
+// see pgtg_load_direction_lut in the header
+static void build_direction_lut(int R, std::vector<uint8_t>& lut) {
+  int n = 2 * R + 1;
+  lut.assign((size_t)n * n, 0);
+  const double PI_8 = M_PI / 8;
+  static const int remap[8] = {2, 1, 0, 7, 6, 5, 4, 3};
+  for (int dy = -R; dy <= R; dy++)
+    for (int dx = -R; dx <= R; dx++) {
+      double a = atan2((double)dy, (double)dx);
+      int o;
+      if (-PI_8 <= a && a < PI_8) o = 2;
+      else if (PI_8 <= a && a < 3 * PI_8) o = 3;
+      else if (3 * PI_8 <= a && a < 5 * PI_8) o = 4;
+      else if (5 * PI_8 <= a && a < 7 * PI_8) o = 5;
+      else if (a >= 7 * PI_8 || a < -7 * PI_8) o = 6;
+      else if (-7 * PI_8 <= a && a < -5 * PI_8) o = 7;
+      else if (-5 * PI_8 <= a && a < -3 * PI_8) o = 0;
+      else o = 1;
+      double a2 = atan2((double)(-dy), (double)dx);
+      int idx = (int)fmod((a2 + M_PI) / (M_PI / 4), 8.0);
+      lut[(size_t)(dy + R) * n + (dx + R)] = (uint8_t)(o | remap[idx & 7] << 3);
+    }
+}
+
+static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
+  memset(&d, 0, sizeof d);
+  if (c.abi_version != PGTG_ABI_VERSION) { why = "pgtg_config.abi_version mismatch"; return -1; }
+  if (c.num_envs < 1) { why = "num_envs must be >= 1"; return -1; }
+  if (c.map_w < 1 || c.map_h < 1 || c.map_w > 16 || c.map_h > 16) { why = "map width/height must be in 1..16 tiles"; return -1; }
+  if (c.num_channels < 0 || c.num_channels > PGTG_MAX_CHANNELS) { why = "too many observation planes"; return -1; }
+  if (c.sliding && (c.window_k < 0 || c.window_k > 15)) { why = "sliding_observation_window_size must be in 0..15"; return -1; }
+  if (c.num_rules < 0 || c.num_rules > PGTG_MAX_RULES) { why = "too many traffic rules"; return -1; }
+  if (c.light_green + c.light_yellow + c.light_red <= 0 || c.light_green + c.light_yellow + c.light_red > 0x7FFF) { why = "traffic light durations out of range"; return -1; }
+  if (c.rng_mode != PGTG_RNG_PHILOX && c.rng_mode != PGTG_RNG_TAPE) { why = "unknown rng_mode"; return -1; }
+  if (c.max_cars > 0xFFFF) { why = "max_cars too large"; return -1; }
+  d.N = c.num_envs; d.W = c.map_w; d.H = c.map_h; d.T = c.map_w * c.map_h; d.WS = c.map_w * TILE; d.HS = c.map_h * TILE;
+  d.C = c.num_channels; d.P = c.sliding ? 2 * c.window_k + 1 : TILE; d.sliding = c.sliding; d.window_k = c.window_k;
+  d.use_nsd = c.use_next_subgoal_direction;
+  for (int i = 0; i < PGTG_MAX_CHANNELS; i++) d.channel_kind[i] = c.channel_kind[i];
+  d.fixed_map = c.fixed_map; d.edges_to_keep = c.edges_to_keep; d.border_connections = c.border_connections;
+  d.start_mode = c.start_mode; d.goal_mode = c.goal_mode;
+  d.start_x = c.start_x; d.start_y = c.start_y; d.start_dir = c.start_dir;
+  d.goal_x = c.goal_x; d.goal_y = c.goal_y; d.goal_dir = c.goal_dir; d.min_sg_dist = c.min_start_goal_distance;
+  d.obstacle_probability = c.obstacle_probability;
+  for (int i = 0; i < 4; i++) d.obstacle_cdf[i] = c.obstacle_cdf[i];
+  d.sum_subgoals_reward = c.sum_subgoals_reward; d.final_goal_bonus = c.final_goal_bonus; d.crash_penalty = c.crash_penalty;
+  d.light_penalty = c.traffic_light_violation_penalty; d.standing_penalty = c.standing_still_penalty;
+  d.visited_penalty = c.already_visited_position_penalty;
+  d.ice_p = c.ice_probability; d.broken_p = c.street_damage_probability; d.sand_p = c.sand_probability;
+  d.traffic_density = c.traffic_density;
+  d.light_green = c.light_green; d.light_yellow = c.light_yellow; d.light_total = c.light_green + c.light_yellow + c.light_red;
+  d.ignore_traffic_collisions = c.ignore_traffic_collisions;
+  for (int i = 0; i < 5; i++) {
+    d.profile_cdf[i] = c.profile_cdf[i]; d.drv_yellow_stop[i] = c.drv_yellow_stop[i]; d.drv_red_violation[i] = c.drv_red_violation[i];
+    d.drv_patience_threshold[i] = c.drv_patience_threshold[i]; d.drv_push_probability[i] = c.drv_push_probability[i];
+    d.drv_speed_multiplier[i] = c.drv_speed_multiplier[i]; d.drv_reaction_delay[i] = c.drv_reaction_delay[i];
+    d.drv_min_following[i] = c.drv_min_following[i];
+  }
+  d.separate_reward_cost = c.separate_reward_cost; d.num_rules = c.num_rules; d.max_episode_steps = c.max_episode_steps;
+  d.write_final_obs = c.write_final_obs;
+  d.max_cars = c.max_cars > 0 ? c.max_cars : 1;
+  d.lut_radius = (d.WS > d.HS ? d.WS : d.HS) + 2;
+  int words = (d.T + 1) / 2;
+  if ((words & 1) == 0) words++;  // odd word stride: conflict-free shared-memory rows
+  d.tile_stride = words * 2;
+  if (c.already_visited_position_penalty != 0) { d.vis_w = d.HS + 2; d.vis_words = ((d.WS + 2) * (d.HS + 2) + 31) / 32; }
+  d.obs_bits = d.C * d.P * d.P;
+  d.env_id_base = c.env_id_base; d.seed = c.seed;
+  if (!c.fixed_map) {
+    int n_slots = 2 * d.W + 2 * d.H - 2;
+    if (c.border_connections < 0 || c.border_connections > n_slots) { why = "random_map_percentage_of_connections must be in [0, 1]"; return -1; }
+    if (c.edges_to_keep < 0) { why = "random_map_percentage_of_connections must be in [0, 1]"; return -1; }
+  }
+  return 0;
+}
+
+extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
+  if (!cfg || !out) return fail(PGTG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  DevCfg dc;
+  std::string why;
+  if (fill_devcfg(*cfg, dc, why)) return fail(PGTG_ERR_INVALID, why);
+  if (bk_set_device(device)) return fail(PGTG_ERR_CUDA, std::string("cannot select device: ") + bk_error());
+  pgtg_env* e = new pgtg_env();
+  e->cfg = *cfg; e->dc = dc; e->device = device; e->launches = 0;
+  e->have_fixed = e->have_tape = e->did_reset = false;
+  memset(&e->dp, 0, sizeof e->dp);
+  if (bk_pick_block(e->dc, &e->block, &e->smem)) { delete e; return fail(PGTG_ERR_INVALID, "observation window too large for shared memory"); }
+  DevPtrs& p = e->dp;
+  size_t N = (size_t)dc.N;
+  bool ok = true;
+#define A(field, type, count) ok = ok && ((p.field = dev_alloc<type>(e, (count))) != nullptr)
+  A(agent, short4, N); A(misc, uint32_t, N); A(elapsed, uint32_t, N); A(episode, uint32_t, N); A(next_car_id, uint32_t, N);
+  A(plan, uint32_t, N); A(tiles, uint16_t, N * dc.T + 8); A(cars, uint64_t, 2 * (size_t)dc.max_cars * N);
+  if (dc.vis_words) A(visited, uint32_t, (size_t)dc.vis_words * N);
+  A(key, uint64_t, N); A(error, uint32_t, N); A(ep_return, double, N);
+  if (cfg->rng_mode == PGTG_RNG_TAPE) { A(cursor, int64_t, N); A(tape_end, int64_t, N); }
+  A(obs_map, int8_t, N * dc.obs_bits + 16); A(obs_position, int32_t, 2 * N); A(obs_velocity, int32_t, 2 * N); A(obs_nsd, int32_t, N);
+  A(reward, double, N); A(cost, double, N); A(terminated, uint8_t, N); A(truncated, uint8_t, N);
+  A(step_state, int32_t, 4 * N); A(step_flags, uint8_t, N);
+  if (dc.write_final_obs) {
+    A(f_obs_map, int8_t, N * dc.obs_bits + 16); A(f_obs_position, int32_t, 2 * N); A(f_obs_velocity, int32_t, 2 * N); A(f_obs_nsd, int32_t, N);
+  }
+  A(stats, double, 8);
+  ok = ok && ((e->mask_dev = dev_alloc<uint8_t>(e, N)) != nullptr);
+  ok = ok && ((e->seeds_dev = dev_alloc<int64_t>(e, N)) != nullptr);
+  ok = ok && ((e->actions_dev = dev_alloc<int32_t>(e, N)) != nullptr);
+#undef A
+  if (!ok) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, std::string("device allocation failed: ") + bk_error()); }
+  // next_subgoal_direction is -1 when the feature is off (environment.py:1358)
+  {
+    std::vector<int32_t> neg(N, -1);
+    bk_h2d(p.obs_nsd, neg.data(), N * 4, nullptr);
+    if (p.f_obs_nsd) bk_h2d(p.f_obs_nsd, neg.data(), N * 4, nullptr);
+    std::vector<uint64_t> keys(N);
+    for (size_t i = 0; i < N; i++) keys[i] = cfg->seed + (uint64_t)cfg->env_id_base + i;
+    bk_h2d(p.key, keys.data(), N * 8, nullptr);
+    bk_sync(nullptr);
+  }
+  // tables
+  if (!cfg->fixed_map) {
+    build_edge_tables(dc.W, dc.H, e->edge_tab, e->edge_rev);
+    build_border_slots(dc.W, dc.H, e->border_slots);
+    e->dc.n_edge_tab = (int)e->edge_tab.size();
+    e->dc.n_border_slots = (int)e->border_slots.size();
+    uint16_t* t1 = dev_alloc<uint16_t>(e, e->edge_tab.size() + 1);
+    uint16_t* t2 = dev_alloc<uint16_t>(e, e->edge_rev.size() + 1);
+    uint16_t* t3 = dev_alloc<uint16_t>(e, e->border_slots.size() + 1);
+    if (!t1 || !t2 || !t3) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }
+    bk_h2d(t1, e->edge_tab.data(), e->edge_tab.size() * 2, nullptr);
+    bk_h2d(t2, e->edge_rev.data(), e->edge_rev.size() * 2, nullptr);
+    bk_h2d(t3, e->border_slots.data(), e->border_slots.size() * 2, nullptr);
+    p.edge_tab = t1; p.edge_rev = t2; p.border_slots = t3;
+  }
+  {
+    std::vector<uint8_t> lut;
+    build_direction_lut(dc.lut_radius, lut);
+    uint8_t* d = dev_alloc<uint8_t>(e, lut.size());
+    pgtg_rule* r = dev_alloc<pgtg_rule>(e, PGTG_MAX_RULES);
+    if (!d || !r) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }
+    bk_h2d(d, lut.data(), lut.size(), nullptr);
+    bk_h2d(r, cfg->rules, sizeof(pgtg_rule) * PGTG_MAX_RULES, nullptr);
+    p.dirlut = d; p.rules = r;
+  }
+  bk_sync(nullptr);
+  *out = e;
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_destroy(pgtg_env* e) {
+  if (!e) return PGTG_OK;
+  bk_set_device(e->device);
+  bk_sync(nullptr);
+  for (void* a : e->allocs) bk_free(a);
+  delete e;
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_load_fixed_map(pgtg_env* e, const pgtg_tile* tiles, int w, int h, int sx, int sy, int sdir, int gx,
+                                   int gy, int gdir) {
+  if (!e || !tiles) return fail(PGTG_ERR_INVALID, "null argument");
+  if (!e->cfg.fixed_map) return fail(PGTG_ERR_STATE, "config was not created with fixed_map");
+  if (w != e->dc.W || h != e->dc.H) return fail(PGTG_ERR_INVALID, "fixed map size differs from the config");
+  if (sx < 0 || sx >= w || sy < 0 || sy >= h || gx < 0 || gx >= w || gy < 0 || gy >= h || sdir < 0 || sdir > 3 || gdir < 0 || gdir > 3)
+    return fail(PGTG_ERR_INVALID, "start/goal outside the map");
+  std::vector<uint16_t> t((size_t)w * h);
+  for (int i = 0; i < w * h; i++) {
+    if (tiles[i].obstacle_type > 4 || tiles[i].obstacle_mask >= PGTG_NUM_MASKS) return fail(PGTG_ERR_INVALID, "bad obstacle type/mask");
+    t[i] = (uint16_t)((tiles[i].exits & 15) | tiles[i].obstacle_type << 4 | (tiles[i].obstacle_type ? tiles[i].obstacle_mask : 0) << 7);
+  }
+  bk_set_device(e->device);
+  uint16_t* d = dev_alloc<uint16_t>(e, t.size() + 1);
+  if (!d) return fail(PGTG_ERR_CUDA, "device allocation failed");
+  bk_h2d(d, t.data(), t.size() * 2, nullptr);
+  bk_sync(nullptr);
+  e->dp.fixed_tiles = d;
+  e->dp.fixed_plan = plan_pack(sx, sy, sdir, gx, gy, gdir, 0);
+  e->have_fixed = true;
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_load_direction_lut(pgtg_env* e, const uint8_t* lut, int radius) {
+  if (!e || !lut) return fail(PGTG_ERR_INVALID, "null argument");
+  if (radius != e->dc.lut_radius) return fail(PGTG_ERR_INVALID, "direction LUT radius must be max(width, height) in squares + 2");
+  bk_set_device(e->device);
+  size_t n = (size_t)(2 * radius + 1) * (2 * radius + 1);
+  bk_h2d((void*)e->dp.dirlut, lut, n, nullptr);
+  bk_sync(nullptr);
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_update_rules(pgtg_env* e, const pgtg_rule* rules, int num_rules) {
+  if (!e || (num_rules > 0 && !rules)) return fail(PGTG_ERR_INVALID, "null argument");
+  if (num_rules < 0 || num_rules > PGTG_MAX_RULES) return fail(PGTG_ERR_INVALID, "too many traffic rules");
+  bk_set_device(e->device);
+  bk_sync(nullptr);
+  if (num_rules) bk_h2d((void*)e->dp.rules, rules, sizeof(pgtg_rule) * num_rules, nullptr);
+  bk_sync(nullptr);
+  e->dc.num_rules = num_rules;
+  e->cfg.num_rules = num_rules;
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_load_draws(pgtg_env* e, const double* values, const uint8_t* tags, const int64_t* offsets) {
+  if (!e || !offsets) return fail(PGTG_ERR_INVALID, "null argument");
+  if (e->cfg.rng_mode != PGTG_RNG_TAPE) return fail(PGTG_ERR_STATE, "config was not created with rng_mode = PGTG_RNG_TAPE");
+  size_t N = (size_t)e->dc.N;
+  int64_t total = offsets[N];
+  if (total < 0 || offsets[0] != 0) return fail(PGTG_ERR_INVALID, "bad tape offsets");
+  bk_set_device(e->device);
+  double* v = dev_alloc<double>(e, (size_t)total + 1, false);
+  uint8_t* t = dev_alloc<uint8_t>(e, (size_t)total + 1, false);
+  if (!v || !t) return fail(PGTG_ERR_CUDA, "device allocation failed");
+  if (total) { bk_h2d(v, values, (size_t)total * 8, nullptr); bk_h2d(t, tags, (size_t)total, nullptr); }
+  bk_h2d(e->dp.cursor, offsets, N * 8, nullptr);
+  bk_h2d(e->dp.tape_end, offsets + 1, N * 8, nullptr);
+  bk_sync(nullptr);
+  e->dp.tape_values = v; e->dp.tape_tags = t;
+  e->have_tape = true;
+  return PGTG_OK;
+}
+
+static int check_ready(pgtg_env* e) {
+  if (!e) return fail(PGTG_ERR_INVALID, "null handle");
+  if (e->cfg.fixed_map && !e->have_fixed) return fail(PGTG_ERR_STATE, "fixed_map config: call pgtg_load_fixed_map first");
+  if (e->cfg.rng_mode == PGTG_RNG_TAPE && !e->have_tape) return fail(PGTG_ERR_STATE, "conformance mode: call pgtg_load_draws first");
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_reset(pgtg_env* e, const int64_t* seeds, const uint8_t* mask, void* stream) {
+  int rc = check_ready(e);
+  if (rc) return rc;
+  bk_set_device(e->device);
+  size_t N = (size_t)e->dc.N;
+  if (!e->did_reset && mask) return fail(PGTG_ERR_STATE, "the first reset must cover all envs");
+  if (seeds) bk_h2d(e->seeds_dev, seeds, N * 8, stream);
+  if (mask) bk_h2d(e->mask_dev, mask, N, stream);
+  if (bk_launch(e, MODE_RESET, mask ? e->mask_dev : nullptr, seeds ? e->seeds_dev : nullptr, nullptr, 0, stream))
+    return fail(PGTG_ERR_CUDA, std::string("reset launch failed: ") + bk_error());
+  e->launches++;
+  e->did_reset = true;
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_step(pgtg_env* e, const void* actions_dev, int action_bytes, void* stream) {
+  int rc = check_ready(e);
+  if (rc) return rc;
+  if (!e->did_reset) return fail(PGTG_ERR_STATE, "step before reset");
+  if (!actions_dev || (action_bytes != 4 && action_bytes != 8)) return fail(PGTG_ERR_INVALID, "actions must be device int32 or int64");
+  bk_set_device(e->device);
+  if (bk_launch(e, MODE_STEP, nullptr, nullptr, actions_dev, action_bytes, stream))
+    return fail(PGTG_ERR_CUDA, std::string("step launch failed: ") + bk_error());
+  e->launches++;
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_step_host(pgtg_env* e, const int32_t* actions, int8_t* obs_map, int32_t* obs_position,
+                              int32_t* obs_velocity, double* reward, uint8_t* terminated, uint8_t* truncated, void* stream) {
+  if (!e || !actions) return fail(PGTG_ERR_INVALID, "null argument");
+  bk_set_device(e->device);
+  size_t N = (size_t)e->dc.N;
+  bk_h2d(e->actions_dev, actions, N * 4, stream);
+  int rc = pgtg_step(e, e->actions_dev, 4, stream);
+  if (rc) return rc;
+  if (obs_map) bk_d2h(obs_map, e->dp.obs_map, N * e->dc.obs_bits, stream);
+  if (obs_position) bk_d2h(obs_position, e->dp.obs_position, N * 8, stream);
+  if (obs_velocity) bk_d2h(obs_velocity, e->dp.obs_velocity, N * 8, stream);
+  if (reward) bk_d2h(reward, e->dp.reward, N * 8, stream);
+  if (terminated) bk_d2h(terminated, e->dp.terminated, N, stream);
+  if (truncated) bk_d2h(truncated, e->dp.truncated, N, stream);
+  if (bk_sync(stream)) return fail(PGTG_ERR_CUDA, std::string("step failed: ") + bk_error());
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_get_buffers(pgtg_env* e, pgtg_buffers* out) {
+  if (!e || !out) return fail(PGTG_ERR_INVALID, "null argument");
+  memset(out, 0, sizeof *out);
+  const DevPtrs& p = e->dp;
+  out->num_envs = e->dc.N; out->num_channels = e->dc.C; out->window = e->dc.P; out->max_cars = e->dc.max_cars;
+  out->obs_map = p.obs_map; out->obs_position = p.obs_position; out->obs_velocity = p.obs_velocity;
+  out->obs_next_subgoal_direction = p.obs_nsd; out->reward = p.reward; out->cost = p.cost;
+  out->terminated = p.terminated; out->truncated = p.truncated; out->step_state = p.step_state; out->step_flags = p.step_flags;
+  out->final_obs_map = p.f_obs_map; out->final_obs_position = p.f_obs_position; out->final_obs_velocity = p.f_obs_velocity;
+  out->final_obs_next_subgoal_direction = p.f_obs_nsd; out->stats = p.stats;
+  return PGTG_OK;
+}
+
+// ---- DLPack (v0 ABI) ---------------------------------------------------------------------------
+struct DLDevice_ { int32_t device_type; int32_t device_id; };
+struct DLDataType_ { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor_ { void* data; DLDevice_ device; int32_t ndim; DLDataType_ dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset; };
+struct DLManagedTensor_ { DLTensor_ dl_tensor; void* manager_ctx; void (*deleter)(DLManagedTensor_*); };
+struct DLHolder { DLManagedTensor_ mt; int64_t shape[4]; };
+static void dl_deleter(DLManagedTensor_* mt) { delete (DLHolder*)mt->manager_ctx; }
+
+extern "C" int pgtg_dlpack(pgtg_env* e, const char* name, void** out) {
+  if (!e || !name || !out) return fail(PGTG_ERR_INVALID, "null argument");
+  const DevCfg& c = e->dc;
+  const DevPtrs& p = e->dp;
+  struct Spec { const char* name; void* ptr; int code, bits, ndim; int64_t shape[4]; };
+  int64_t N = c.N, C = c.C, P = c.P;
+  const Spec specs[] = {
+      {"obs_map", p.obs_map, 0, 8, 4, {N, C, P, P}},
+      {"obs_position", p.obs_position, 0, 32, 2, {N, 2}},
+      {"obs_velocity", p.obs_velocity, 0, 32, 2, {N, 2}},
+      {"obs_next_subgoal_direction", p.obs_nsd, 0, 32, 1, {N}},
+      {"reward", p.reward, 2, 64, 1, {N}},
+      {"cost", p.cost, 2, 64, 1, {N}},
+      {"terminated", p.terminated, 1, 8, 1, {N}},
+      {"truncated", p.truncated, 1, 8, 1, {N}},
+      {"step_state", p.step_state, 0, 32, 2, {N, 4}},
+      {"step_flags", p.step_flags, 1, 8, 1, {N}},
+      {"final_obs_map", p.f_obs_map, 0, 8, 4, {N, C, P, P}},
+      {"final_obs_position", p.f_obs_position, 0, 32, 2, {N, 2}},
+      {"final_obs_velocity", p.f_obs_velocity, 0, 32, 2, {N, 2}},
+      {"final_obs_next_subgoal_direction", p.f_obs_nsd, 0, 32, 1, {N}},
+      {"stats", p.stats, 2, 64, 1, {8}},
+  };
+  for (const Spec& s : specs) {
+    if (strcmp(s.name, name)) continue;
+    if (!s.ptr) return fail(PGTG_ERR_STATE, std::string("buffer not allocated in this configuration: ") + name);
+    DLHolder* h = new DLHolder();
+    for (int i = 0; i < s.ndim; i++) h->shape[i] = s.shape[i];
+    h->mt.dl_tensor.data = s.ptr;
+    h->mt.dl_tensor.device.device_type = bk_dl_device_type();
+    h->mt.dl_tensor.device.device_id = e->device;
+    h->mt.dl_tensor.ndim = s.ndim;
+    h->mt.dl_tensor.dtype.code = (uint8_t)s.code; h->mt.dl_tensor.dtype.bits = (uint8_t)s.bits; h->mt.dl_tensor.dtype.lanes = 1;
+    h->mt.dl_tensor.shape = h->shape; h->mt.dl_tensor.strides = nullptr; h->mt.dl_tensor.byte_offset = 0;
+    h->mt.manager_ctx = h; h->mt.deleter = dl_deleter;
+    *out = &h->mt;
+    return PGTG_OK;
+  }
+  return fail(PGTG_ERR_INVALID, std::string("unknown buffer name: ") + name);
+}
+
+extern "C" int pgtg_get_state(pgtg_env* e, pgtg_state* s) {
+  if (!e || !s) return fail(PGTG_ERR_INVALID, "null argument");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  const DevCfg& c = e->dc;
+  const DevPtrs& p = e->dp;
+  size_t N = (size_t)c.N;
+  std::vector<short4> agent(N);
+  std::vector<uint32_t> misc(N), tmp(N);
+  bk_d2h(agent.data(), p.agent, N * sizeof(short4), nullptr);
+  bk_d2h(misc.data(), p.misc, N * 4, nullptr);
+  bk_sync(nullptr);
+  for (size_t i = 0; i < N; i++) {
+    if (s->agent) { s->agent[4 * i] = agent[i].x; s->agent[4 * i + 1] = agent[i].y; s->agent[4 * i + 2] = agent[i].z; s->agent[4 * i + 3] = agent[i].w; }
+    if (s->flat_tire) s->flat_tire[i] = (uint8_t)(misc[i] & 1);
+    if (s->light_counter) s->light_counter[i] = (int32_t)((misc[i] >> 1) & 0x7FFF);
+    if (s->num_cars) s->num_cars[i] = (int32_t)(misc[i] >> 16);
+  }
+  if (s->elapsed) { bk_d2h(tmp.data(), p.elapsed, N * 4, nullptr); bk_sync(nullptr); for (size_t i = 0; i < N; i++) s->elapsed[i] = (int32_t)tmp[i]; }
+  if (s->cars) {
+    size_t MC = (size_t)c.max_cars;
+    std::vector<uint64_t> cars(MC * N);
+    bk_d2h(cars.data(), p.cars, MC * N * 8, nullptr);
+    bk_sync(nullptr);
+    memset(s->cars, 0, sizeof(int32_t) * N * MC * 7);
+    for (size_t i = 0; i < N; i++) {
+      size_t n = misc[i] >> 16;
+      for (size_t k = 0; k < n && k < MC; k++) {
+        Car car = car_unpack(cars[k * N + i]);
+        int32_t* o = s->cars + (i * MC + k) * 7;
+        o[0] = (int32_t)car.id; o[1] = car.x; o[2] = car.y; o[3] = car.route; o[4] = car.profile; o[5] = car.patience; o[6] = car.delay;
+      }
+    }
+  }
+  if (s->tiles || s->used) {
+    std::vector<uint16_t> tiles(N * c.T);
+    bk_d2h(tiles.data(), p.tiles, N * c.T * 2, nullptr);
+    bk_sync(nullptr);
+    for (size_t i = 0; i < N * (size_t)c.T; i++) {
+      if (s->tiles) s->tiles[i] = (uint16_t)(tiles[i] & 0x3FFF);
+      if (s->used) s->used[i] = (uint8_t)((tiles[i] >> 14) & 1);
+    }
+  }
+  if (s->plan) {
+    bk_d2h(tmp.data(), p.plan, N * 4, nullptr);
+    bk_sync(nullptr);
+    for (size_t i = 0; i < N; i++) {
+      int32_t* o = s->plan + 8 * i;
+      unsigned pl = tmp[i];
+      o[0] = plan_sx(pl); o[1] = plan_sy(pl); o[2] = plan_sd(pl); o[3] = plan_gx(pl); o[4] = plan_gy(pl); o[5] = plan_gd(pl); o[6] = plan_ns(pl); o[7] = 0;
+    }
+  }
+  if (s->draw_cursor) {
+    if (p.cursor) { bk_d2h(s->draw_cursor, p.cursor, N * 8, nullptr); bk_sync(nullptr); }
+    else memset(s->draw_cursor, 0, N * 8);
+  }
+  if (s->error) { bk_d2h(s->error, p.error, N * 4, nullptr); bk_sync(nullptr); }
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_set_state(pgtg_env* e, const pgtg_state* s) {
+  // set_to_state (environment.py:1301-1342): position, velocity, flat_tire and cars only
+  if (!e || !s) return fail(PGTG_ERR_INVALID, "null argument");
+  if (!e->did_reset) return fail(PGTG_ERR_STATE, "set_state before reset");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  const DevCfg& c = e->dc;
+  const DevPtrs& p = e->dp;
+  size_t N = (size_t)c.N, MC = (size_t)c.max_cars;
+  if (s->agent) {
+    std::vector<short4> agent(N);
+    for (size_t i = 0; i < N; i++) { agent[i].x = (short)s->agent[4 * i]; agent[i].y = (short)s->agent[4 * i + 1]; agent[i].z = (short)s->agent[4 * i + 2]; agent[i].w = (short)s->agent[4 * i + 3]; }
+    bk_h2d(p.agent, agent.data(), N * sizeof(short4), nullptr);
+  }
+  std::vector<uint32_t> misc(N);
+  bk_d2h(misc.data(), p.misc, N * 4, nullptr);
+  bk_sync(nullptr);
+  if (s->flat_tire) for (size_t i = 0; i < N; i++) misc[i] = (misc[i] & ~1u) | (s->flat_tire[i] ? 1u : 0u);
+  if (s->cars && s->num_cars) {
+    std::vector<uint64_t> cars(MC * N, 0);
+    std::vector<uint32_t> next_id(N);
+    bk_d2h(next_id.data(), p.next_car_id, N * 4, nullptr);
+    bk_sync(nullptr);
+    for (size_t i = 0; i < N; i++) {
+      size_t n = (size_t)s->num_cars[i];
+      if (n > MC) return fail(PGTG_ERR_INVALID, "more cars than max_cars");
+      for (size_t k = 0; k < n; k++) {
+        const int32_t* o = s->cars + (i * MC + k) * 7;
+        Car car; car.id = (unsigned)o[0]; car.x = o[1]; car.y = o[2]; car.route = o[3]; car.profile = o[4]; car.patience = 0; car.delay = 0;
+        cars[k * N + i] = car_pack(car);
+        if (k == n - 1) next_id[i] = (unsigned)o[0] + 1;  // :1340
+      }
+      misc[i] = (misc[i] & 0xFFFFu) | (uint32_t)n << 16;
+    }
+    bk_h2d(p.cars, cars.data(), MC * N * 8, nullptr);
+    bk_h2d(p.next_car_id, next_id.data(), N * 4, nullptr);
+  }
+  bk_h2d(p.misc, misc.data(), N * 4, nullptr);
+  bk_sync(nullptr);
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_stats(pgtg_env* e, double* out8, int reset_after) {
+  if (!e || !out8) return fail(PGTG_ERR_INVALID, "null argument");
+  bk_set_device(e->device);
+  bk_d2h(out8, e->dp.stats, 64, nullptr);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  if (reset_after) { bk_memset(e->dp.stats, 0, 64); bk_sync(nullptr); }
+  return PGTG_OK;
+}
+
+extern "C" int64_t pgtg_launch_count(pgtg_env* e) { return e ? e->launches : 0; }

@@ -1,0 +1,369 @@
+// pgtg_device.cuh -- device-side data layout and per-env logic of the batched PGTG simulator.
+//
+// Design (B200-first):
+//  * env state is structure-of-arrays in HBM; one env per thread for the sequential game logic;
+//  * a map is never materialised as squares: every square feature is a pure function of a 16-bit
+//    tile descriptor + 81-bit LUT bitmaps staged in shared memory;
+//  * done envs are compacted per CTA (ballot + scan) and regenerated on device in the same launch;
+//  * observations leave the SM as one contiguous, 16-byte-vectorised byte stream per CTA, expanded
+//    from a packed bitstring assembled in shared memory.
+//
+// Reference citations are paths under /root/reference/pgtg/.
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+
+// The per-env logic in this header and in pgtg_logic.cuh is written once and compiled twice:
+// by nvcc for sm_100a (the product), and by g++ for tests/emu (a host-side emulation of the same
+// kernel phases used ONLY by the CPU test-suite to debug the logic without a GPU; the product
+// library contains no CPU step path).
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define PG_HD __device__ __forceinline__
+#define PG_HDN __device__ __noinline__
+#define PG_HOSTDEV __host__ __device__ inline
+#define PG_MEMBER __device__
+#define PG_DEVCONST __device__ const
+#define pg_umulhi(a, b) __umulhi((a), (b))
+#define pg_ffs(v) __ffs((int)(v))
+#define pg_popc(v) __popc((unsigned)(v))
+#define pg_popcll(v) __popcll((unsigned long long)(v))
+#define pg_ldg(p) __ldg(p)
+#define pg_dmul(a, b) __dmul_rn((a), (b))
+#define pg_dadd(a, b) __dadd_rn((a), (b))
+#define pg_ddiv(a, b) __ddiv_rn((a), (b))
+#define pg_atomic_or(p, v) atomicOr((p), (v))
+#else
+#include <math.h>
+#include <string.h>
+#define PG_HD static inline
+#define PG_HDN static
+#define PG_HOSTDEV static inline
+#define PG_MEMBER
+#define PG_DEVCONST static const
+static inline uint32_t pg_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+#define pg_ffs(v) __builtin_ffs((int)(v))
+#define pg_popc(v) __builtin_popcount((unsigned)(v))
+#define pg_popcll(v) __builtin_popcountll((unsigned long long)(v))
+#define pg_ldg(p) (*(p))
+// the emulation build uses -ffp-contract=off, so plain operators are correctly rounded, unfused
+#define pg_dmul(a, b) ((a) * (b))
+#define pg_dadd(a, b) ((a) + (b))
+#define pg_ddiv(a, b) ((a) / (b))
+#define pg_atomic_or(p, v) (*(p) |= (v))
+struct short4 { short x, y, z, w; };
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+#endif
+
+#include "../../include/pgtg_b200.h"
+#include "pgtg_tables.h"
+
+namespace pgtg {
+
+constexpr int TILE = 9;
+constexpr int MAX_EDGE_TAB = 4 * PGTG_MAX_TILES;  // directed grid edges
+constexpr int MAX_BORDER_SLOTS = 64;
+
+// tile descriptor (uint16): exits 0-3 | obstacle type 4-6 | mask id 7-10 | subgoal dir 11-13
+// (0 none, 1+dir; on the goal tile 1+goal_dir) | bit 14: subgoal of this tile consumed
+constexpr unsigned TD_USED = 1u << 14;
+PG_HOSTDEV int td_exits(unsigned td) { return td & 15; }
+PG_HOSTDEV int td_otype(unsigned td) { return (td >> 4) & 7; }
+PG_HOSTDEV int td_omask(unsigned td) { return (td >> 7) & 15; }
+PG_HOSTDEV int td_sg(unsigned td) { return (td >> 11) & 7; }
+
+// plan word: sx 0-3 | sy 4-7 | sdir 8-9 | gx 10-13 | gy 14-17 | gdir 18-19 | num_subgoals 20-28
+PG_HOSTDEV unsigned plan_pack(int sx, int sy, int sd, int gx, int gy, int gd, int ns) {
+  return (unsigned)sx | (unsigned)sy << 4 | (unsigned)sd << 8 | (unsigned)gx << 10 | (unsigned)gy << 14 |
+         (unsigned)gd << 18 | (unsigned)ns << 20;
+}
+PG_HOSTDEV int plan_sx(unsigned p) { return p & 15; }
+PG_HOSTDEV int plan_sy(unsigned p) { return (p >> 4) & 15; }
+PG_HOSTDEV int plan_sd(unsigned p) { return (p >> 8) & 3; }
+PG_HOSTDEV int plan_gx(unsigned p) { return (p >> 10) & 15; }
+PG_HOSTDEV int plan_gy(unsigned p) { return (p >> 14) & 15; }
+PG_HOSTDEV int plan_gd(unsigned p) { return (p >> 18) & 3; }
+PG_HOSTDEV int plan_ns(unsigned p) { return (p >> 20) & 511; }
+
+// car record (uint64): x 0-7 | y 8-15 | route 16-20 | profile 21-23 | delay 24-25 |
+// patience 26-39 (saturating) | id 40-63
+constexpr unsigned PATIENCE_MAX = (1u << 14) - 1;
+struct Car {
+  int x, y, route, profile, delay, patience;
+  unsigned id;
+};
+PG_HOSTDEV uint64_t car_pack(const Car& c) {
+  unsigned pat = c.patience > (int)PATIENCE_MAX ? PATIENCE_MAX : (unsigned)c.patience;
+  return (uint64_t)(unsigned)c.x | (uint64_t)(unsigned)c.y << 8 | (uint64_t)c.route << 16 | (uint64_t)c.profile << 21 |
+         (uint64_t)c.delay << 24 | (uint64_t)pat << 26 | (uint64_t)(c.id & 0xFFFFFFu) << 40;
+}
+PG_HOSTDEV Car car_unpack(uint64_t v) {
+  Car c;
+  c.x = (int)(v & 255); c.y = (int)((v >> 8) & 255); c.route = (int)((v >> 16) & 31); c.profile = (int)((v >> 21) & 7);
+  c.delay = (int)((v >> 24) & 3); c.patience = (int)((v >> 26) & PATIENCE_MAX); c.id = (unsigned)(v >> 40);
+  return c;
+}
+PG_HOSTDEV unsigned car_xy(uint64_t v) { return (unsigned)(v & 0xFFFF); }
+
+// Values of the config the kernels read; passed by value as a __grid_constant__ kernel parameter
+// (constant bank, uniform access).
+struct DevCfg {
+  int N, W, H, T, WS, HS;  // envs, tiles, squares
+  int C, P, sliding, window_k, use_nsd;
+  int channel_kind[PGTG_MAX_CHANNELS];
+  int fixed_map, edges_to_keep, n_edge_tab, border_connections, n_border_slots;
+  int start_mode, goal_mode, start_x, start_y, start_dir, goal_x, goal_y, goal_dir, min_sg_dist;
+  double obstacle_probability, obstacle_cdf[4];
+  double sum_subgoals_reward, final_goal_bonus, crash_penalty, light_penalty, standing_penalty, visited_penalty;
+  double ice_p, broken_p, sand_p, traffic_density;
+  int light_green, light_yellow, light_total, ignore_traffic_collisions;
+  double profile_cdf[5], drv_yellow_stop[5], drv_red_violation[5], drv_patience_threshold[5], drv_push_probability[5],
+      drv_speed_multiplier[5], drv_reaction_delay[5];
+  int drv_min_following[5];
+  int separate_reward_cost, num_rules, max_episode_steps, write_final_obs, max_cars, lut_radius;
+  int tile_stride;   // uint16 elements per env in the shared-memory tile stage (odd word count)
+  int vis_w, vis_words;  // visited bitmap geometry (0 when the penalty is off)
+  int obs_bits;      // C * P * P
+  int64_t env_id_base;
+  uint64_t seed;
+};
+
+// Device pointers (all owned by the handle).
+struct DevPtrs {
+  // state, SoA
+  short4* agent;        // [N] x, y, vx, vy
+  uint32_t* misc;       // [N] flat_tire | light_counter << 1 | n_cars << 16
+  uint32_t* elapsed;    // [N]
+  uint32_t* episode;    // [N]
+  uint32_t* next_car_id;  // [N]
+  uint32_t* plan;       // [N]
+  uint16_t* tiles;      // [N][T]
+  uint64_t* cars;       // [2 * max_cars][N], second half = same-tick respawn scratch
+  uint32_t* visited;    // [vis_words][N] or null
+  uint64_t* key;        // [N] philox key (the env's seed)
+  int64_t* cursor;      // [N] tape cursor
+  int64_t* tape_end;    // [N]
+  const double* tape_values;
+  const uint8_t* tape_tags;
+  uint32_t* error;      // [N] sticky
+  double* ep_return;    // [N]
+  // tables
+  const uint16_t* fixed_tiles;  // [T] (fixed map)
+  uint32_t fixed_plan;
+  const uint16_t* edge_tab;     // [n_edge_tab] a | b << 8  (edges() order)
+  const uint16_t* edge_rev;     // [n_edge_tab] index of the reverse edge
+  const uint16_t* border_slots; // [n_border_slots] tile | dir << 8
+  const uint8_t* dirlut;        // (2R+1)^2
+  const pgtg_rule* rules;
+  // outputs
+  int8_t* obs_map; int32_t* obs_position; int32_t* obs_velocity; int32_t* obs_nsd;
+  double* reward; double* cost; uint8_t* terminated; uint8_t* truncated;
+  int32_t* step_state; uint8_t* step_flags;
+  int8_t* f_obs_map; int32_t* f_obs_position; int32_t* f_obs_velocity; int32_t* f_obs_nsd;
+  double* stats;
+};
+
+// ---------------------------------------------------------------------------------------------
+// LUTs (generated from the reference's tile data by tools/gen_tables.py), staged in shared memory
+struct Lut {
+  uint32_t wall[16][3];
+  uint32_t exit_line[4][3];
+  uint32_t mask[PGTG_NUM_MASKS][3];
+  uint32_t lane_any[16][3];
+  uint8_t native_spawner[16];
+  uint8_t entry_sq[4];
+  uint32_t spawner_cols;  // local columns that can hold a car_spawner (derived when staging)
+};
+struct LutInit { uint32_t wall[16][3], exit_line[4][3], mask[PGTG_NUM_MASKS][3], lane_any[16][3]; uint8_t native_spawner[16], entry_sq[4]; };
+PG_DEVCONST LutInit g_lut = {PGTG_TAB_WALL, PGTG_TAB_EXIT_LINE, PGTG_TAB_MASK, PGTG_TAB_LANE_ANY, PGTG_TAB_NATIVE_SPAWNER, PGTG_TAB_ENTRY_SQ};
+PG_DEVCONST uint64_t g_lane_desc[16][81] = PGTG_TAB_LANE_DESC;
+
+PG_HD bool bit81(const uint32_t* w, int sq) { return (w[sq >> 5] >> (sq & 31)) & 1u; }
+PG_HD uint64_t lane_desc(int type, int sq) { return pg_ldg(&g_lane_desc[type][sq]); }
+PG_HD int ld_all(uint64_t d) { return (int)(d & 7); }          // 0 none, 1 + dir
+PG_HD int ld_n(uint64_t d) { return (int)((d >> 3) & 7); }
+PG_HD int ld_route(uint64_t d, int i) { return (int)((d >> (6 + 7 * i)) & 31); }
+PG_HD int ld_dir(uint64_t d, int i) { return (int)((d >> (11 + 7 * i)) & 3); }
+
+// square feature bits
+enum : unsigned { SF_WALL = 1, SF_SUBGOAL = 2, SF_USED = 4, SF_START = 8, SF_FINAL = 16, SF_ICE = 32, SF_BROKEN = 64, SF_SAND = 128, SF_LIGHT = 256 };
+
+// ---------------------------------------------------------------------------------------------
+// Per-env working set. Lives in registers of the thread that currently works on the env and is
+// parked in shared memory between the step, reset and observe phases (a different thread of the
+// CTA may run the reset of a done env after compaction).
+struct EnvRegs {
+  int x, y, vx, vy;
+  uint32_t misc;  // flat | light << 1 | ncars << 16
+  uint32_t elapsed, episode, next_car_id, plan;
+  uint32_t err;
+  int64_t cursor;
+  uint32_t flags;  // bit0 tiles dirty, bit1 done, bit2 plan dirty
+};
+constexpr uint32_t EF_TILES_DIRTY = 1, EF_DONE = 2, EF_RESET = 4;
+
+PG_HD int misc_flat(uint32_t m) { return m & 1; }
+PG_HD int misc_light(uint32_t m) { return (m >> 1) & 0x7FFF; }
+PG_HD int misc_ncars(uint32_t m) { return m >> 16; }
+PG_HD uint32_t misc_pack(int flat, int light, int ncars) { return (uint32_t)flat | (uint32_t)light << 1 | (uint32_t)ncars << 16; }
+
+// ---------------------------------------------------------------------------------------------
+// Random draws (semantic API shared with the oracle, include/pgtg_b200.h):
+//   tape   : draws recorded from the reference's five np_random children (environment.py:593-599)
+//   philox : Philox4x32-10, key = env seed, counter = (k, tick, episode, stream)
+PG_HD void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = pg_umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = pg_umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+template <int RNG>
+struct Rng {
+  const DevPtrs& p;
+  EnvRegs& e;
+  int env;
+  uint32_t k0, k1;
+  uint32_t kcount[5];
+  PG_MEMBER Rng(const DevPtrs& p_, EnvRegs& e_, int env_) : p(p_), e(e_), env(env_) {
+    if (RNG == PGTG_RNG_PHILOX) {
+      uint64_t key = p.key[env];
+      k0 = (uint32_t)key; k1 = (uint32_t)(key >> 32);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) kcount[i] = 0;
+  }
+  PG_MEMBER void block(int stream, uint32_t& w0, uint32_t& w1) {
+    uint32_t c0 = kcount[stream]++, c1 = e.elapsed, c2 = e.episode, c3 = (uint32_t)stream;
+    philox4x32_10(c0, c1, c2, c3, k0, k1);
+    w0 = c0; w1 = c1;
+  }
+  PG_MEMBER double tape_next(int stream, int kind) {
+    if (e.cursor >= p.tape_end[env]) { e.err |= 1; return 0.0; }
+    if (p.tape_tags[e.cursor] != (uint8_t)(stream * 8 + kind)) e.err |= 2;
+    return p.tape_values[e.cursor++];
+  }
+  // Generator.random()
+  PG_MEMBER double uniform(int stream) {
+    if (RNG == PGTG_RNG_TAPE) return tape_next(stream, PGTG_DRAW_DOUBLE);
+    uint32_t w0, w1;
+    block(stream, w0, w1);
+    return pg_ddiv(pg_dadd(pg_dmul((double)(w0 >> 5), 67108864.0), (double)(w1 >> 6)), 9007199254740992.0);
+  }
+  // Generator.integers(0, n) / choice over n items; nothing is consumed for n == 1
+  PG_MEMBER int index(int stream, int n) {
+    if (n <= 1) return 0;
+    if (RNG == PGTG_RNG_TAPE) {
+      int v = (int)tape_next(stream, PGTG_DRAW_INDEX);
+      if (v < 0 || v >= n) { e.err |= 4; v = 0; }
+      return v;
+    }
+    uint32_t w0, w1;
+    block(stream, w0, w1);
+    return (int)pg_umulhi(w0, (uint32_t)n);
+  }
+  // Generator.choice(items, p=...): cdf.searchsorted(u, side="right")
+  PG_MEMBER int choice_cdf(int stream, const double* cdf, int n) {
+    if (RNG == PGTG_RNG_TAPE) {
+      int v = (int)tape_next(stream, PGTG_DRAW_INDEX);
+      if (v < 0 || v >= n) { e.err |= 4; v = 0; }
+      return v;
+    }
+    double u = uniform(stream);
+    int i = 0;
+    while (i < n - 1 && cdf[i] <= u) i++;
+    return i;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Map queries on the packed representation.
+struct MapView {
+  const DevCfg& c;
+  const Lut& L;
+  uint16_t* tiles;  // shared memory, this env's T descriptors
+  uint32_t plan;
+  PG_MEMBER bool inside(int x, int y) const { return !(x < 0 || y < 0 || x >= c.WS || y >= c.HS); }  // map.py:44-47
+  PG_MEMBER int start_tile() const { return plan_sy(plan) * c.W + plan_sx(plan); }
+  PG_MEMBER int goal_tile() const { return plan_gy(plan) * c.W + plan_gx(plan); }
+
+  // Which exit lines of tile t carry a goal-ish label (parser.py:55-77, applied in that order):
+  // returns per-direction label codes packed 4 bits each: 0 none, 1 subgoal, 2 used, 3 start, 4 final
+  PG_MEMBER unsigned line_labels(int t, unsigned td) const {
+    unsigned lab = 0;
+    int ex = td_exits(td), sg = td_sg(td), gt = goal_tile();
+    if (sg && t != gt && ((ex >> (sg - 1)) & 1)) lab |= ((td & TD_USED) ? 2u : 1u) << (4 * (sg - 1));
+    if (t == start_tile()) { int d = plan_sd(plan); if (((ex >> d) & 1) && !((lab >> (4 * d)) & 15)) lab |= 3u << (4 * d); }
+    if (t == gt) { int d = plan_gd(plan); if (((ex >> d) & 1) && !((lab >> (4 * d)) & 15)) lab |= 4u << (4 * d); }
+    return lab;
+  }
+  // features of one square inside the map (the reference's set[str], parser.py:44-155)
+  PG_MEMBER unsigned features(int x, int y) const {
+    int tx = x / TILE, ty = y / TILE, sq = (x - tx * TILE) * TILE + (y - ty * TILE), t = ty * c.W + tx;
+    unsigned td = tiles[t];
+    int ex = td_exits(td);
+    if (bit81(L.wall[ex], sq)) return SF_WALL;
+    unsigned f = 0;
+    int ot = td_otype(td);
+    if (ot && bit81(L.mask[td_omask(td)], sq)) f |= (SF_ICE >> 1) << ot;  // 1 ice .. 4 light
+    if (td_sg(td) || t == start_tile()) {
+      unsigned lab = line_labels(t, td);
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        unsigned l = (lab >> (4 * d)) & 15;
+        if (l && bit81(L.exit_line[d], sq)) f |= (l == 1 ? SF_SUBGOAL : l == 2 ? SF_USED : l == 3 ? SF_START : SF_FINAL);
+      }
+    }
+    return f;
+  }
+  PG_MEMBER int tile_type_at(int x, int y) const { return td_exits(tiles[(y / TILE) * c.W + x / TILE]); }
+  PG_MEMBER int local_sq(int x, int y) const { return (x % TILE) * TILE + (y % TILE); }
+  PG_MEMBER bool light_at(int x, int y) const {
+    int tx = x / TILE, ty = y / TILE, sq = (x - tx * TILE) * TILE + (y - ty * TILE);
+    unsigned td = tiles[ty * c.W + tx];
+    return td_otype(td) == 4 && bit81(L.mask[td_omask(td)], sq) && !bit81(L.wall[td_exits(td)], sq);
+  }
+  // set_subgoals_to_used (map.py:143-171): the flood covers exactly the tile's 3-square exit line
+  PG_MEMBER void consume_subgoal(int x, int y) { tiles[(y / TILE) * c.W + x / TILE] |= TD_USED; }
+
+  // nearest remaining subgoal / final-goal square: first strict minimum of the Manhattan distance
+  // in the x-major scan (environment.py:1047-1053, 1474-1480) == lexicographic min of (d, x, y)
+  PG_MEMBER bool nearest_goal(int px, int py, int& gx, int& gy) const {
+    int best = 0x7fffffff, bx = 0, by = 0;
+    int gt = goal_tile();
+    for (int t = 0; t < c.T; t++) {
+      unsigned td = tiles[t];
+      int sg = td_sg(td);
+      if (!sg) continue;
+      int d;
+      if (t == gt) { d = plan_gd(plan); if (!((td_exits(td) >> d) & 1)) continue; }
+      else { if (td & TD_USED) continue; d = sg - 1; }
+      // claimed earlier by start? (only possible on degenerate fixed maps) -- labels decide
+      unsigned lab = (line_labels(t, td) >> (4 * d)) & 15;
+      if (lab != 1 && lab != 4) continue;
+      int ox = (t % c.W) * TILE, oy = (t / c.W) * TILE;
+      // the 3 squares of exit line d, taken from the LUT (north (3..5,0) east (8,3..5) ...)
+#pragma unroll
+      for (int w = 0; w < 3; w++) {
+        uint32_t bits = L.exit_line[d][w];
+        while (bits) {
+          int sq = w * 32 + pg_ffs(bits) - 1;
+          bits &= bits - 1;
+          int X = ox + sq / TILE, Y = oy + sq % TILE;
+          int dist = abs(X - px) + abs(Y - py);
+          if (dist < best || (dist == best && (X < bx || (X == bx && Y < by)))) { best = dist; bx = X; by = Y; }
+        }
+      }
+    }
+    gx = bx; gy = by;
+    return best != 0x7fffffff;
+  }
+};
+
+}  // namespace pgtg

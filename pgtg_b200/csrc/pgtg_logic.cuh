@@ -1,0 +1,747 @@
+// pgtg_logic.cuh -- the per-env game logic: one tick, one reset (incl. procedural map generation),
+// and the observation planes, all on the packed tile-descriptor representation.
+// Compiled by nvcc into the kernels of pgtg_kernels.cu (and by g++ into tests/emu, see
+// pgtg_device.cuh). Reference citations are paths under /root/reference/pgtg/.
+#pragma once
+#include "pgtg_device.cuh"
+
+namespace pgtg {
+
+PG_HD uint64_t& car_slot(const DevCfg& c, const DevPtrs& p, int env, int slot) { return p.cars[(size_t)slot * c.N + env]; }
+
+PG_HD int light_phase(const DevCfg& c, int counter) {  // environment.py:1004-1015: 0 green 1 yellow 2 red
+  return counter < c.light_green ? 0 : (counter < c.light_green + c.light_yellow ? 1 : 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// car spawners: squares carrying "car_spawner", enumerated in the x-major order of
+// EpisodeMap.__init__ (map.py:31-42) without materialising the list.
+PG_HD void spawner_bits(const DevCfg& c, const Lut& L, int ex, int tx, int ty, uint32_t out[3]) {
+  out[0] = out[1] = out[2] = 0;
+  if (ex == 0) return;  // no lanes on wall-only tiles (parser.py:113-118)
+  int ns = L.native_spawner[ex];
+  if (ns != 255) out[ns >> 5] |= 1u << (ns & 31);
+  // border tiles: tile-entry squares 'car_lane all <inward>' (parser.py:120-148)
+  if (tx == 0) { int sq = L.entry_sq[3]; if (ld_all(lane_desc(ex, sq)) == 4) out[sq >> 5] |= 1u << (sq & 31); }
+  if (tx == c.W - 1) { int sq = L.entry_sq[2]; if (ld_all(lane_desc(ex, sq)) == 3) out[sq >> 5] |= 1u << (sq & 31); }
+  if (ty == 0) { int sq = L.entry_sq[1]; if (ld_all(lane_desc(ex, sq)) == 2) out[sq >> 5] |= 1u << (sq & 31); }
+  if (ty == c.H - 1) { int sq = L.entry_sq[0]; if (ld_all(lane_desc(ex, sq)) == 1) out[sq >> 5] |= 1u << (sq & 31); }
+}
+PG_HD uint32_t col9(const uint32_t w[3], int lx) {  // the 9 bits of local column lx
+  int b = lx * TILE, wi = b >> 5, sh = b & 31;
+  uint32_t v = w[wi] >> sh;
+  if (sh > 23 && wi < 2) v |= w[wi + 1] << (32 - sh);
+  return v & 0x1FFu;
+}
+// find == -1: count; else: coordinates of the find-th spawner
+PG_HDN int spawner_scan(const DevCfg& c, const MapView& m, int find, int& ox, int& oy) {
+  int n = 0;
+  for (int tx = 0; tx < c.W; tx++)
+    for (int lx = 0; lx < TILE; lx++) {
+      if (!((m.L.spawner_cols >> lx) & 1)) continue;
+      for (int ty = 0; ty < c.H; ty++) {
+        uint32_t sb[3];
+        spawner_bits(c, m.L, td_exits(m.tiles[ty * c.W + tx]), tx, ty, sb);
+        uint32_t col = col9(sb, lx);
+        int cnt = pg_popc(col);
+        if (find >= 0 && find < n + cnt) {
+          int k = find - n;
+          while (k--) col &= col - 1;
+          ox = tx * TILE + lx; oy = ty * TILE + pg_ffs(col) - 1;
+          return n + cnt;
+        }
+        n += cnt;
+      }
+    }
+  return n;
+}
+
+// the idx-th square with any car lane, x-major (traffic_spawnable_positions, map.py:35-38)
+PG_HDN void spawnable_at(const DevCfg& c, const MapView& m, int idx, int& ox, int& oy) {
+  for (int tx = 0; tx < c.W; tx++)
+    for (int lx = 0; lx < TILE; lx++)
+      for (int ty = 0; ty < c.H; ty++) {
+        uint32_t col = col9(m.L.lane_any[td_exits(m.tiles[ty * c.W + tx])], lx);
+        int cnt = pg_popc(col);
+        if (idx < cnt) {
+          while (idx--) col &= col - 1;
+          ox = tx * TILE + lx; oy = ty * TILE + pg_ffs(col) - 1;
+          return;
+        }
+        idx -= cnt;
+      }
+  ox = oy = 0;
+}
+PG_HD int spawnable_count(const DevCfg& c, const MapView& m) {
+  int n = 0;
+  for (int t = 0; t < c.T; t++) {
+    const uint32_t* w = m.L.lane_any[td_exits(m.tiles[t])];
+    n += pg_popc(w[0]) + pg_popc(w[1]) + pg_popc(w[2]);
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// traffic (environment.py:658-691, 830-1002, 1121-1127)
+template <int RNG>
+PG_HD int random_route_at(const MapView& m, Rng<RNG>& rng, EnvRegs& e, int x, int y) {
+  uint64_t d = lane_desc(m.tile_type_at(x, y), m.local_sq(x, y));
+  int n = ld_n(d);
+  if (n == 0) { e.err |= 16; return 0; }
+  return ld_route(d, rng.index(PGTG_STREAM_CAR, n));  // sorted route names, car_rng.choice (:861-874)
+}
+
+template <int RNG>
+PG_HD bool any_car_at(const DevCfg& c, const DevPtrs& p, int env, unsigned xy, int lo, int hi) {
+  for (int k = lo; k < hi; k++)
+    if (car_xy(car_slot(c, p, env, k)) == xy) return true;
+  return false;
+}
+
+// one car tick; returns false when the car leaves the map (None at environment.py:968)
+template <int RNG>
+PG_HDN bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env, Car& car,
+                     int r, int w, int n, int s) {
+  // _should_car_move (:678-691)
+  bool move;
+  if (car.delay > 0) { car.delay--; move = false; }
+  else if (rng.uniform(PGTG_STREAM_CAR) < c.drv_reaction_delay[car.profile]) { car.delay = 1 + rng.index(PGTG_STREAM_CAR, 3); move = false; }
+  else move = rng.uniform(PGTG_STREAM_CAR) < c.drv_speed_multiplier[car.profile];
+  if (!move) { car.patience++; return true; }
+#pragma unroll 1
+  for (int d = 0; d < 4; d++) {  // up, down, left, right (:891-902)
+    int px = car.x + (d == 2 ? -1 : d == 3 ? 1 : 0), py = car.y + (d == 0 ? -1 : d == 1 ? 1 : 0);
+    if (!m.inside(px, py)) continue;
+    uint64_t ld = lane_desc(m.tile_type_at(px, py), m.local_sq(px, py));
+    if (ld == 0) continue;
+    if (ld_all(ld) == d + 1) {  // entering a new tile: uniform new route (:915-928)
+      car.patience = 0;
+      car.route = ld_route(ld, rng.index(PGTG_STREAM_CAR, ld_n(ld)));
+      car.x = px; car.y = py;
+      return true;
+    }
+    int nl = ld_n(ld);
+    for (int i = 0; i < nl; i++) {
+      if (ld_route(ld, i) != car.route || ld_dir(ld, i) != d) continue;  // :932
+      if (m.light_at(px, py)) {  // :934-942
+        int phase = light_phase(c, misc_light(e.misc));
+        bool stop = false;
+        if (phase == 1) stop = rng.uniform(PGTG_STREAM_CAR) < c.drv_yellow_stop[car.profile];
+        else if (phase == 2) stop = rng.uniform(PGTG_STREAM_CAR) >= c.drv_red_violation[car.profile];
+        if (stop) { car.patience++; return true; }
+      }
+      // cars_on_next_position over the live list: survivors [0,w), not-yet-moved (r,n), and the
+      // replacements spawned earlier this tick (scratch half) (:944-948)
+      unsigned xy = (unsigned)px | (unsigned)py << 8;
+      bool blocked = any_car_at<RNG>(c, p, env, xy, 0, w) || any_car_at<RNG>(c, p, env, xy, r + 1, n) ||
+                     any_car_at<RNG>(c, p, env, xy, c.max_cars, c.max_cars + s);
+      if (blocked) {  // :950-962
+        if (c.drv_min_following[car.profile] == 0 || (double)car.patience > c.drv_patience_threshold[car.profile]) {
+          if (rng.uniform(PGTG_STREAM_CAR) < c.drv_push_probability[car.profile]) { car.patience = 0; car.x = px; car.y = py; return true; }
+        }
+        car.patience++;
+        return true;
+      }
+      car.patience = 0; car.x = px; car.y = py;  // :964-965
+      return true;
+    }
+  }
+  car.patience++;
+  return false;
+}
+
+template <int RNG>
+PG_HD void advance_cars(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env) {
+  // environment.py:1121-1127. Order-stable in place: survivors are compacted to [0,w), replacements
+  // are parked in the scratch half in spawn order and appended afterwards (w + s == n).
+  int n = misc_ncars(e.misc), w = 0, s = 0;
+  for (int r = 0; r < n; r++) {
+    Car car = car_unpack(car_slot(c, p, env, r));
+    if (car_next<RNG>(c, p, m, e, rng, env, car, r, w, n, s)) {
+      car_slot(c, p, env, w++) = car_pack(car);
+    } else {  // _spawn_new_car (:970-1002)
+      int sx = 0, sy = 0;
+      int ns = spawner_scan(c, m, -1, sx, sy);
+      if (ns > 0) spawner_scan(c, m, rng.index(PGTG_STREAM_CAR, ns), sx, sy);
+      Car nc;
+      nc.profile = rng.choice_cdf(PGTG_STREAM_CAR, c.profile_cdf, PGTG_NUM_PROFILES);
+      nc.route = random_route_at<RNG>(m, rng, e, sx, sy);
+      nc.id = e.next_car_id++;
+      nc.x = sx; nc.y = sy; nc.patience = 0; nc.delay = 0;
+      car_slot(c, p, env, c.max_cars + s++) = car_pack(nc);
+    }
+  }
+  for (int i = 0; i < s; i++) car_slot(c, p, env, w + i) = car_slot(c, p, env, c.max_cars + i);
+}
+
+template <int RNG>
+PG_HD void create_initial_traffic(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env) {
+  // _create_initial_traffic (environment.py:830-879)
+  int num_positions = spawnable_count(c, m);
+  int num_cars = (int)((double)num_positions * c.traffic_density);
+  if (num_cars > num_positions) num_cars = num_positions;
+  if (num_cars <= 0) return;
+  if (num_cars > c.max_cars) { e.err |= 32; num_cars = c.max_cars; }
+  // car_rng.choice(n, size=k, replace=False): k distinct indices, kept raw in the car slots first
+  for (int j = 0; j < num_cars; j++) {
+    int v;
+    if (RNG == PGTG_RNG_TAPE) {
+      v = (int)rng.tape_next(PGTG_STREAM_CAR, PGTG_DRAW_INDEX);
+      if (v < 0 || v >= num_positions) { e.err |= 4; v = 0; }
+    } else {
+      for (;;) {  // sequential rejection sampling (spec shared with the oracle)
+        uint32_t w0, w1;
+        rng.block(PGTG_STREAM_CAR, w0, w1);
+        v = (int)pg_umulhi(w0, (uint32_t)num_positions);
+        bool dup = false;
+        for (int q = 0; q < j; q++) if ((int)car_slot(c, p, env, q) == v) { dup = true; break; }
+        if (!dup) break;
+      }
+    }
+    car_slot(c, p, env, j) = (uint64_t)(uint32_t)v;
+  }
+  for (int j = 0; j < num_cars; j++) {
+    int x, y;
+    spawnable_at(c, m, (int)car_slot(c, p, env, j), x, y);
+    Car car;
+    car.profile = rng.choice_cdf(PGTG_STREAM_CAR, c.profile_cdf, PGTG_NUM_PROFILES);
+    car.route = random_route_at<RNG>(m, rng, e, x, y);
+    car.id = e.next_car_id++;
+    car.x = x; car.y = y; car.patience = 0; car.delay = 0;
+    car_slot(c, p, env, j) = car_pack(car);
+  }
+  e.misc = misc_pack(misc_flat(e.misc), misc_light(e.misc), num_cars);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rule engine (environment.py:162-294)
+PG_HD int floordiv9(int a) { return a >= 0 ? a / TILE : -((-a + TILE - 1) / TILE); }
+
+PG_HDN int agent_direction(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e) {
+  // get_agent_direction (:185-206) over _get_subgoal_compass_directions (:1037-1090)
+  int gx, gy;
+  if (m.nearest_goal(e.x, e.y, gx, gy)) {
+    int dx = gx - e.x, dy = gy - e.y;
+    if (!(abs(dx) <= c.window_k && abs(dy) <= c.window_k)) {
+      int R = c.lut_radius;
+      int o = pg_ldg(&p.dirlut[(dy + R) * (2 * R + 1) + (dx + R)]) & 7;  // host-evaluated atan2 sector
+      return o >> 1;  // N,NE -> s2n; E,SE -> w2e; S,SW -> n2s; W,NW -> e2w
+    }
+  }
+  return (e.vx == 0 && e.vy == 0) ? PGTG_AGENT_STATIONARY : PGTG_AGENT_NEAR_GOAL;  // norm < 0.1
+}
+
+PG_HDN bool apply_braking(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env) {
+  // apply_braking / evaluate_rule (:226-294)
+  int n = misc_ncars(e.misc);
+  if (n == 0 || c.num_rules == 0) {
+    // min_traffic <= 0 rules could still fire without cars; handled below when rules ask for it
+    bool any0 = false;
+    for (int i = 0; i < c.num_rules; i++) any0 |= p.rules[i].min_traffic <= 0 && p.rules[i].min_matching_traffic <= 0;
+    if (!any0) return false;
+  }
+  int tx = floordiv9(e.x), ty = floordiv9(e.y);
+  tx = tx < 0 ? 0 : (tx > c.W - 1 ? c.W - 1 : tx);
+  ty = ty < 0 ? 0 : (ty > c.H - 1 ? c.H - 1 : ty);
+  int type = td_exits(m.tiles[ty * c.W + tx]);
+  double speed = sqrt((double)(e.vx * e.vx + e.vy * e.vy));
+  int adir = -1;
+  for (int i = 0; i < c.num_rules; i++) {
+    const pgtg_rule& rule = p.rules[i];
+    if (type != rule.tile_type) continue;
+    if (!(rule.vel_lo <= speed && speed <= rule.vel_hi)) continue;
+    int in_tile = 0;
+    for (int k = 0; k < n; k++) {
+      unsigned xy = car_xy(car_slot(c, p, env, k));
+      if ((int)(xy & 255) / TILE == tx && (int)(xy >> 8) / TILE == ty) in_tile++;
+    }
+    if (in_tile < rule.min_traffic) continue;
+    if (adir < 0) adir = agent_direction(c, p, m, e);
+    int matching = 0;
+    for (int k = 0; k < n; k++) {
+      uint64_t cv = car_slot(c, p, env, k);
+      unsigned xy = car_xy(cv);
+      if ((int)(xy & 255) / TILE == tx && (int)(xy >> 8) / TILE == ty) matching += rule.weight[adir][(cv >> 16) & 31];
+    }
+    if (matching >= rule.min_matching_traffic) return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one tick (environment.py:1092-1281)
+struct StepResult {
+  double reward, cost;
+  int terminated, braking, outcome;  // outcome: 0 running, 1 crash, 2 final goal (3 truncated, set by phase_step)
+  double ep_return;                  // return of the episode that just finished (phase_step)
+};
+
+PG_HD bool visited_test_set(const DevCfg& c, const DevPtrs& p, int env, int x, int y, bool set) {
+  int idx = (x + 1) * c.vis_w + (y + 1);
+  uint32_t& w = p.visited[(size_t)(idx >> 5) * c.N + env];
+  bool was = (w >> (idx & 31)) & 1u;
+  if (set) w |= 1u << (idx & 31);
+  return was;
+}
+
+template <int RNG>
+PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env, int action) {
+  Rng<RNG> rng(p, e, env);
+  StepResult r;
+  r.reward = 0; r.cost = 0; r.terminated = 0; r.braking = 0; r.outcome = 0;
+  double perf = 0;
+  e.elapsed++;
+  int light = (misc_light(e.misc) + 1) % c.light_total;  // :1113-1115
+  e.misc = misc_pack(misc_flat(e.misc), light, misc_ncars(e.misc));
+  int ax = action / 3 - 1, ay = action % 3 - 1;  // constants.py:6-16
+  int n_cars = misc_ncars(e.misc);
+  if (n_cars > 0) advance_cars<RNG>(c, p, m, e, rng, env);  // :1121-1127
+  int cx = e.x, cy = e.y;
+  e.vx += ax; e.vy += ay;  // :1139
+  if (apply_braking(c, p, m, e, env)) { r.braking = 1; e.vx = 0; e.vy = 0; }  // :1145
+
+  // _decompose_velocity (:693-748), produced lazily one unit sub-step at a time; the float64
+  // rounding of _round(i * m) is reproduced with explicitly unfused IEEE operations
+  int dx = e.vx, dy = e.vy;
+  int adx = abs(dx), ady = abs(dy);
+  int n_sub = adx > ady ? adx : ady;
+  int sgx = (dx > 0) - (dx < 0), sgy = (dy > 0) - (dy < 0);
+  double slope = 0.0;
+  if (dx != 0 && dy != 0) slope = adx >= ady ? pg_ddiv((double)dy, (double)adx) : pg_ddiv((double)dx, (double)ady);
+  int pxp = 0, pyp = 0;
+  bool red = light_phase(c, light) == 2;
+  int flat = misc_flat(e.misc);
+  for (int i = 1; i <= n_sub + 1; i++) {
+    int sx = 0, sy = 0;
+    bool has_part = i <= n_sub;
+    if (has_part) {
+      int px, py;
+      if (dx == 0) { px = 0; py = i * sgy; }
+      else if (dy == 0) { px = i * sgx; py = 0; }
+      else if (adx >= ady) { px = i * sgx; py = (int)floor(pg_dadd(pg_dmul((double)i, slope), 0.5)); }
+      else { py = i * sgy; px = (int)floor(pg_dadd(pg_dmul((double)i, slope), 0.5)); }
+      sx = px - pxp; sy = py - pyp; pxp = px; pyp = py;
+    }
+    // crash: off-map, wall, or a car on the square (:1158-1171)
+    bool inside = m.inside(cx, cy);
+    unsigned f = inside ? m.features(cx, cy) : (unsigned)SF_WALL;
+    bool crash = !inside || (f & SF_WALL);
+    if (!crash && !c.ignore_traffic_collisions && n_cars > 0)
+      crash = any_car_at<RNG>(c, p, env, (unsigned)cx | (unsigned)cy << 8, 0, n_cars);
+    if (crash) {
+      if (c.separate_reward_cost) r.cost += c.crash_penalty; else r.reward -= c.crash_penalty;
+      r.terminated = 1; r.outcome = 1;
+      break;
+    }
+    if (f & SF_FINAL) {  // :1174-1180
+      double isr = c.sum_subgoals_reward / (double)plan_ns(e.plan);  // :631-633
+      if (c.separate_reward_cost) perf += isr + c.final_goal_bonus; else r.reward += isr + c.final_goal_bonus;
+      r.terminated = 1; r.outcome = 2;
+      break;
+    }
+    if (f & SF_SUBGOAL) {  // :1183-1188
+      double isr = c.sum_subgoals_reward / (double)plan_ns(e.plan);
+      if (c.separate_reward_cost) perf += isr; else r.reward += isr;
+      m.consume_subgoal(cx, cy);
+      e.flags |= EF_TILES_DIRTY;
+    }
+    if (!has_part) continue;  // :1191-1192
+    int nx = cx + sx, ny = cy + sy;  // red light on the NEXT square, before ice (:1195-1202)
+    if (red && m.inside(nx, ny) && m.light_at(nx, ny)) {
+      if (c.separate_reward_cost) r.cost += c.light_penalty; else r.reward -= c.light_penalty;
+    }
+    if ((f & SF_ICE) && rng.uniform(PGTG_STREAM_ICE) < c.ice_p) {  // :1205-1213
+      int ia = rng.index(PGTG_STREAM_ICE, 9);
+      sx = ia / 3 - 1; sy = ia % 3 - 1;
+    }
+    if ((f & SF_BROKEN) && rng.uniform(PGTG_STREAM_BROKEN) < c.broken_p) flat = 1;  // :1216-1223
+    if ((f & SF_SAND) && rng.uniform(PGTG_STREAM_SAND) < c.sand_p) {  // :1226-1234
+      cx += sx; cy += sy; e.vx = 0; e.vy = 0;
+      break;
+    }
+    cx += sx; cy += sy;  // :1236
+  }
+  if (flat) { e.vx = 0; e.vy = 0; }  // :1240-1241
+  e.misc = misc_pack(flat, light, misc_ncars(e.misc));
+  if (c.vis_words) {  // :1244-1255
+    bool was = visited_test_set(c, p, env, cx, cy, true);
+    if (was && !(ax == 0 && ay == 0)) {
+      if (c.separate_reward_cost) r.cost += c.visited_penalty; else r.reward -= c.visited_penalty;
+    }
+  }
+  if (c.standing_penalty != 0 && ax == 0 && ay == 0 && e.x == cx && e.y == cy) {  // :1257-1263
+    if (c.separate_reward_cost) r.cost += c.standing_penalty; else r.reward -= c.standing_penalty;
+  }
+  e.x = cx; e.y = cy;
+  if (c.separate_reward_cost) r.reward = perf;  // :1271-1281
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// procedural map generation (map_generator.py:43-472) on bitboards
+struct Board {
+  uint64_t w[4];
+};
+PG_HD bool bget(const Board& b, int i) { return (b.w[i >> 6] >> (i & 63)) & 1ull; }
+PG_HD void bset(Board& b, int i) { b.w[i >> 6] |= 1ull << (i & 63); }
+PG_HD void bclr(Board& b, int i) { b.w[i >> 6] &= ~(1ull << (i & 63)); }
+
+// start/goal connectivity of the grid graph; E bit i: edge i<->i+1, S bit i: edge i<->i+W
+PG_HDN bool grid_connected(const DevCfg& c, const Board& E, const Board& S, int s, int g) {
+  if (s == g) return true;
+  if (c.T <= 64) {
+    uint64_t e = E.w[0], so = S.w[0], reach = 1ull << s, goal = 1ull << g;
+    for (;;) {
+      uint64_t nx = reach | ((reach & e) << 1) | ((reach >> 1) & e) | ((reach & so) << c.W) | ((reach >> c.W) & so);
+      if (nx & goal) return true;
+      if (nx == reach) return false;
+      reach = nx;
+    }
+  }
+  Board seen; seen.w[0] = seen.w[1] = seen.w[2] = seen.w[3] = 0;
+  uint8_t q[PGTG_MAX_TILES];
+  int qh = 0, qt = 0;
+  bset(seen, s); q[qt++] = (uint8_t)s;
+  while (qh < qt) {
+    int n = q[qh++];
+    if (n == g) return true;
+    int x = n % c.W;
+    int cand[4] = {n - c.W, n + 1, n + c.W, n - 1};
+    bool ok[4] = {n >= c.W && bget(S, n - c.W), x < c.W - 1 && bget(E, n), n + c.W < c.T && bget(S, n), x > 0 && bget(E, n - 1)};
+    for (int k = 0; k < 4; k++)
+      if (ok[k] && !bget(seen, cand[k])) { bset(seen, cand[k]); q[qt++] = (uint8_t)cand[k]; }
+  }
+  return false;
+}
+
+template <int RNG>
+PG_HD void random_border_position(const DevCfg& c, Rng<RNG>& rng, int& x, int& y) {
+  // chose_random_start_or_goal_position (map_generator.py:600-626)
+  switch (rng.index(PGTG_STREAM_MAP, 4)) {
+    case 0: x = rng.index(PGTG_STREAM_MAP, c.W); y = 0; break;
+    case 1: x = c.W - 1; y = rng.index(PGTG_STREAM_MAP, c.H); break;
+    case 2: x = rng.index(PGTG_STREAM_MAP, c.W); y = c.H - 1; break;
+    default: x = 0; y = rng.index(PGTG_STREAM_MAP, c.H); break;
+  }
+}
+template <int RNG>
+PG_HD int random_direction(const DevCfg& c, Rng<RNG>& rng, int x, int y) {
+  // chose_random_start_or_goal_direction (:571-597): candidates in north, east, south, west order
+  int d[4], n = 0;
+  if (y == 0) d[n++] = 0;
+  if (x == c.W - 1) d[n++] = 1;
+  if (y == c.H - 1) d[n++] = 2;
+  if (x == 0) d[n++] = 3;
+  int k = rng.index(PGTG_STREAM_MAP, n);
+  return k == 0 ? d[0] : k == 1 ? d[1] : k == 2 ? d[2] : d[3];
+}
+
+template <int RNG>
+PG_HDN void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng) {
+  // chose_random_start_and_goal_position_and_direction (:475-568)
+  int sx = c.start_x, sy = c.start_y, sd = c.start_dir, gx = c.goal_x, gy = c.goal_y, gd = c.goal_dir;
+  if (c.start_mode == 2) random_border_position<RNG>(c, rng, sx, sy);
+  if (c.goal_mode == 2) random_border_position<RNG>(c, rng, gx, gy);
+  if (c.min_sg_dist >= 0)
+    while (abs(sx - gx) + abs(sy - gy) < c.min_sg_dist) {
+      random_border_position<RNG>(c, rng, sx, sy);
+      random_border_position<RNG>(c, rng, gx, gy);
+    }
+  if (c.start_mode != 0) sd = random_direction<RNG>(c, rng, sx, sy);
+  if (c.goal_mode != 0) gd = random_direction<RNG>(c, rng, gx, gy);
+  while (sx == gx && sy == gy && sd == gd) {
+    if (c.start_mode == 2) random_border_position<RNG>(c, rng, sx, sy);
+    if (c.start_mode != 0) sd = random_direction<RNG>(c, rng, sx, sy);
+    if (c.goal_mode == 2) random_border_position<RNG>(c, rng, gx, gy);
+    if (c.goal_mode != 0) gd = random_direction<RNG>(c, rng, gx, gy);
+  }
+  int W = c.W, T = c.T;
+  int st = sy * W + sx, gt = gy * W + gx;
+
+  // generate_map_graph (:192-266). The full grid; an edge picked from removable_edges (edges()
+  // order, host table) stays removed iff start and goal remain connected -- which is what the
+  // reference's "on the BFS path? then is_connected? else restore" amounts to, independent of
+  // BFS tie-breaking.
+  Board E, S;
+  E.w[0] = E.w[1] = E.w[2] = E.w[3] = 0; S = E;
+  for (int t = 0; t < T; t++) {
+    if (t % W < W - 1) bset(E, t);
+    if (t + W < T) bset(S, t);
+  }
+  uint32_t alive[MAX_EDGE_TAB / 32];
+  int n_tab = c.n_edge_tab, n_alive = n_tab, cur = n_tab;
+  for (int i = 0; i < (n_tab + 31) / 32; i++) alive[i] = (i * 32 + 32 <= n_tab) ? 0xFFFFFFFFu : ((1u << (n_tab & 31)) - 1u);
+  while (cur > c.edges_to_keep && n_alive > 0) {  // :245
+    int idx = rng.index(PGTG_STREAM_MAP, n_alive);  // :249
+    int wi = 0;
+    for (;; wi++) { int pc = pg_popc(alive[wi]); if (idx < pc) break; idx -= pc; }
+    uint32_t word = alive[wi];
+    while (idx--) word &= word - 1;
+    int i = wi * 32 + pg_ffs(word) - 1;
+    int j = pg_ldg(&p.edge_rev[i]);
+    alive[i >> 5] &= ~(1u << (i & 31));
+    alive[j >> 5] &= ~(1u << (j & 31));
+    n_alive -= 2;
+    unsigned ab = pg_ldg(&p.edge_tab[i]);
+    int a = ab & 255, b = ab >> 8;
+    int lo = a < b ? a : b;
+    bool horiz = (a > b ? a - b : b - a) == 1;
+    if (horiz) bclr(E, lo); else bclr(S, lo);
+    if (grid_connected(c, E, S, st, gt)) cur -= 2;
+    else { if (horiz) bset(E, lo); else bset(S, lo); }
+  }
+  // map_graph_to_tile_map_object (:269-334)
+  for (int t = 0; t < T; t++) {
+    int ex = 0;
+    if (t >= W && bget(S, t - W)) ex |= 1;
+    if (bget(E, t)) ex |= 2;
+    if (bget(S, t)) ex |= 4;
+    if (t % W > 0 && bget(E, t - 1)) ex |= 8;
+    m.tiles[t] = (uint16_t)ex;
+  }
+  m.tiles[st] |= (uint16_t)(1 << sd);
+  m.tiles[gt] |= (uint16_t)(1 << gd);
+  // add_connections_to_borders (:337-371): slots in host-table order, default start/goal removed
+  uint64_t slots = c.n_border_slots >= 64 ? ~0ull : ((1ull << c.n_border_slots) - 1ull);
+  int n_slots = c.n_border_slots;
+  for (int k = 0; k < c.border_connections && n_slots > 0; k++) {
+    int idx = rng.index(PGTG_STREAM_MAP, n_slots);  // :367
+    uint64_t sl = slots;
+    while (idx--) sl &= sl - 1;
+    int i = pg_popcll((sl & (~sl + 1)) - 1);
+    slots &= ~(1ull << i);
+    n_slots--;
+    unsigned v = pg_ldg(&p.border_slots[i]);
+    m.tiles[v & 255] |= (uint16_t)(1 << (v >> 8));
+  }
+  // add_obstacles_to_map (:374-472), row-major, one random() per tile whatever the outcome
+  if (c.obstacle_probability > 0) {
+    for (int t = 0; t < T; t++) {
+      double u = rng.uniform(PGTG_STREAM_MAP);  // :415
+      int ex = td_exits(m.tiles[t]);
+      if (!(u < c.obstacle_probability) || ex == 0) continue;
+      int type = 1 + rng.choice_cdf(PGTG_STREAM_MAP, c.obstacle_cdf, 4);  // :418
+      int mask;
+      if (type != 4) mask = rng.index(PGTG_STREAM_MAP, 8);  // :430
+      else {
+        int opts[6], n = 0, cnt = pg_popc(ex);
+        if (ex & 1) opts[n++] = 8;
+        if (ex & 2) opts[n++] = 9;
+        if (ex & 4) opts[n++] = 10;
+        if (ex & 8) opts[n++] = 11;
+        if ((ex & 1) && (ex & 4) && cnt >= 3) opts[n++] = 12;
+        if ((ex & 2) && (ex & 8) && cnt >= 3) opts[n++] = 13;
+        int k = rng.index(PGTG_STREAM_MAP, n);  // :470
+        mask = opts[0];
+        for (int q = 1; q < 6; q++) if (q == k) mask = opts[q];
+      }
+      m.tiles[t] = (uint16_t)(ex | type << 4 | mask << 7);
+    }
+  }
+  e.plan = plan_pack(sx, sy, sd, gx, gy, gd, 0);
+}
+
+// parse_map_object's path part (parser.py:27-37, 158-164): Dijkstra with unit weights and
+// (cost, push counter) keys == FIFO BFS, successors in N, E, S, W insertion order
+// (parse_tile_map_to_graph, parser.py:244-276), first-discovered predecessor.
+PG_HDN void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
+  int W = c.W, H = c.H, T = c.T;
+  int st = plan_sy(e.plan) * W + plan_sx(e.plan), gt = plan_gy(e.plan) * W + plan_gx(e.plan);
+  uint8_t q[PGTG_MAX_TILES], prev[PGTG_MAX_TILES];
+  Board seen; seen.w[0] = seen.w[1] = seen.w[2] = seen.w[3] = 0;
+  int qh = 0, qt = 0;
+  bool found = false;
+  bset(seen, st); q[qt++] = (uint8_t)st;
+  while (qh < qt) {
+    int n = q[qh++];
+    if (n == gt) { found = true; break; }
+    int ex = td_exits(m.tiles[n]), x = n % W, y = n / W;
+    int cand[4] = {n - W, n + 1, n + W, n - 1};
+    bool ok[4] = {(ex & 1) && y > 0, (ex & 2) && x < W - 1, (ex & 4) && y < H - 1, (ex & 8) && x > 0};
+    for (int k = 0; k < 4; k++)
+      if (ok[k] && !bget(seen, cand[k])) { bset(seen, cand[k]); prev[cand[k]] = (uint8_t)n; q[qt++] = (uint8_t)cand[k]; }
+  }
+  for (int t = 0; t < T; t++) m.tiles[t] &= 0x07FF;  // clear subgoal dir + used
+  int ns = 1;
+  m.tiles[gt] |= (uint16_t)((1 + plan_gd(e.plan)) << 11);  // final tile carries the goal direction (parser.py:158)
+  if (!found) e.err |= 8;
+  else {
+    int cur = gt;
+    while (cur != st) {
+      int pr = prev[cur];
+      int d = cur == pr - W ? 0 : cur == pr + 1 ? 1 : cur == pr + W ? 2 : 3;  // find_direction (parser.py:279-306)
+      m.tiles[pr] |= (uint16_t)((1 + d) << 11);
+      cur = pr; ns++;
+    }
+  }
+  e.plan = (e.plan & 0xFFFFFu) | (unsigned)ns << 20;
+}
+
+template <int RNG>
+PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
+  // PGTGEnv.reset (environment.py:581-656)
+  e.episode++;
+  e.elapsed = 0;
+  Rng<RNG> rng(p, e, env);
+  if (c.fixed_map) {
+    for (int t = 0; t < c.T; t++) m.tiles[t] = pg_ldg(&p.fixed_tiles[t]);
+    e.plan = p.fixed_plan;
+  } else {
+    generate_map<RNG>(c, p, m, e, rng);
+  }
+  assign_subgoals(c, m, e);
+  m.plan = e.plan;
+  e.flags |= EF_TILES_DIRTY | EF_RESET;
+  // self.position = map_rng.choice(self.map.starters) (:635); starters in x-major order
+  int stile = m.start_tile(), sd = plan_sd(e.plan);
+  unsigned lab = (m.line_labels(stile, m.tiles[stile]) >> (4 * sd)) & 15;
+  e.x = e.y = 0;
+  if (lab == 3) {
+    int k = rng.index(PGTG_STREAM_MAP, 3);
+    int ox = (stile % c.W) * TILE, oy = (stile / c.W) * TILE;
+    for (int w = 0; w < 3; w++) {
+      uint32_t bits = m.L.exit_line[sd][w];
+      while (bits) {
+        int sq = w * 32 + pg_ffs(bits) - 1;
+        bits &= bits - 1;
+        if (k-- == 0) { e.x = ox + sq / TILE; e.y = oy + sq % TILE; }
+      }
+    }
+  } else e.err |= 64;
+  e.vx = e.vy = 0;
+  e.misc = 0;  // flat_tire, light counter, cars (:637-650)
+  e.next_car_id = 0;
+  if (c.vis_words) {
+    for (int i = 0; i < c.vis_words; i++) p.visited[(size_t)i * c.N + env] = 0;
+    visited_test_set(c, p, env, e.x, e.y, true);  // positions_path = [position] (:643)
+  }
+  if (c.traffic_density > 0) create_initial_traffic<RNG>(c, p, m, e, rng, env);  // :652-653
+}
+
+// ---------------------------------------------------------------------------------------------
+// observation (environment.py:1344-1506): planes as bitmaps
+PG_HD void tile_plane(const DevCfg& c, const MapView& m, int kind, int t, int phase, uint32_t out[3]) {
+  out[0] = out[1] = out[2] = 0;
+  unsigned td = m.tiles[t];
+  int ex = td_exits(td);
+  const uint32_t* wall = m.L.wall[ex];
+  switch (kind) {
+    case PGTG_CH_WALLS: out[0] = wall[0]; out[1] = wall[1]; out[2] = wall[2]; return;
+    case PGTG_CH_ICE: case PGTG_CH_BROKEN: case PGTG_CH_SAND: {
+      if (td_otype(td) != kind - PGTG_CH_ICE + 1) return;
+      const uint32_t* mk = m.L.mask[td_omask(td)];
+      out[0] = mk[0] & ~wall[0]; out[1] = mk[1] & ~wall[1]; out[2] = mk[2] & ~wall[2];
+      return;
+    }
+    case PGTG_CH_LIGHT_GREEN: case PGTG_CH_LIGHT_YELLOW: case PGTG_CH_LIGHT_RED: {
+      if (td_otype(td) != 4 || phase != kind - PGTG_CH_LIGHT_GREEN) return;
+      const uint32_t* mk = m.L.mask[td_omask(td)];
+      out[0] = mk[0] & ~wall[0]; out[1] = mk[1] & ~wall[1]; out[2] = mk[2] & ~wall[2];
+      return;
+    }
+    case PGTG_CH_GOALS: case PGTG_CH_SUBGOAL: case PGTG_CH_FINAL_GOAL: case PGTG_CH_START: case PGTG_CH_USED_SUBGOAL: {
+      if (!td_sg(td) && t != m.start_tile()) return;
+      unsigned lab = m.line_labels(t, td);
+      for (int d = 0; d < 4; d++) {
+        unsigned l = (lab >> (4 * d)) & 15;
+        bool on = kind == PGTG_CH_GOALS ? (l == 1 || l == 4) : kind == PGTG_CH_SUBGOAL ? l == 1 : kind == PGTG_CH_FINAL_GOAL ? l == 4
+                : kind == PGTG_CH_START ? l == 3 : l == 2;
+        if (on) { out[0] |= m.L.exit_line[d][0]; out[1] |= m.L.exit_line[d][1]; out[2] |= m.L.exit_line[d][2]; }
+      }
+      return;
+    }
+    case PGTG_CH_CAR_SPAWNER: spawner_bits(c, m.L, ex, t % c.W, t / c.W, out); return;
+    default: return;
+  }
+}
+
+PG_HD void emit_bits(uint32_t* bits, uint32_t off, uint32_t v) {
+  if (!v) return;
+  uint32_t s = off & 31;
+  pg_atomic_or(&bits[off >> 5], v << s);
+  if (s && (v >> (32 - s))) pg_atomic_or(&bits[(off >> 5) + 1], v >> (32 - s));
+}
+
+// writes env's C*P*P observation bits at bit offset `base` of `bits`, plus position/velocity/nsd
+PG_HDN void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, uint32_t* bits,
+                        uint32_t base, int32_t* pos, int32_t* vel, int32_t* nsd) {
+  int pix = e.x < 0 ? 0 : (e.x > c.WS - 1 ? c.WS - 1 : e.x);  // :1352-1356
+  int piy = e.y < 0 ? 0 : (e.y > c.HS - 1 ? c.HS - 1 : e.y);
+  int tx = pix / TILE, ty = piy / TILE;
+  int phase = light_phase(c, misc_light(e.misc));
+  int ncars = misc_ncars(e.misc);
+  int PP = c.P * c.P;
+  if (!c.sliding) {
+    int t = ty * c.W + tx;
+    for (int ch = 0; ch < c.C; ch++) {
+      int kind = c.channel_kind[ch];
+      uint32_t w[3];
+      if (kind == PGTG_CH_TRAFFIC) {  // :1397-1409
+        w[0] = w[1] = w[2] = 0;
+        for (int k = 0; k < ncars; k++) {
+          unsigned xy = car_xy(car_slot(c, p, env, k));
+          int lx = (int)(xy & 255) - tx * TILE, ly = (int)(xy >> 8) - ty * TILE;
+          if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE) { int sq = lx * TILE + ly; w[sq >> 5] |= 1u << (sq & 31); }
+        }
+      } else if (kind == PGTG_CH_ZERO) continue;
+      else tile_plane(c, m, kind, t, phase, w);
+      uint32_t off = base + ch * 81;
+      emit_bits(bits, off, w[0]); emit_bits(bits, off + 32, w[1]); emit_bits(bits, off + 64, w[2]);
+    }
+    pos[0] = pix - tx * TILE; pos[1] = piy - ty * TILE;  // :1448-1461
+  } else {
+    int k = c.window_k, x0 = e.x - k, y0 = e.y - k;  // window around the UNCLAMPED position (:1370-1377)
+    for (int ch = 0; ch < c.C; ch++) {
+      int kind = c.channel_kind[ch];
+      if (kind == PGTG_CH_ZERO) continue;
+      uint32_t off = base + ch * PP;
+      if (kind == PGTG_CH_TRAFFIC) {
+        for (int q = 0; q < ncars; q++) {
+          unsigned xy = car_xy(car_slot(c, p, env, q));
+          int ix = (int)(xy & 255) - x0, iy = (int)(xy >> 8) - y0;
+          if (ix >= 0 && ix < c.P && iy >= 0 && iy < c.P) emit_bits(bits, off + ix * c.P + iy, 1u);
+        }
+        continue;
+      }
+      for (int ix = 0; ix < c.P; ix++) {
+        int X = x0 + ix;
+        uint32_t col = 0;
+        uint32_t full = c.P >= 32 ? 0xFFFFFFFFu : ((1u << c.P) - 1u);
+        if (X < 0 || X >= c.WS) { if (kind == PGTG_CH_WALLS) col = full; }  // fill {"wall"} (:1384)
+        else {
+          int ttx = X / TILE, lx = X - ttx * TILE;
+          for (int iy = 0; iy < c.P;) {
+            int Y = y0 + iy;
+            if (Y < 0 || Y >= c.HS) { if (kind == PGTG_CH_WALLS) col |= 1u << iy; iy++; continue; }
+            int tty = Y / TILE, ly = Y - tty * TILE;
+            uint32_t w[3];
+            tile_plane(c, m, kind, tty * c.W + ttx, phase, w);
+            uint32_t c9 = col9(w, lx) >> ly;  // rows ly.. of this tile column
+            int cnt = TILE - ly;
+            if (cnt > c.P - iy) cnt = c.P - iy;
+            col |= (c9 & ((1u << cnt) - 1u)) << iy;
+            iy += cnt;
+          }
+        }
+        emit_bits(bits, off + ix * c.P, col);
+      }
+    }
+    pos[0] = k; pos[1] = k;  // quirk A.3-4
+  }
+  vel[0] = e.vx; vel[1] = e.vy;
+  int d = -1;
+  if (c.use_nsd) {  // :1466-1504
+    int sg = td_sg(m.tiles[ty * c.W + tx]);  // map.py:120-141
+    d = sg ? sg - 1 : -1;
+    if (d == -1 || c.sliding) {
+      int gx, gy;
+      if (m.nearest_goal(pix, piy, gx, gy)) {
+        int R = c.lut_radius;
+        d = (pg_ldg(&p.dirlut[(gy - piy + R) * (2 * R + 1) + (gx - pix + R)]) >> 3) & 7;
+      }
+    }
+  }
+  *nsd = d;
+}
+
+}  // namespace pgtg

@@ -1,0 +1,91 @@
+// pgtg_emu.cpp -- HOST EMULATION of the pgtg_b200 kernel phases. TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the product's per-env logic (pgtg_b200/csrc/pgtg_logic.cuh, pgtg_phases.cuh) and its
+// C-ABI implementation (pgtg_api_impl.hpp) with g++ over a host-memory backend, running the CTA
+// phases as plain loops. It exists so that the CPU test-suite (-m "not gpu") can replay the golden
+// reference traces through the SAME logic the sm_100a kernels execute, without a GPU. It is never
+// loaded by the pgtg_b200 package, bench.py or smoke(): the product has no CPU path.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../pgtg_b200/csrc/pgtg_phases.cuh"
+
+struct pgtg_env;
+static void* bk_alloc(size_t n) { void* p = nullptr; if (posix_memalign(&p, 256, n)) return nullptr; return p; }
+static void bk_free(void* p) { free(p); }
+static int bk_set_device(int) { return 0; }
+static int bk_h2d(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
+static int bk_d2h(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
+static int bk_memset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+static int bk_sync(void*) { return 0; }
+static const char* bk_error() { return "emu"; }
+static int bk_dl_device_type() { return 1; }  // kDLCPU
+static int bk_pick_block(const pgtg::DevCfg&, int* block, size_t* smem) { *block = 128; *smem = 0; return 0; }
+static int bk_launch(pgtg_env*, int, const uint8_t*, const int64_t*, const void*, int, void*);
+
+#include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
+
+template <int RNG>
+static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes,
+                      int blk, unsigned char* smem) {
+  const DevCfg& c = h->dc;
+  const DevPtrs& p = h->dp;
+  int B = h->block, env0 = blk * B, nvalid = c.N - env0 < B ? c.N - env0 : B;
+  BlockShared sh = carve_shared(smem, c, B);
+  for (int t = 0; t < B; t++) phase_stage(c, p, sh, t, B, env0, nvalid, true);
+  int n_done = 0;
+  double st[8] = {0};
+  if (mode == MODE_STEP) {
+    for (int t = 0; t < nvalid; t++) {
+      int env = env0 + t;
+      int a = action_bytes == 8 ? (int)((const int64_t*)actions)[env] : ((const int32_t*)actions)[env];
+      StepResult r = phase_step<RNG>(c, p, sh, t, env, a);
+      if (r.outcome) {
+        sh.done_list[n_done++] = t;
+        st[0] += 1; st[1] += r.ep_return; st[2] += sh.regs[t].elapsed;
+        st[3] += r.outcome == 2; st[4] += r.outcome == 1; st[5] += r.outcome == 3;
+      }
+    }
+    if (c.write_final_obs && n_done) {
+      for (int k = 0; k < n_done; k++) phase_emit(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true);
+      for (int t = 0; t < B; t++) phase_expand_final(c, p.f_obs_map, sh, t, B, env0, n_done);
+      for (int i = 0; i < sh.bits_words; i++) sh.bits[i] = 0;
+    }
+  } else if (mode == MODE_RESET) {
+    for (int t = 0; t < nvalid; t++) {
+      int env = env0 + t;
+      sh.regs[t] = load_regs(c, p, env);
+      if (!mask || mask[env]) {
+        if (seeds) { p.key[env] = (uint64_t)seeds[env]; sh.regs[t].episode = 0; }
+        p.ep_return[env] = 0;
+        sh.done_list[n_done++] = t;
+      }
+    }
+  } else {
+    for (int t = 0; t < nvalid; t++) sh.regs[t] = load_regs(c, p, env0 + t);
+  }
+  for (int k = 0; k < n_done; k++) phase_reset<RNG>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+  for (int t = 0; t < nvalid; t++) phase_emit(c, p, sh, t, env0 + t, false);
+  for (int t = 0; t < B; t++) phase_expand(c, p.obs_map, sh, t, B, env0, nvalid);
+  for (int k = 0; k < 8; k++) p.stats[k] += st[k];
+}
+
+static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void*) {
+  size_t bytes = block_shared_bytes(h->dc, h->block);
+  unsigned char* smem = (unsigned char*)bk_alloc(bytes);
+  int nblk = (h->dc.N + h->block - 1) / h->block;
+  for (int b = 0; b < nblk; b++) {
+    memset(smem, 0xA5, bytes);  // shared memory starts undefined on the device too
+    if (h->cfg.rng_mode == PGTG_RNG_TAPE) run_block<PGTG_RNG_TAPE>(h, mode, mask, seeds, actions, action_bytes, b, smem);
+    else run_block<PGTG_RNG_PHILOX>(h, mode, mask, seeds, actions, action_bytes, b, smem);
+  }
+  free(smem);
+  return 0;
+}
+
+extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
+  if (!e || !e->did_reset) return fail(PGTG_ERR_STATE, "observe before reset");
+  bk_launch(e, 2, nullptr, nullptr, nullptr, 0, stream);
+  e->launches++;
+  return PGTG_OK;
+}
