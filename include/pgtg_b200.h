@@ -251,7 +251,12 @@ int pgtg_dlpack(pgtg_env* env, const char* name, void** out_managed_tensor);
 int pgtg_get_state(pgtg_env* env, pgtg_state* out);
 /* set_to_state (environment.py:1301-1342): agent, flat_tire and cars only (quirk A.3-10). */
 int pgtg_set_state(pgtg_env* env, const pgtg_state* in);
-/* Copies the 8 statistics doubles to the host (synchronises). */
+/* Episode statistics are accumulated per CTA on the device. pgtg_reduce_stats sums them into the
+ * 8-double `stats` buffer on `stream` without synchronising (so the host can NCCL-all-reduce that
+ * device buffer); pgtg_reset_stats clears them. */
+int pgtg_reduce_stats(pgtg_env* env, void* stream);
+int pgtg_reset_stats(pgtg_env* env, void* stream);
+/* Reduces, then copies the 8 statistics doubles to the host (synchronises). */
 int pgtg_stats(pgtg_env* env, double* out8, int reset_after);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t pgtg_launch_count(pgtg_env* env);

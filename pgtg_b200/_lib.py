@@ -47,6 +47,8 @@ EXPORTS = {
     "pgtg_get_state": (C.c_int, [C.c_void_p, C.POINTER(PgtgState)]),
     "pgtg_set_state": (C.c_int, [C.c_void_p, C.POINTER(PgtgState)]),
     "pgtg_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "pgtg_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pgtg_reset_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgtg_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

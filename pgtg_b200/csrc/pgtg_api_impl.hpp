@@ -10,7 +10,8 @@
 //   int bk_pick_block(const DevCfg&, int* block, size_t* smem);
 //   int bk_launch(pgtg_env*, int mode, const uint8_t* mask_dev, const int64_t* seeds_dev,
 //                 const void* actions_dev, int action_bytes, void* stream);
-//   const char* bk_error();
+//   const char* bk_error();  int bk_dl_device_type();
+//   int bk_stats_reduce(pgtg_env*, void* stream);  int bk_stats_reset(pgtg_env*, void* stream);
 #pragma once
 #include <math.h>
 #include <stdio.h>
@@ -23,7 +24,7 @@
 
 using namespace pgtg;
 
-enum { MODE_STEP = 0, MODE_RESET = 1 };
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
 
 struct pgtg_env {
   pgtg_config cfg;
@@ -35,7 +36,8 @@ struct pgtg_env {
   int64_t launches;
   std::vector<void*> allocs;
   bool have_fixed, have_tape, did_reset;
-  int tape_mode;
+  int nblk;             // CTAs per launch
+  double* stats_rows;   // [nblk][8] per-CTA episode statistics (CUDA backend)
   // device scratch for reset arguments and host-buffer steps
   uint8_t* mask_dev;
   int64_t* seeds_dev;
@@ -196,6 +198,8 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   e->have_fixed = e->have_tape = e->did_reset = false;
   memset(&e->dp, 0, sizeof e->dp);
   if (bk_pick_block(e->dc, &e->block, &e->smem)) { delete e; return fail(PGTG_ERR_INVALID, "observation window too large for shared memory"); }
+  e->nblk = (dc.N + e->block - 1) / e->block;
+  e->stats_rows = nullptr;
   DevPtrs& p = e->dp;
   size_t N = (size_t)dc.N;
   bool ok = true;
@@ -212,6 +216,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     A(f_obs_map, int8_t, N * dc.obs_bits + 16); A(f_obs_position, int32_t, 2 * N); A(f_obs_velocity, int32_t, 2 * N); A(f_obs_nsd, int32_t, N);
   }
   A(stats, double, 8);
+  ok = ok && ((e->stats_rows = dev_alloc<double>(e, 8 * (size_t)e->nblk)) != nullptr);
   ok = ok && ((e->mask_dev = dev_alloc<uint8_t>(e, N)) != nullptr);
   ok = ok && ((e->seeds_dev = dev_alloc<int64_t>(e, N)) != nullptr);
   ok = ok && ((e->actions_dev = dev_alloc<int32_t>(e, N)) != nullptr);
@@ -546,12 +551,27 @@ extern "C" int pgtg_set_state(pgtg_env* e, const pgtg_state* s) {
   return PGTG_OK;
 }
 
+extern "C" int pgtg_reduce_stats(pgtg_env* e, void* stream) {
+  if (!e) return fail(PGTG_ERR_INVALID, "null handle");
+  bk_set_device(e->device);
+  if (bk_stats_reduce(e, stream)) return fail(PGTG_ERR_CUDA, std::string("stats reduction failed: ") + bk_error());
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_reset_stats(pgtg_env* e, void* stream) {
+  if (!e) return fail(PGTG_ERR_INVALID, "null handle");
+  bk_set_device(e->device);
+  if (bk_stats_reset(e, stream)) return fail(PGTG_ERR_CUDA, std::string("stats reset failed: ") + bk_error());
+  return PGTG_OK;
+}
+
 extern "C" int pgtg_stats(pgtg_env* e, double* out8, int reset_after) {
   if (!e || !out8) return fail(PGTG_ERR_INVALID, "null argument");
   bk_set_device(e->device);
+  if (bk_stats_reduce(e, nullptr)) return fail(PGTG_ERR_CUDA, std::string("stats reduction failed: ") + bk_error());
   bk_d2h(out8, e->dp.stats, 64, nullptr);
   if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
-  if (reset_after) { bk_memset(e->dp.stats, 0, 64); bk_sync(nullptr); }
+  if (reset_after) { bk_stats_reset(e, nullptr); bk_sync(nullptr); }
   return PGTG_OK;
 }
 

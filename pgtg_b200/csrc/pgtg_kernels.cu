@@ -1,0 +1,197 @@
+// pgtg_kernels.cu -- sm_100a kernels and the CUDA backend of the C ABI (include/pgtg_b200.h).
+//
+// One fused launch per tick: every CTA owns a contiguous slice of B envs and runs
+//   stage -> step (1 env / thread) -> ballot+scan compaction of done envs -> on-device reset /
+//   procedural map regeneration by the first n_done threads -> observation bit assembly in shared
+//   memory -> vectorised expansion to the int8 observation planes (contiguous 16-byte stores).
+// Nothing here is a dense contraction, so no tensor cores: the kernel is bounded by HBM traffic
+// (observation write + SoA state scan), see DESIGN.md for the byte accounting.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "pgtg_phases.cuh"
+
+struct pgtg_env;
+static thread_local cudaError_t g_cuda_err = cudaSuccess;
+static const char* bk_error() { return cudaGetErrorString(g_cuda_err); }
+static int ck(cudaError_t e) { if (e != cudaSuccess) { g_cuda_err = e; return -1; } return 0; }
+static void* bk_alloc(size_t n) { void* p = nullptr; if (ck(cudaMalloc(&p, n))) return nullptr; return p; }
+static void bk_free(void* p) { cudaFree(p); }
+static int bk_set_device(int d) { return ck(cudaSetDevice(d)); }
+static int bk_h2d(void* d, const void* s, size_t n, void* st) { return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, (cudaStream_t)st)); }
+static int bk_d2h(void* d, const void* s, size_t n, void* st) { return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st)); }
+static int bk_memset(void* d, int v, size_t n) { return ck(cudaMemset(d, v, n)); }
+static int bk_sync(void* st) { return ck(st ? cudaStreamSynchronize((cudaStream_t)st) : cudaDeviceSynchronize()); }
+static int bk_dl_device_type() { return 2; }  // kDLCUDA
+static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem);
+static int bk_launch(pgtg_env*, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream);
+static int bk_stats_reduce(pgtg_env*, void* stream);
+static int bk_stats_reset(pgtg_env*, void* stream);
+
+#include "pgtg_api_impl.hpp"
+
+namespace pgtg {
+
+constexpr int STATS_STRIDE = 8;
+
+// per-CTA episode statistics row (no cross-CTA atomics on the hot path)
+struct StatsArgs {
+  double* rows;  // [gridDim.x][8]
+};
+
+template <int RNG, int MODE>
+__global__ void __launch_bounds__(128) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
+                                                        const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
+                                                        const void* __restrict__ actions, int action_bytes, StatsArgs sa) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int B = blockDim.x, tid = threadIdx.x;
+  const int env0 = blockIdx.x * B;
+  const int nvalid = min(B, c.N - env0);
+  const int env = env0 + tid;
+  const bool valid = tid < nvalid;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = B >> 5;
+  BlockShared sh = carve_shared(smem, c, B);
+
+  phase_stage(c, p, sh, tid, B, env0, nvalid, true);
+  if (tid < 8) { sh.counters[8 + tid] = 0; sh.dsum[tid] = 0.0; }
+  __syncthreads();
+
+  bool done = false;
+  if (MODE == MODE_STEP) {
+    StepResult r;
+    r.outcome = 0; r.ep_return = 0;
+    int len = 0;
+    if (valid) {
+      int a = action_bytes == 8 ? (int)((const long long*)actions)[env] : ((const int*)actions)[env];
+      r = phase_step<RNG>(c, p, sh, tid, env, a);
+      done = r.outcome != 0;
+      len = done ? (int)sh.regs[tid].elapsed : 0;
+    }
+    // episode statistics: ballots for the counters, warp reductions for the sums, one row per CTA
+    unsigned any = __ballot_sync(0xffffffffu, done);
+    if (any) {
+      unsigned g = __ballot_sync(0xffffffffu, r.outcome == 2), cr = __ballot_sync(0xffffffffu, r.outcome == 1),
+               tr = __ballot_sync(0xffffffffu, r.outcome == 3);
+      int lsum = __reduce_add_sync(0xffffffffu, len);
+      double rs = r.ep_return;
+      for (int o = 16; o > 0; o >>= 1) rs += __shfl_down_sync(0xffffffffu, rs, o);
+      if (lane == 0) {
+        atomicAdd(&sh.counters[8], __popc(g)); atomicAdd(&sh.counters[9], __popc(cr)); atomicAdd(&sh.counters[10], __popc(tr));
+        atomicAdd(&sh.counters[11], lsum);
+        atomicAdd(&sh.dsum[0], rs);
+      }
+    }
+  } else if (MODE == MODE_RESET) {
+    if (valid) {
+      EnvRegs e = load_regs(c, p, env);
+      if (!mask || mask[env]) {
+        if (seeds) { p.key[env] = (uint64_t)seeds[env]; e.episode = 0; }
+        p.ep_return[env] = 0.0;
+        done = true;
+      }
+      sh.regs[tid] = e;
+    }
+  } else {
+    if (valid) sh.regs[tid] = load_regs(c, p, env);
+  }
+
+  // compaction of the done envs: warp ballot + CTA scan -> dense list in shared memory
+  unsigned ballot = __ballot_sync(0xffffffffu, done);
+  if (lane == 0) sh.counters[1 + warp] = __popc(ballot);
+  __syncthreads();
+  int base = 0, n_done = 0;
+  for (int w = 0; w < nwarps; w++) { int v = sh.counters[1 + w]; if (w < warp) base += v; n_done += v; }
+  if (done) sh.done_list[base + __popc(ballot & ((1u << lane) - 1u))] = tid;
+  if (MODE == MODE_STEP && tid == 0 && n_done) {
+    double* row = sa.rows + (size_t)blockIdx.x * STATS_STRIDE;
+    row[0] += n_done; row[1] += sh.dsum[0]; row[2] += sh.counters[11];
+    row[3] += sh.counters[8]; row[4] += sh.counters[9]; row[5] += sh.counters[10];
+  }
+  __syncthreads();
+
+  if (MODE == MODE_STEP && c.write_final_obs && n_done) {  // CTA-uniform condition
+    if (done) phase_emit(c, p, sh, tid, env, true);
+    __syncthreads();
+    phase_expand_final(c, p.f_obs_map, sh, tid, B, env0, n_done);
+    __syncthreads();
+    for (int i = tid; i < sh.bits_words; i += B) sh.bits[i] = 0;
+    __syncthreads();
+  }
+
+  if (MODE != MODE_OBSERVE) {
+    if (tid < n_done) {
+      int local = sh.done_list[tid];
+      phase_reset<RNG>(c, p, sh, local, env0 + local);
+    }
+    __syncthreads();
+  }
+  if (valid) phase_emit(c, p, sh, tid, env, false);
+  __syncthreads();
+  phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid);
+}
+
+__global__ void pgtg_reduce_stats_kernel(const double* __restrict__ rows, int nrows, double* __restrict__ out) {
+  // out[k] = sum over CTAs of rows[.][k]; one warp per statistic
+  int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double s = 0;
+  for (int r = lane; r < nrows; r += 32) s += rows[(size_t)r * STATS_STRIDE + k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[k] = s;
+}
+
+}  // namespace pgtg
+
+// ---- CUDA backend: launch ----------------------------------------------------------------------
+static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem) {
+  for (int B : {128, 64, 32}) {
+    size_t s = pgtg::block_shared_bytes(c, B);
+    if (s <= 200 * 1024) { *block = B; *smem = s; return 0; }
+  }
+  return -1;
+}
+
+template <int RNG, int MODE>
+static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
+  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE>;
+  if (e->smem > 48 * 1024) {
+    if (ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem))) return -1;
+  }
+  pgtg::StatsArgs sa = {e->stats_rows};
+  kern<<<e->nblk, e->block, e->smem, st>>>(e->dc, e->dp, mask, seeds, actions, action_bytes, sa);
+  return ck(cudaGetLastError());
+}
+
+static int bk_launch(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tape = e->cfg.rng_mode == PGTG_RNG_TAPE;
+  switch (mode) {
+    case MODE_STEP:
+      return tape ? launch_one<PGTG_RNG_TAPE, MODE_STEP>(e, mask, seeds, actions, action_bytes, st)
+                  : launch_one<PGTG_RNG_PHILOX, MODE_STEP>(e, mask, seeds, actions, action_bytes, st);
+    case MODE_RESET:
+      return tape ? launch_one<PGTG_RNG_TAPE, MODE_RESET>(e, mask, seeds, actions, action_bytes, st)
+                  : launch_one<PGTG_RNG_PHILOX, MODE_RESET>(e, mask, seeds, actions, action_bytes, st);
+    default:
+      return launch_one<PGTG_RNG_PHILOX, MODE_OBSERVE>(e, mask, seeds, actions, action_bytes, st);
+  }
+}
+
+extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
+  if (!e || !e->did_reset) return fail(PGTG_ERR_STATE, "observe before reset");
+  bk_set_device(e->device);
+  if (bk_launch(e, MODE_OBSERVE, nullptr, nullptr, nullptr, 0, stream)) return fail(PGTG_ERR_CUDA, std::string("observe launch failed: ") + bk_error());
+  e->launches++;
+  return PGTG_OK;
+}
+
+// Sum the per-CTA statistic rows into the 8-double `stats` buffer on the device (the buffer the
+// host all-reduces with NCCL), on `stream`, without synchronising.
+static int bk_stats_reduce(pgtg_env* e, void* stream) {
+  pgtg::pgtg_reduce_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->stats_rows, e->nblk, e->dp.stats);
+  e->launches++;
+  return ck(cudaGetLastError());
+}
+static int bk_stats_reset(pgtg_env* e, void* stream) {
+  if (ck(cudaMemsetAsync(e->stats_rows, 0, sizeof(double) * pgtg::STATS_STRIDE * (size_t)e->nblk, (cudaStream_t)stream))) return -1;
+  return ck(cudaMemsetAsync(e->dp.stats, 0, 64, (cudaStream_t)stream));
+}

@@ -1,0 +1,227 @@
+"""`PGTGVectorEnv` -- the batched, GPU-resident drop-in for rollouts of the reference `PGTGEnv`.
+
+Mirrors the reference's public surface (pgtg/environment.py):
+  * constructor keyword arguments and defaults of `PGTGEnv.__init__` (:302-359);
+  * `single_action_space = Discrete(9)` (:415) and the observation Dict (:417-441);
+  * `reset(seed)` (:581) and `step(action)` (:1092) with the reward / terminated / truncated
+    semantics of the reference; truncation comes from `max_episode_steps` (the reference uses a
+    `TimeLimit` wrapper, train.py:39);
+  * gymnasium 0.28.1 vector semantics (the version pinned by the reference's poetry.lock): env i is
+    seeded with `seed + i`, and an env that finishes is reset inside the same `step` call -- the
+    returned observation is the first observation of the new episode, the terminal one is under
+    `info["final_observation"]` when `final_observation=True`.
+
+All state lives in HBM; `step` is one fused CUDA launch enqueued on torch's current stream with no
+host synchronisation. Observations, rewards and flags are torch views (DLPack) of buffers owned
+by the native handle -- valid until the next `step`/`reset`; clone what must outlive it.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import spaces
+from .config import AGENT_DIRECTIONS, PROFILE_NAMES, RNG_PHILOX, RNG_TAPE, HostConfig, make_config
+from ._names import ROUTE_NAMES
+from .raw import RawEnv
+
+
+def _device_index(device) -> int:
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise RuntimeError("PGTGVectorEnv runs on CUDA devices only (there is no CPU fallback)")
+    return torch.cuda.current_device() if d.index is None else d.index
+
+
+class PGTGVectorEnv:
+    metadata = {"render_modes": []}
+
+    def __init__(self, num_envs: int = 1, map_path: str | None = None, *, device="cuda", conformance_draws=None,
+                 **kwargs: Any):
+        if not torch.cuda.is_available():
+            raise RuntimeError("PGTGVectorEnv needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device_index = _device_index(device)
+        self.device = torch.device("cuda", self.device_index)
+        if conformance_draws is not None:
+            kwargs["rng_mode"] = RNG_TAPE
+        self.hc: HostConfig = make_config(map_path, num_envs=num_envs, **kwargs)
+        self.num_envs = num_envs
+        with torch.cuda.device(self.device):
+            self.raw = RawEnv(self.hc, device=self.device_index)
+            self._t = {}
+            for name in ("obs_map", "obs_position", "obs_velocity", "obs_next_subgoal_direction", "reward", "cost",
+                         "terminated", "truncated", "step_state", "step_flags", "stats"):
+                self._t[name] = torch.from_dlpack(self.raw.dlpack_capsule(name))
+            if self.hc.pod.write_final_obs:
+                for name in ("final_obs_map", "final_obs_position", "final_obs_velocity", "final_obs_next_subgoal_direction"):
+                    self._t[name] = torch.from_dlpack(self.raw.dlpack_capsule(name))
+            self._actions = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
+        if conformance_draws is not None:
+            self.raw.load_draws(*conformance_draws)
+        self._terminated = self._t["terminated"].view(torch.bool)
+        self._truncated = self._t["truncated"].view(torch.bool)
+
+        P = self.hc.window
+        kw = self.hc.kwargs
+        self.use_next_subgoal_direction = bool(kw["use_next_subgoal_direction"])
+        self.separate_reward_cost = bool(kw["separate_reward_cost"])
+        self.single_action_space = spaces.Discrete(9)
+        obs_space = {
+            "position": spaces.MultiDiscrete([9, 9], dtype=np.int32),
+            "velocity": spaces.Box(low=-99, high=99, shape=(2,), dtype=np.int32),
+            "map": spaces.Dict({k: spaces.MultiBinary((P, P)) for k in self.hc.observation_keys}),
+        }
+        if self.use_next_subgoal_direction:
+            obs_space["next_subgoal_direction"] = spaces.Discrete(9, start=-1)
+        self.single_observation_space = spaces.Dict(obs_space)
+        self.action_space = spaces.MultiDiscrete([9] * num_envs)
+        self.observation_space = spaces.batch_space(self.single_observation_space, num_envs)
+        self._was_reset = False
+
+    # ---- Gymnasium vector API ----------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _observation(self, final: bool = False) -> dict:
+        pre = "final_" if final else ""
+        m = self._t[pre + "obs_map"]
+        obs = {
+            "position": self._t[pre + "obs_position"],
+            "velocity": self._t[pre + "obs_velocity"],
+            "map": {k: m[:, i] for i, k in enumerate(self.hc.observation_keys)},
+        }
+        if self.use_next_subgoal_direction:
+            obs["next_subgoal_direction"] = self._t[pre + "obs_next_subgoal_direction"]
+        return obs
+
+    def reset(self, *, seed: int | list | np.ndarray | None = None, options: dict | None = None):
+        seeds = None
+        if seed is not None:
+            seeds = np.asarray(seed, dtype=np.int64)
+            if seeds.ndim == 0:
+                seeds = int(seeds) + np.arange(self.num_envs, dtype=np.int64)
+            if seeds.shape != (self.num_envs,):
+                raise ValueError("seed must be an int or one seed per env")
+        with torch.cuda.device(self.device):
+            self.raw.reset(seeds, None, self._stream())
+        self._was_reset = True
+        return self._observation(), self._info(reset=True)
+
+    def _info(self, reset: bool = False) -> dict:
+        ss = self._t["step_state"]
+        info: dict[str, Any] = {}
+        if not reset:
+            fl = self._t["step_flags"]
+            info.update(x=ss[:, 0], y=ss[:, 1], x_velocity=ss[:, 2], y_velocity=ss[:, 3],
+                        flat_tire=(fl & 1).bool(), braking_applied=(fl & 2).bool())
+            if self.separate_reward_cost:
+                info["cost"] = self._t["cost"]
+                info["safety_cost"] = self._t["cost"]
+                info["performance_reward"] = self._t["reward"]
+            if self.hc.pod.write_final_obs:
+                info["final_observation"] = self._observation(final=True)
+                info["_final_observation"] = self._terminated | self._truncated
+        return info
+
+    def step(self, actions):
+        if not self._was_reset:
+            raise RuntimeError("step() called before reset()")
+        with torch.cuda.device(self.device):
+            if isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype in (torch.int32, torch.int64) \
+                    and actions.is_contiguous() and actions.shape == (self.num_envs,):
+                ptr, nbytes = actions.data_ptr(), actions.element_size()
+            else:
+                a = torch.as_tensor(np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions), dtype=torch.int32)
+                if a.shape != (self.num_envs,):
+                    raise ValueError(f"expected {self.num_envs} actions")
+                self._actions.copy_(a, non_blocking=True)
+                ptr, nbytes = self._actions.data_ptr(), 4
+            self.raw.step_device(ptr, nbytes, self._stream())
+        return self._observation(), self._t["reward"], self._terminated, self._truncated, self._info()
+
+    def step_host(self, actions: np.ndarray, out: dict | None = None) -> dict:
+        """The same tick through HOST buffers (`pgtg_step_host`): copies in and out inside the call.
+        This is the entry a non-CUDA consumer (the reference-facing plugin boundary) uses."""
+        N, C, P = self.num_envs, self.hc.pod.num_channels, self.hc.window
+        if out is None:
+            out = dict(obs_map=np.empty((N, C, P, P), np.int8), obs_position=np.empty((N, 2), np.int32),
+                       obs_velocity=np.empty((N, 2), np.int32), reward=np.empty(N, np.float64),
+                       terminated=np.empty(N, np.uint8), truncated=np.empty(N, np.uint8))
+        with torch.cuda.device(self.device):
+            self.raw.step_host(actions, stream=self._stream(), **out)
+        return out
+
+    def close(self):
+        self.raw.close()
+
+    # ---- reference extras ------------------------------------------------------------------------
+    def add_traffic_rule(self, rule_dict: dict):
+        """PGTGEnv.add_traffic_rule (environment.py:569-571)."""
+        if any(r["name"] == rule_dict["name"] for r in self.hc.rules):
+            raise ValueError(f"Rule with name {rule_dict['name']} already exists.")
+        self.hc.rules.append(rule_dict)
+        self.raw.update_rules(self.hc.rules)
+
+    def remove_traffic_rule(self, rule_name: str) -> bool:
+        """PGTGEnv.remove_traffic_rule (environment.py:573-575)."""
+        for i, r in enumerate(self.hc.rules):
+            if r["name"] == rule_name:
+                del self.hc.rules[i]
+                self.raw.update_rules(self.hc.rules)
+                return True
+        return False
+
+    def get_state(self) -> dict:
+        """Host snapshot of every env (the tensors behind PGTGEnv.get_info, environment.py:1538)."""
+        return self.raw.get_state()
+
+    def get_info_dicts(self) -> list[dict]:
+        """Per-env dicts shaped like PGTGEnv.get_info() (debugging aid; synchronises)."""
+        st = self.raw.get_state()
+        out = []
+        for i in range(self.num_envs):
+            cars = [dict(id=int(c[0]), x=int(c[1]), y=int(c[2]), route=ROUTE_NAMES[c[3]], driver_profile=PROFILE_NAMES[c[4]],
+                         patience_counter=int(c[5])) for c in st["cars"][i, : st["num_cars"][i]]]
+            out.append(dict(x=int(st["agent"][i, 0]), y=int(st["agent"][i, 1]), x_velocity=int(st["agent"][i, 2]),
+                            y_velocity=int(st["agent"][i, 3]), flat_tire=bool(st["flat_tire"][i]), cars=cars))
+        return out
+
+    def set_to_state(self, agent=None, flat_tire=None, num_cars=None, cars=None):
+        """PGTGEnv.set_to_state (environment.py:1301-1342) for all envs: position, velocity,
+        flat_tire and cars only; returns the refreshed observation."""
+        with torch.cuda.device(self.device):
+            self.raw.set_state(agent=agent, flat_tire=flat_tire, num_cars=num_cars, cars=cars)
+            self.raw.observe(self._stream())
+        return self._observation(), self._info(reset=True)
+
+    def episode_stats(self, reset: bool = False, all_reduce: bool = True) -> dict:
+        """Episode statistics accumulated on the device since the last reset of the counters.
+        With torch.distributed initialised the 8 doubles are summed over ranks with one NCCL
+        all-reduce -- the only collective in the system."""
+        with torch.cuda.device(self.device):
+            _check(self.raw, self.raw.lib.pgtg_reduce_stats(self.raw._h, self._stream()))
+            s = self._t["stats"].clone()
+            if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(s)
+            if reset:
+                _check(self.raw, self.raw.lib.pgtg_reset_stats(self.raw._h, self._stream()))
+        v = s.cpu().tolist()
+        n = max(v[0], 1.0)
+        return dict(episodes=v[0], mean_return=v[1] / n, mean_length=v[2] / n, goals=v[3], crashes=v[4], truncations=v[5])
+
+    def launch_count(self) -> int:
+        return self.raw.launch_count()
+
+
+def _check(raw, rc):
+    from . import _lib
+
+    _lib.check(raw.lib, rc)
+
+
+def make_vec(num_envs: int, **kwargs) -> PGTGVectorEnv:
+    """`gymnasium.make("pgtg-v4", **kwargs)` rollouts, batched (the reference registers pgtg-v4,
+    pgtg/__init__.py:7)."""
+    return PGTGVectorEnv(num_envs, **kwargs)

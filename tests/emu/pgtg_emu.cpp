@@ -22,6 +22,8 @@ static const char* bk_error() { return "emu"; }
 static int bk_dl_device_type() { return 1; }  // kDLCPU
 static int bk_pick_block(const pgtg::DevCfg&, int* block, size_t* smem) { *block = 128; *smem = 0; return 0; }
 static int bk_launch(pgtg_env*, int, const uint8_t*, const int64_t*, const void*, int, void*);
+static int bk_stats_reduce(pgtg_env*, void*);
+static int bk_stats_reset(pgtg_env*, void*);
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
@@ -85,7 +87,11 @@ static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* 
 
 extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
   if (!e || !e->did_reset) return fail(PGTG_ERR_STATE, "observe before reset");
-  bk_launch(e, 2, nullptr, nullptr, nullptr, 0, stream);
+  bk_launch(e, MODE_OBSERVE, nullptr, nullptr, nullptr, 0, stream);
   e->launches++;
   return PGTG_OK;
 }
+
+// the emulation accumulates straight into the 8-double stats buffer
+static int bk_stats_reduce(pgtg_env*, void*) { return 0; }
+static int bk_stats_reset(pgtg_env* e, void*) { memset(e->dp.stats, 0, 64); return 0; }

@@ -19,7 +19,25 @@ def trace_kwargs(tr):
     for k in ("random_map_start_position", "random_map_goal_position", "traffic_light_phases_duration"):
         if isinstance(kw.get(k), list):
             kw[k] = tuple(kw[k])
+    if "map_plan" in kw:  # fixed maps travel inside the trace
+        kw["map_plan"] = tr["meta"]["maps"][kw["map_plan"]]
+    kw["num_envs"] = tr["meta"]["num_envs"]
+    kw["max_episode_steps"] = tr["meta"]["max_episode_steps"]
     return kw
+
+
+def golden_traces():
+    import glob
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(glob.glob(os.path.join(here, "trace_*.npz")))
+
+
+def trace_id(path):
+    import os
+
+    return os.path.basename(path)[len("trace_"):-len(".npz")]
 
 
 def _eq(name, a, b, t):
