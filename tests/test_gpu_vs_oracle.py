@@ -1,0 +1,73 @@
+"""GPU vs oracle in Philox mode, at the BASELINE.json configurations (sizes the oracle finishes in
+seconds) and on ragged / extreme shapes. Bit-exact: integers, bytes and float64 rewards."""
+import warnings
+
+import numpy as np
+import pytest
+
+import philox_compare as pc
+from oracle.oracle import OracleVectorEnv
+
+
+def _pair(n, **kw):
+    from native_env import NativeAdapter
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = NativeAdapter("cuda", num_envs=n, final_observation=True, **kw)
+        ora = OracleVectorEnv(num_envs=n, final_observation=True, threads=8, **kw)
+    return env, ora
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(pc.CONFIGS))
+def test_cuda_matches_oracle_small(name):
+    kw, n, ticks = pc.CONFIGS[name]
+    env, ora = _pair(n, seed=4242, **kw)
+    assert pc.compare(env, ora, ticks, state_every=10) > 0
+    env.close(); ora.close()
+
+
+@pytest.mark.gpu
+def test_config2_4096_envs_fixed_map_256_ticks():
+    """BASELINE config 2: 4096 envs on one fixed map, traffic off, no obstacles, 256 ticks."""
+    import json, os
+
+    tr = json.loads(bytes(np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_config2_fixed_map.npz"))["meta"]).decode())
+    plan = tr["maps"]["serpentine_5x3"]
+    env, ora = _pair(4096, seed=7, map_plan=plan)
+    assert pc.compare(env, ora, 256, state_every=64) > 1000
+    env.close(); ora.close()
+
+
+@pytest.mark.gpu
+def test_config3_traffic_obstacles_4k():
+    """BASELINE config 3 settings at 4096 envs x 48 ticks (the oracle's budget)."""
+    env, ora = _pair(4096, seed=11, traffic_density=0.05, random_map_obstacle_probability=0.2)
+    assert pc.compare(env, ora, 48, state_every=16, check_obs_every=4) > 1000
+    env.close(); ora.close()
+
+
+@pytest.mark.gpu
+def test_config4_large_maps_dense_traffic():
+    """BASELINE config 4 settings (8x8 tiles, 80 % connections, traffic 0.2, obstacles 0.5)."""
+    env, ora = _pair(300, seed=3, random_map_width=8, random_map_height=8, random_map_percentage_of_connections=0.8,
+                     traffic_density=0.2, random_map_obstacle_probability=0.5)
+    assert pc.compare(env, ora, 16, state_every=8) > 0
+    env.close(); ora.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 31, 129, 1000])
+def test_ragged_sizes(n):
+    env, ora = _pair(n, seed=5, traffic_density=0.05)
+    pc.compare(env, ora, 20)
+    env.close(); ora.close()
+
+
+@pytest.mark.gpu
+def test_default_64k_envs():
+    """Default settings at 65536 envs: lock-step with the (8-thread) oracle for 12 ticks."""
+    env, ora = _pair(65536, seed=99)
+    assert pc.compare(env, ora, 12, check_obs_every=3) > 100000
+    env.close(); ora.close()
