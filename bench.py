@@ -54,40 +54,56 @@ def algorithmic_bytes(kw: dict) -> float:
     return C * P * P + 16 + 8 + 2 + 1 + 2 * 16 + T * 2 + 2 * ((T + 7) // 8) + 2 * 8 * n_cars
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons DURING the timed region (profiling guide recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (profiling guide recipe):
+    one streaming `nvidia-smi -lms 50` process, rows kept only if sampled inside [begin, end]."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
 
     def stop(self) -> dict:
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        time.sleep(0.12)
+        self.proc.terminate()
+        self.thread.join(timeout=3)
+        rows = [r for t, r in self.rows if self.t_begin - 0.02 <= t <= self.t_end + 0.08 and len(r) >= 10]
+        if not rows:
+            rows = [r for _, r in self.rows[-2:] if len(r) >= 10]
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None  # noqa: E731
+        sm = [num(r[2]) for r in rows if num(r[2]) is not None]
+        mx = [num(r[3]) for r in rows if num(r[3]) is not None]
+        pw = [num(r[4]) for r in rows if num(r[4]) is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[6:10]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
-                    samples=len(self.rows))
+                    power_w_max=max(pw) if pw else None, samples=len(rows))
 
 
 def cpu_baseline(kw: dict, n_envs: int, seconds: float, threads: int) -> dict:
@@ -144,8 +160,8 @@ def run_reference(args, kw, n_cpu):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="default-2M", choices=list(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (overrides the workload's)")
@@ -192,7 +208,10 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)
     barrier()
+    if sampler:
+        sampler.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0.record()
@@ -203,6 +222,8 @@ def main():
     stats = env.episode_stats(all_reduce=True)  # the only collective: 8 doubles, once
     ev1.record()
     barrier()
+    if sampler:
+        sampler.end()
     ms = ev0.elapsed_time(ev1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     launches = env.launch_count() - launches0
@@ -219,17 +240,19 @@ def main():
     out = dict(obs_map=pin((N, C, P, P), torch.int8), obs_position=pin((N, 2), torch.int32), obs_velocity=pin((N, 2), torch.int32),
                reward=pin((N,), torch.float64), terminated=pin((N,), torch.uint8), truncated=pin((N,), torch.uint8))
     hact = [torch.randint(0, 9, (N,), dtype=torch.int32).pin_memory().numpy() for _ in range(2)]
-    env.step_host(hact[0], out)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.e2e_steps):
-        env.step_host(hact[i % 2], out)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * args.e2e_steps / float(t.item())
+    e2e_value = None
+    if args.e2e_steps > 0:
+        env.step_host(hact[0], out)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            env.step_host(hact[i % 2], out)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * N * args.e2e_steps / float(t.item())
     h2d = N * 4
     d2h = sum(v.nbytes for v in out.values())
 
@@ -245,7 +268,7 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload)
-        cpu = cpu_baseline(kw, n_cpu, args.cpu_seconds, os.cpu_count() or 1)
+        cpu = cpu_baseline(kw, n_cpu, args.cpu_seconds, os.cpu_count() or 1) if args.cpu_seconds > 0 else None
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
