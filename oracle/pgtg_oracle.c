@@ -71,7 +71,9 @@ typedef struct {
   /* rng */
   uint64_t seed;     /* philox key */
   uint32_t episode;
-  uint32_t draw_k[5];
+  uint32_t draw_k[5];       /* words consumed per stream this tick */
+  uint32_t blk[4], blk_index; /* cached Philox block of blk_stream */
+  int blk_stream;
   int64_t cursor, tape_end;
   int error;
   /* outputs of the last step */
@@ -118,13 +120,18 @@ void ora_philox(uint32_t ctr[4], uint32_t k0, uint32_t k1) { philox4x32_10(ctr, 
 
 typedef struct { ora_batch* b; ora_env* e; } rctx;
 
-static void philox_draw(rctx* r, int stream, uint32_t out[4]) {
+/* Philox word stream: block b = philox(counter = (b, tick, episode, stream), key = seed), 4 words per
+ * block; an index draw takes one word, a double two consecutive words. */
+static uint32_t philox_word(rctx* r, int stream) {
   ora_env* e = r->e;
-  out[0] = e->draw_k[stream]++;
-  out[1] = (uint32_t)e->elapsed;
-  out[2] = e->episode;
-  out[3] = (uint32_t)stream;
-  philox4x32_10(out, (uint32_t)e->seed, (uint32_t)(e->seed >> 32));
+  uint32_t pos = e->draw_k[stream]++;
+  uint32_t b = pos >> 2;
+  if (e->blk_stream != stream || e->blk_index != b) {
+    e->blk[0] = b; e->blk[1] = (uint32_t)e->elapsed; e->blk[2] = e->episode; e->blk[3] = (uint32_t)stream;
+    philox4x32_10(e->blk, (uint32_t)e->seed, (uint32_t)(e->seed >> 32));
+    e->blk_stream = stream; e->blk_index = b;
+  }
+  return e->blk[pos & 3u];
 }
 
 static double tape_next(rctx* r, int stream, int kind) {
@@ -137,9 +144,8 @@ static double tape_next(rctx* r, int stream, int kind) {
 /* Generator.random() */
 static double rng_double(rctx* r, int stream) {
   if (r->b->cfg.rng_mode == PGTG_RNG_TAPE) return tape_next(r, stream, PGTG_DRAW_DOUBLE);
-  uint32_t w[4];
-  philox_draw(r, stream, w);
-  return ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) / 9007199254740992.0;
+  uint32_t w0 = philox_word(r, stream), w1 = philox_word(r, stream);
+  return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) / 9007199254740992.0;
 }
 
 /* Generator.integers(0, n) / Generator.choice over n items; numpy consumes nothing for n == 1 */
@@ -150,9 +156,7 @@ static int rng_index(rctx* r, int stream, int n) {
     if (v < 0 || v >= n) { r->e->error |= 4; v = 0; }
     return v;
   }
-  uint32_t w[4];
-  philox_draw(r, stream, w);
-  return (int)(((uint64_t)w[0] * (uint64_t)n) >> 32);
+  return (int)(((uint64_t)philox_word(r, stream) * (uint64_t)n) >> 32);
 }
 
 /* Generator.choice(items, p=...): one uniform double, cdf.searchsorted(u, side="right") */
@@ -179,9 +183,7 @@ static void rng_distinct(rctx* r, int stream, int n, int k, int* out) {
       continue;
     }
     for (;;) {
-      uint32_t w[4];
-      philox_draw(r, stream, w);
-      int v = (int)(((uint64_t)w[0] * (uint64_t)n) >> 32);
+      int v = (int)(((uint64_t)philox_word(r, stream) * (uint64_t)n) >> 32);
       int dup = 0;
       for (int q = 0; q < j; q++) if (out[q] == v) { dup = 1; break; }
       if (!dup) { out[j] = v; break; }
@@ -800,7 +802,7 @@ static void env_reset(ora_batch* b, ora_env* e) {
   rctx r = {b, e};
   e->episode++;
   e->elapsed = 0;
-  memset(e->draw_k, 0, sizeof e->draw_k);
+  memset(e->draw_k, 0, sizeof e->draw_k); e->blk_stream = -1;
   if (b->cfg.fixed_map) {
     e->W = b->fw; e->H = b->fh;
     for (int t = 0; t < b->fw * b->fh; t++) {
@@ -832,7 +834,7 @@ static double env_step(ora_batch* b, ora_env* e, int action, double* cost_out) {
   const pgtg_config* c = &b->cfg;
   rctx r = {b, e};
   e->elapsed++;
-  memset(e->draw_k, 0, sizeof e->draw_k);
+  memset(e->draw_k, 0, sizeof e->draw_k); e->blk_stream = -1;
   int light_total = c->light_green + c->light_yellow + c->light_red;
   e->light_counter = (e->light_counter + 1) % light_total; /* :1113-1115 */
   int ax = action / 3 - 1, ay = action % 3 - 1;            /* constants.py:6-16 */

@@ -175,6 +175,10 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   int words = (d.T + 1) / 2;
   if ((words & 1) == 0) words++;  // odd word stride: conflict-free shared-memory rows
   d.tile_stride = words * 2;
+  for (int t = 0; t < d.T; t++) {
+    if (t % d.W < d.W - 1) d.full_e[t >> 5] |= 1u << (t & 31);
+    if (t + d.W < d.T) d.full_s[t >> 5] |= 1u << (t & 31);
+  }
   if (c.already_visited_position_penalty != 0) { d.vis_w = d.HS + 2; d.vis_words = ((d.WS + 2) * (d.HS + 2) + 31) / 32; }
   d.obs_bits = d.C * d.P * d.P;
   d.env_id_base = c.env_id_base; d.seed = c.seed;

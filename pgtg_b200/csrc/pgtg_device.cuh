@@ -126,6 +126,7 @@ struct DevCfg {
   int tile_stride;   // uint16 elements per env in the shared-memory tile stage (odd word count)
   int vis_w, vis_words;  // visited bitmap geometry (0 when the penalty is off)
   int obs_bits;      // C * P * P
+  uint32_t full_e[8], full_s[8];  // full grid graph: bit t = edge t<->t+1 / t<->t+W exists
   int64_t env_id_base;
   uint64_t seed;
 };
@@ -224,13 +225,19 @@ PG_HD void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
   }
 }
 
+// Philox word stream (specification shared with the oracle): for a given (stream, tick, episode)
+// the 32-bit words come from consecutive Philox4x32-10 blocks, block b = philox(counter =
+// (b, tick, episode, stream), key = env seed), 4 words per block. An index draw takes ONE word
+// ((word * n) >> 32); a double takes TWO consecutive words ((w0 >> 5) * 2^26 + (w1 >> 6)) / 2^53.
 template <int RNG>
 struct Rng {
   const DevPtrs& p;
   EnvRegs& e;
   int env;
   uint32_t k0, k1;
-  uint32_t kcount[5];
+  uint32_t kcount[5];  // words consumed per stream this tick
+  uint32_t b0, b1, b2, b3, cur_block;
+  int cur_stream;
   PG_MEMBER Rng(const DevPtrs& p_, EnvRegs& e_, int env_) : p(p_), e(e_), env(env_) {
     if (RNG == PGTG_RNG_PHILOX) {
       uint64_t key = p.key[env];
@@ -238,11 +245,18 @@ struct Rng {
     }
 #pragma unroll
     for (int i = 0; i < 5; i++) kcount[i] = 0;
+    cur_stream = -1; cur_block = 0; b0 = b1 = b2 = b3 = 0;
   }
-  PG_MEMBER void block(int stream, uint32_t& w0, uint32_t& w1) {
-    uint32_t c0 = kcount[stream]++, c1 = e.elapsed, c2 = e.episode, c3 = (uint32_t)stream;
-    philox4x32_10(c0, c1, c2, c3, k0, k1);
-    w0 = c0; w1 = c1;
+  PG_MEMBER uint32_t word(int stream) {
+    uint32_t pos = kcount[stream]++;
+    uint32_t b = pos >> 2;
+    if (stream != cur_stream || b != cur_block) {
+      b0 = b; b1 = e.elapsed; b2 = e.episode; b3 = (uint32_t)stream;
+      philox4x32_10(b0, b1, b2, b3, k0, k1);
+      cur_stream = stream; cur_block = b;
+    }
+    uint32_t j = pos & 3u;
+    return j == 0 ? b0 : j == 1 ? b1 : j == 2 ? b2 : b3;
   }
   PG_MEMBER double tape_next(int stream, int kind) {
     if (e.cursor >= p.tape_end[env]) { e.err |= 1; return 0.0; }
@@ -252,8 +266,7 @@ struct Rng {
   // Generator.random()
   PG_MEMBER double uniform(int stream) {
     if (RNG == PGTG_RNG_TAPE) return tape_next(stream, PGTG_DRAW_DOUBLE);
-    uint32_t w0, w1;
-    block(stream, w0, w1);
+    uint32_t w0 = word(stream), w1 = word(stream);
     return pg_ddiv(pg_dadd(pg_dmul((double)(w0 >> 5), 67108864.0), (double)(w1 >> 6)), 9007199254740992.0);
   }
   // Generator.integers(0, n) / choice over n items; nothing is consumed for n == 1
@@ -264,9 +277,7 @@ struct Rng {
       if (v < 0 || v >= n) { e.err |= 4; v = 0; }
       return v;
     }
-    uint32_t w0, w1;
-    block(stream, w0, w1);
-    return (int)pg_umulhi(w0, (uint32_t)n);
+    return (int)pg_umulhi(word(stream), (uint32_t)n);
   }
   // Generator.choice(items, p=...): cdf.searchsorted(u, side="right")
   PG_MEMBER int choice_cdf(int stream, const double* cdf, int n) {

@@ -39,7 +39,7 @@ struct StatsArgs {
   double* rows;  // [gridDim.x][8]
 };
 
-template <int RNG, int MODE>
+template <int RNG, int MODE, int TMAX>
 __global__ void __launch_bounds__(128) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
                                                         const void* __restrict__ actions, int action_bytes, StatsArgs sa) {
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) pgtg_tick_kernel(const __grid_constant__ 
   if (MODE != MODE_OBSERVE) {
     if (tid < n_done) {
       int local = sh.done_list[tid];
-      phase_reset<RNG>(c, p, sh, local, env0 + local);
+      phase_reset<RNG, TMAX>(c, p, sh, local, env0 + local);
     }
     __syncthreads();
   }
@@ -150,9 +150,9 @@ static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem) {
   return -1;
 }
 
-template <int RNG, int MODE>
+template <int RNG, int MODE, int TMAX>
 static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
-  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE>;
+  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX>;
   if (e->smem > 48 * 1024) {
     if (ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem))) return -1;
   }
@@ -161,18 +161,26 @@ static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, co
   return ck(cudaGetLastError());
 }
 
+// TMAX = compile-time bound on the tile count (register-resident boards for the default 4x4 map)
+template <int RNG, int MODE>
+static int launch_sized(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
+  if (e->dc.T <= 16) return launch_one<RNG, MODE, 16>(e, mask, seeds, actions, action_bytes, st);
+  if (e->dc.T <= 64) return launch_one<RNG, MODE, 64>(e, mask, seeds, actions, action_bytes, st);
+  return launch_one<RNG, MODE, 256>(e, mask, seeds, actions, action_bytes, st);
+}
+
 static int bk_launch(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   bool tape = e->cfg.rng_mode == PGTG_RNG_TAPE;
   switch (mode) {
     case MODE_STEP:
-      return tape ? launch_one<PGTG_RNG_TAPE, MODE_STEP>(e, mask, seeds, actions, action_bytes, st)
-                  : launch_one<PGTG_RNG_PHILOX, MODE_STEP>(e, mask, seeds, actions, action_bytes, st);
+      return tape ? launch_sized<PGTG_RNG_TAPE, MODE_STEP>(e, mask, seeds, actions, action_bytes, st)
+                  : launch_sized<PGTG_RNG_PHILOX, MODE_STEP>(e, mask, seeds, actions, action_bytes, st);
     case MODE_RESET:
-      return tape ? launch_one<PGTG_RNG_TAPE, MODE_RESET>(e, mask, seeds, actions, action_bytes, st)
-                  : launch_one<PGTG_RNG_PHILOX, MODE_RESET>(e, mask, seeds, actions, action_bytes, st);
+      return tape ? launch_sized<PGTG_RNG_TAPE, MODE_RESET>(e, mask, seeds, actions, action_bytes, st)
+                  : launch_sized<PGTG_RNG_PHILOX, MODE_RESET>(e, mask, seeds, actions, action_bytes, st);
     default:
-      return launch_one<PGTG_RNG_PHILOX, MODE_OBSERVE>(e, mask, seeds, actions, action_bytes, st);
+      return launch_one<PGTG_RNG_PHILOX, MODE_OBSERVE, 16>(e, mask, seeds, actions, action_bytes, st);
   }
 }
 

@@ -190,9 +190,7 @@ PG_HD void create_initial_traffic(const DevCfg& c, const DevPtrs& p, const MapVi
       if (v < 0 || v >= num_positions) { e.err |= 4; v = 0; }
     } else {
       for (;;) {  // sequential rejection sampling (spec shared with the oracle)
-        uint32_t w0, w1;
-        rng.block(PGTG_STREAM_CAR, w0, w1);
-        v = (int)pg_umulhi(w0, (uint32_t)num_positions);
+        v = (int)pg_umulhi(rng.word(PGTG_STREAM_CAR), (uint32_t)num_positions);
         bool dup = false;
         for (int q = 0; q < j; q++) if ((int)car_slot(c, p, env, q) == v) { dup = true; break; }
         if (!dup) break;
@@ -378,40 +376,78 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
 }
 
 // ---------------------------------------------------------------------------------------------
-// procedural map generation (map_generator.py:43-472) on bitboards
+// procedural map generation (map_generator.py:43-472) on bitboards. TMAX (16 / 64 / 256) is the
+// compile-time bound on the tile count: it sizes the boards (one 32-bit word for the default 4x4
+// map), the alive mask of removable edges and the BFS scratch, so the default case runs entirely
+// in registers.
+template <int TMAX>
 struct Board {
-  uint64_t w[4];
+  static constexpr int NW = (TMAX + 31) / 32;
+  uint32_t w[NW];
 };
-PG_HD bool bget(const Board& b, int i) { return (b.w[i >> 6] >> (i & 63)) & 1ull; }
-PG_HD void bset(Board& b, int i) { b.w[i >> 6] |= 1ull << (i & 63); }
-PG_HD void bclr(Board& b, int i) { b.w[i >> 6] &= ~(1ull << (i & 63)); }
+template <int TMAX> PG_HD bool bget(const Board<TMAX>& b, int i) {
+  if (Board<TMAX>::NW == 1) return (b.w[0] >> i) & 1u;
+  return (b.w[i >> 5] >> (i & 31)) & 1u;
+}
+template <int TMAX> PG_HD void bset(Board<TMAX>& b, int i) {
+  if (Board<TMAX>::NW == 1) b.w[0] |= 1u << i; else b.w[i >> 5] |= 1u << (i & 31);
+}
+template <int TMAX> PG_HD void bclr(Board<TMAX>& b, int i) {
+  if (Board<TMAX>::NW == 1) b.w[0] &= ~(1u << i); else b.w[i >> 5] &= ~(1u << (i & 31));
+}
+template <int TMAX> PG_HD void bzero(Board<TMAX>& b) {
+#pragma unroll
+  for (int k = 0; k < Board<TMAX>::NW; k++) b.w[k] = 0;
+}
+
+// position of the n-th (0-based) set bit, n < popc(v): popcount binary search, no loop
+PG_HD int select32(uint32_t v, int n) {
+  int pos = 0, cnt;
+  cnt = pg_popc(v & 0xFFFFu); if (n >= cnt) { n -= cnt; pos += 16; v >>= 16; }
+  cnt = pg_popc(v & 0xFFu); if (n >= cnt) { n -= cnt; pos += 8; v >>= 8; }
+  cnt = pg_popc(v & 0xFu); if (n >= cnt) { n -= cnt; pos += 4; v >>= 4; }
+  cnt = pg_popc(v & 0x3u); if (n >= cnt) { n -= cnt; pos += 2; v >>= 2; }
+  if (n >= (int)(v & 1u)) pos += 1;
+  return pos;
+}
 
 // start/goal connectivity of the grid graph; E bit i: edge i<->i+1, S bit i: edge i<->i+W
-PG_HDN bool grid_connected(const DevCfg& c, const Board& E, const Board& S, int s, int g) {
+template <int TMAX>
+PG_HD bool grid_connected(const DevCfg& c, const Board<TMAX>& E, const Board<TMAX>& S, int s, int g) {
   if (s == g) return true;
-  if (c.T <= 64) {
-    uint64_t e = E.w[0], so = S.w[0], reach = 1ull << s, goal = 1ull << g;
+  if (TMAX <= 32) {  // whole board in one register: flood fill by shifts
+    uint32_t e = E.w[0], so = S.w[0], reach = 1u << s, goal = 1u << g;
+    for (;;) {
+      uint32_t nx = reach | ((reach & e) << 1) | ((reach >> 1) & e) | ((reach & so) << c.W) | ((reach >> c.W) & so);
+      if (nx & goal) return true;
+      if (nx == reach) return false;
+      reach = nx;
+    }
+  } else if (TMAX <= 64) {
+    uint64_t e = (uint64_t)E.w[0] | (uint64_t)E.w[1] << 32, so = (uint64_t)S.w[0] | (uint64_t)S.w[1] << 32;
+    uint64_t reach = 1ull << s, goal = 1ull << g;
     for (;;) {
       uint64_t nx = reach | ((reach & e) << 1) | ((reach >> 1) & e) | ((reach & so) << c.W) | ((reach >> c.W) & so);
       if (nx & goal) return true;
       if (nx == reach) return false;
       reach = nx;
     }
+  } else {
+    Board<TMAX> seen;
+    bzero(seen);
+    uint8_t q[TMAX];
+    int qh = 0, qt = 0;
+    bset(seen, s); q[qt++] = (uint8_t)s;
+    while (qh < qt) {
+      int n = q[qh++];
+      if (n == g) return true;
+      int cand[4] = {n - c.W, n + 1, n + c.W, n - 1};
+      bool ok[4] = {n >= c.W && bget(S, n - c.W), bget(E, n), bget(S, n), n > 0 && bget(E, n - 1)};
+      for (int k = 0; k < 4; k++)
+        if (ok[k] && !bget(seen, cand[k])) { bset(seen, cand[k]); q[qt++] = (uint8_t)cand[k]; }
+    }
+    return false;
   }
-  Board seen; seen.w[0] = seen.w[1] = seen.w[2] = seen.w[3] = 0;
-  uint8_t q[PGTG_MAX_TILES];
-  int qh = 0, qt = 0;
-  bset(seen, s); q[qt++] = (uint8_t)s;
-  while (qh < qt) {
-    int n = q[qh++];
-    if (n == g) return true;
-    int x = n % c.W;
-    int cand[4] = {n - c.W, n + 1, n + c.W, n - 1};
-    bool ok[4] = {n >= c.W && bget(S, n - c.W), x < c.W - 1 && bget(E, n), n + c.W < c.T && bget(S, n), x > 0 && bget(E, n - 1)};
-    for (int k = 0; k < 4; k++)
-      if (ok[k] && !bget(seen, cand[k])) { bset(seen, cand[k]); q[qt++] = (uint8_t)cand[k]; }
-  }
-  return false;
 }
 
 template <int RNG>
@@ -437,9 +473,8 @@ PG_HD int random_direction(const DevCfg& c, Rng<RNG>& rng, int x, int y) {
 }
 
 template <int RNG>
-PG_HDN void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng) {
+PG_HDN void choose_start_goal(const DevCfg& c, Rng<RNG>& rng, int& sx, int& sy, int& sd, int& gx, int& gy, int& gd) {
   // chose_random_start_and_goal_position_and_direction (:475-568)
-  int sx = c.start_x, sy = c.start_y, sd = c.start_dir, gx = c.goal_x, gy = c.goal_y, gd = c.goal_dir;
   if (c.start_mode == 2) random_border_position<RNG>(c, rng, sx, sy);
   if (c.goal_mode == 2) random_border_position<RNG>(c, rng, gx, gy);
   if (c.min_sg_dist >= 0)
@@ -455,48 +490,63 @@ PG_HDN void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
     if (c.goal_mode == 2) random_border_position<RNG>(c, rng, gx, gy);
     if (c.goal_mode != 0) gd = random_direction<RNG>(c, rng, gx, gy);
   }
+}
+
+template <int RNG, int TMAX>
+PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng) {
+  int sx = c.start_x, sy = c.start_y, sd = c.start_dir, gx = c.goal_x, gy = c.goal_y, gd = c.goal_dir;
+  if (c.start_mode != 0 || c.goal_mode != 0) choose_start_goal<RNG>(c, rng, sx, sy, sd, gx, gy, gd);
   int W = c.W, T = c.T;
   int st = sy * W + sx, gt = gy * W + gx;
 
-  // generate_map_graph (:192-266). The full grid; an edge picked from removable_edges (edges()
-  // order, host table) stays removed iff start and goal remain connected -- which is what the
-  // reference's "on the BFS path? then is_connected? else restore" amounts to, independent of
-  // BFS tie-breaking.
-  Board E, S;
-  E.w[0] = E.w[1] = E.w[2] = E.w[3] = 0; S = E;
-  for (int t = 0; t < T; t++) {
-    if (t % W < W - 1) bset(E, t);
-    if (t + W < T) bset(S, t);
-  }
-  uint32_t alive[MAX_EDGE_TAB / 32];
+  // generate_map_graph (:192-266). The full grid (host-built masks); an edge picked from
+  // removable_edges (edges() order, host table) stays removed iff start and goal remain connected
+  // -- which is what the reference's "on the BFS path? then is_connected? else restore" amounts
+  // to, independent of BFS tie-breaking.
+  Board<TMAX> E, S;
+#pragma unroll
+  for (int k = 0; k < Board<TMAX>::NW; k++) { E.w[k] = c.full_e[k]; S.w[k] = c.full_s[k]; }
+  constexpr int AW = (4 * TMAX + 31) / 32;
+  uint32_t alive[AW];
   int n_tab = c.n_edge_tab, n_alive = n_tab, cur = n_tab;
-  for (int i = 0; i < (n_tab + 31) / 32; i++) alive[i] = (i * 32 + 32 <= n_tab) ? 0xFFFFFFFFu : ((1u << (n_tab & 31)) - 1u);
+#pragma unroll
+  for (int i = 0; i < AW; i++) alive[i] = (i * 32 + 32 <= n_tab) ? 0xFFFFFFFFu : (i * 32 < n_tab ? ((1u << (n_tab & 31)) - 1u) : 0u);
   while (cur > c.edges_to_keep && n_alive > 0) {  // :245
     int idx = rng.index(PGTG_STREAM_MAP, n_alive);  // :249
-    int wi = 0;
-    for (;; wi++) { int pc = pg_popc(alive[wi]); if (idx < pc) break; idx -= pc; }
-    uint32_t word = alive[wi];
-    while (idx--) word &= word - 1;
-    int i = wi * 32 + pg_ffs(word) - 1;
+    int i;
+    if (AW == 2) {  // default 4x4 map: 48 directed edges in two registers
+      int pc0 = pg_popc(alive[0]);
+      bool hi = idx >= pc0;
+      i = select32(hi ? alive[1] : alive[0], hi ? idx - pc0 : idx) + (hi ? 32 : 0);
+    } else {
+      int wi = 0;
+      for (;; wi++) { int pc = pg_popc(alive[wi]); if (idx < pc) break; idx -= pc; }
+      i = wi * 32 + select32(alive[wi], idx);
+    }
     int j = pg_ldg(&p.edge_rev[i]);
-    alive[i >> 5] &= ~(1u << (i & 31));
-    alive[j >> 5] &= ~(1u << (j & 31));
+    if (AW == 2) {
+      uint64_t clr = ~((1ull << i) | (1ull << j));
+      alive[0] &= (uint32_t)clr; alive[1] &= (uint32_t)(clr >> 32);
+    } else {
+      alive[i >> 5] &= ~(1u << (i & 31));
+      alive[j >> 5] &= ~(1u << (j & 31));
+    }
     n_alive -= 2;
     unsigned ab = pg_ldg(&p.edge_tab[i]);
     int a = ab & 255, b = ab >> 8;
     int lo = a < b ? a : b;
     bool horiz = (a > b ? a - b : b - a) == 1;
     if (horiz) bclr(E, lo); else bclr(S, lo);
-    if (grid_connected(c, E, S, st, gt)) cur -= 2;
+    if (grid_connected<TMAX>(c, E, S, st, gt)) cur -= 2;
     else { if (horiz) bset(E, lo); else bset(S, lo); }
   }
-  // map_graph_to_tile_map_object (:269-334)
+  // map_graph_to_tile_map_object (:269-334); an E bit is only ever set left of the last column
   for (int t = 0; t < T; t++) {
     int ex = 0;
     if (t >= W && bget(S, t - W)) ex |= 1;
     if (bget(E, t)) ex |= 2;
     if (bget(S, t)) ex |= 4;
-    if (t % W > 0 && bget(E, t - 1)) ex |= 8;
+    if (t > 0 && bget(E, t - 1)) ex |= 8;
     m.tiles[t] = (uint16_t)ex;
   }
   m.tiles[st] |= (uint16_t)(1 << sd);
@@ -506,9 +556,10 @@ PG_HDN void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
   int n_slots = c.n_border_slots;
   for (int k = 0; k < c.border_connections && n_slots > 0; k++) {
     int idx = rng.index(PGTG_STREAM_MAP, n_slots);  // :367
-    uint64_t sl = slots;
-    while (idx--) sl &= sl - 1;
-    int i = pg_popcll((sl & (~sl + 1)) - 1);
+    uint32_t lo32 = (uint32_t)slots, hi32 = (uint32_t)(slots >> 32);
+    int pc0 = pg_popc(lo32);
+    bool hi = idx >= pc0;
+    int i = select32(hi ? hi32 : lo32, hi ? idx - pc0 : idx) + (hi ? 32 : 0);
     slots &= ~(1ull << i);
     n_slots--;
     unsigned v = pg_ldg(&p.border_slots[i]);
@@ -544,41 +595,78 @@ PG_HDN void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
 // parse_map_object's path part (parser.py:27-37, 158-164): Dijkstra with unit weights and
 // (cost, push counter) keys == FIFO BFS, successors in N, E, S, W insertion order
 // (parse_tile_map_to_graph, parser.py:244-276), first-discovered predecessor.
-PG_HDN void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
-  int W = c.W, H = c.H, T = c.T;
+template <int TMAX>
+PG_HD void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
+  int W = c.W, T = c.T;
   int st = plan_sy(e.plan) * W + plan_sx(e.plan), gt = plan_gy(e.plan) * W + plan_gx(e.plan);
-  uint8_t q[PGTG_MAX_TILES], prev[PGTG_MAX_TILES];
-  Board seen; seen.w[0] = seen.w[1] = seen.w[2] = seen.w[3] = 0;
-  int qh = 0, qt = 0;
-  bool found = false;
-  bset(seen, st); q[qt++] = (uint8_t)st;
-  while (qh < qt) {
-    int n = q[qh++];
-    if (n == gt) { found = true; break; }
-    int ex = td_exits(m.tiles[n]), x = n % W, y = n / W;
-    int cand[4] = {n - W, n + 1, n + W, n - 1};
-    bool ok[4] = {(ex & 1) && y > 0, (ex & 2) && x < W - 1, (ex & 4) && y < H - 1, (ex & 8) && x > 0};
-    for (int k = 0; k < 4; k++)
-      if (ok[k] && !bget(seen, cand[k])) { bset(seen, cand[k]); prev[cand[k]] = (uint8_t)n; q[qt++] = (uint8_t)cand[k]; }
-  }
   for (int t = 0; t < T; t++) m.tiles[t] &= 0x07FF;  // clear subgoal dir + used
-  int ns = 1;
   m.tiles[gt] |= (uint16_t)((1 + plan_gd(e.plan)) << 11);  // final tile carries the goal direction (parser.py:158)
-  if (!found) e.err |= 8;
-  else {
-    int cur = gt;
-    while (cur != st) {
-      int pr = prev[cur];
-      int d = cur == pr - W ? 0 : cur == pr + 1 ? 1 : cur == pr + W ? 2 : 3;  // find_direction (parser.py:279-306)
-      m.tiles[pr] |= (uint16_t)((1 + d) << 11);
-      cur = pr; ns++;
+  int ns = 1;
+  bool found = false;
+  // a tile has an east / west neighbour iff the full grid has that edge
+  auto has_e = [&](int n) { return (c.full_e[n >> 5] >> (n & 31)) & 1u; };
+  if (TMAX <= 16) {
+    // queue and predecessors as packed nibbles: the whole BFS in registers
+    uint64_t q = (uint64_t)st, prev = 0;
+    uint32_t seen = 1u << st;
+    int qh = 0, qt = 1;
+    while (qh < qt) {
+      int n = (int)((q >> (4 * qh)) & 15u);
+      qh++;
+      if (n == gt) { found = true; break; }
+      int ex = td_exits(m.tiles[n]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        int cand = k == 0 ? n - W : k == 1 ? n + 1 : k == 2 ? n + W : n - 1;
+        bool ok = k == 0 ? ((ex & 1) && n >= W) : k == 1 ? ((ex & 2) && has_e(n)) : k == 2 ? ((ex & 4) && n + W < T) : ((ex & 8) && n > 0 && has_e(n - 1));
+        if (ok && !((seen >> cand) & 1u)) {
+          seen |= 1u << cand;
+          prev |= (uint64_t)n << (4 * cand);
+          q |= (uint64_t)cand << (4 * qt);
+          qt++;
+        }
+      }
+    }
+    if (found) {
+      int cur = gt;
+      while (cur != st) {
+        int pr = (int)((prev >> (4 * cur)) & 15u);
+        int d = cur == pr - W ? 0 : cur == pr + 1 ? 1 : cur == pr + W ? 2 : 3;  // find_direction (parser.py:279-306)
+        m.tiles[pr] |= (uint16_t)((1 + d) << 11);
+        cur = pr; ns++;
+      }
+    }
+  } else {
+    uint8_t q[TMAX], prev[TMAX];
+    Board<TMAX> seen;
+    bzero(seen);
+    int qh = 0, qt = 0;
+    bset(seen, st); q[qt++] = (uint8_t)st;
+    while (qh < qt) {
+      int n = q[qh++];
+      if (n == gt) { found = true; break; }
+      int ex = td_exits(m.tiles[n]);
+      int cand[4] = {n - W, n + 1, n + W, n - 1};
+      bool ok[4] = {(ex & 1) && n >= W, (ex & 2) && has_e(n), (ex & 4) && n + W < T, (ex & 8) && n > 0 && has_e(n - 1)};
+      for (int k = 0; k < 4; k++)
+        if (ok[k] && !bget(seen, cand[k])) { bset(seen, cand[k]); prev[cand[k]] = (uint8_t)n; q[qt++] = (uint8_t)cand[k]; }
+    }
+    if (found) {
+      int cur = gt;
+      while (cur != st) {
+        int pr = prev[cur];
+        int d = cur == pr - W ? 0 : cur == pr + 1 ? 1 : cur == pr + W ? 2 : 3;
+        m.tiles[pr] |= (uint16_t)((1 + d) << 11);
+        cur = pr; ns++;
+      }
     }
   }
+  if (!found) e.err |= 8;
   e.plan = (e.plan & 0xFFFFFu) | (unsigned)ns << 20;
 }
 
-template <int RNG>
-PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
+template <int RNG, int TMAX>
+PG_HDN void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
   // PGTGEnv.reset (environment.py:581-656)
   e.episode++;
   e.elapsed = 0;
@@ -587,9 +675,9 @@ PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
     for (int t = 0; t < c.T; t++) m.tiles[t] = pg_ldg(&p.fixed_tiles[t]);
     e.plan = p.fixed_plan;
   } else {
-    generate_map<RNG>(c, p, m, e, rng);
+    generate_map<RNG, TMAX>(c, p, m, e, rng);
   }
-  assign_subgoals(c, m, e);
+  assign_subgoals<TMAX>(c, m, e);
   m.plan = e.plan;
   e.flags |= EF_TILES_DIRTY | EF_RESET;
   // self.position = map_rng.choice(self.map.starters) (:635); starters in x-major order

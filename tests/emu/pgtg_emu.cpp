@@ -27,7 +27,7 @@ static int bk_stats_reset(pgtg_env*, void*);
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
-template <int RNG>
+template <int RNG, int TMAX>
 static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes,
                       int blk, unsigned char* smem) {
   const DevCfg& c = h->dc;
@@ -66,7 +66,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
   } else {
     for (int t = 0; t < nvalid; t++) sh.regs[t] = load_regs(c, p, env0 + t);
   }
-  for (int k = 0; k < n_done; k++) phase_reset<RNG>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+  for (int k = 0; k < n_done; k++) phase_reset<RNG, TMAX>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
   for (int t = 0; t < nvalid; t++) phase_emit(c, p, sh, t, env0 + t, false);
   for (int t = 0; t < B; t++) phase_expand(c, p.obs_map, sh, t, B, env0, nvalid);
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
@@ -78,8 +78,13 @@ static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* 
   int nblk = (h->dc.N + h->block - 1) / h->block;
   for (int b = 0; b < nblk; b++) {
     memset(smem, 0xA5, bytes);  // shared memory starts undefined on the device too
-    if (h->cfg.rng_mode == PGTG_RNG_TAPE) run_block<PGTG_RNG_TAPE>(h, mode, mask, seeds, actions, action_bytes, b, smem);
-    else run_block<PGTG_RNG_PHILOX>(h, mode, mask, seeds, actions, action_bytes, b, smem);
+    bool tape = h->cfg.rng_mode == PGTG_RNG_TAPE;
+    int T = h->dc.T;  // same TMAX dispatch as the CUDA backend
+#define RUN(R, M) run_block<R, M>(h, mode, mask, seeds, actions, action_bytes, b, smem)
+    if (T <= 16) { if (tape) RUN(PGTG_RNG_TAPE, 16); else RUN(PGTG_RNG_PHILOX, 16); }
+    else if (T <= 64) { if (tape) RUN(PGTG_RNG_TAPE, 64); else RUN(PGTG_RNG_PHILOX, 64); }
+    else { if (tape) RUN(PGTG_RNG_TAPE, 256); else RUN(PGTG_RNG_PHILOX, 256); }
+#undef RUN
   }
   free(smem);
   return 0;
