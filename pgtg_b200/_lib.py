@@ -56,7 +56,7 @@ _cache: dict[str, C.CDLL] = {}
 
 
 def load(path: str | None = None) -> C.CDLL:
-    path = path or LIB_PATH
+    path = path or os.environ.get("PGTG_B200_LIB") or LIB_PATH  # env override: A/B builds of the same CUDA library
     if path in _cache:
         return _cache[path]
     if not os.path.exists(path):

@@ -170,6 +170,7 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   }
   d.separate_reward_cost = c.separate_reward_cost; d.num_rules = c.num_rules; d.max_episode_steps = c.max_episode_steps;
   d.write_final_obs = c.write_final_obs;
+  for (int i = 0; i < c.num_rules; i++) if (c.rules[i].min_traffic <= 0 && c.rules[i].min_matching_traffic <= 0) d.rules_without_traffic = 1;
   d.max_cars = c.max_cars > 0 ? c.max_cars : 1;
   d.lut_radius = (d.WS > d.HS ? d.WS : d.HS) + 2;
   int words = (d.T + 1) / 2;
@@ -183,6 +184,8 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   d.obs_bits = d.C * d.P * d.P;
   d.env_id_base = c.env_id_base; d.seed = c.seed;
   if (!c.fixed_map) {
+    d.n_edge_tab = 2 * (d.W * (d.H - 1) + d.H * (d.W - 1));
+    d.n_border_slots = 2 * d.W + 2 * d.H - 2;
     int n_slots = 2 * d.W + 2 * d.H - 2;
     if (c.border_connections < 0 || c.border_connections > n_slots) { why = "random_map_percentage_of_connections must be in [0, 1]"; return -1; }
     if (c.edges_to_keep < 0) { why = "random_map_percentage_of_connections must be in [0, 1]"; return -1; }
@@ -240,8 +243,10 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   if (!cfg->fixed_map) {
     build_edge_tables(dc.W, dc.H, e->edge_tab, e->edge_rev);
     build_border_slots(dc.W, dc.H, e->border_slots);
-    e->dc.n_edge_tab = (int)e->edge_tab.size();
-    e->dc.n_border_slots = (int)e->border_slots.size();
+    if (e->dc.n_edge_tab != (int)e->edge_tab.size() || e->dc.n_border_slots != (int)e->border_slots.size()) {
+      pgtg_destroy(e);
+      return fail(PGTG_ERR_INVALID, "internal: map table sizes");
+    }
     uint16_t* t1 = dev_alloc<uint16_t>(e, e->edge_tab.size() + 1);
     uint16_t* t2 = dev_alloc<uint16_t>(e, e->edge_rev.size() + 1);
     uint16_t* t3 = dev_alloc<uint16_t>(e, e->border_slots.size() + 1);
@@ -316,6 +321,8 @@ extern "C" int pgtg_update_rules(pgtg_env* e, const pgtg_rule* rules, int num_ru
   if (num_rules) bk_h2d((void*)e->dp.rules, rules, sizeof(pgtg_rule) * num_rules, nullptr);
   bk_sync(nullptr);
   e->dc.num_rules = num_rules;
+  e->dc.rules_without_traffic = 0;
+  for (int i = 0; i < num_rules; i++) if (rules[i].min_traffic <= 0 && rules[i].min_matching_traffic <= 0) e->dc.rules_without_traffic = 1;
   e->cfg.num_rules = num_rules;
   return PGTG_OK;
 }

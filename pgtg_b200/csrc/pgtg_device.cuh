@@ -123,6 +123,7 @@ struct DevCfg {
       drv_speed_multiplier[5], drv_reaction_delay[5];
   int drv_min_following[5];
   int separate_reward_cost, num_rules, max_episode_steps, write_final_obs, max_cars, lut_radius;
+  int rules_without_traffic;  // some rule has min_traffic <= 0 and min_matching_traffic <= 0
   int tile_stride;   // uint16 elements per env in the shared-memory tile stage (odd word count)
   int vis_w, vis_words;  // visited bitmap geometry (0 when the penalty is off)
   int obs_bits;      // C * P * P
@@ -214,7 +215,10 @@ PG_HD uint32_t misc_pack(int flat, int light, int ncars) { return (uint32_t)flat
 // Random draws (semantic API shared with the oracle, include/pgtg_b200.h):
 //   tape   : draws recorded from the reference's five np_random children (environment.py:593-599)
 //   philox : Philox4x32-10, key = env seed, counter = (k, tick, episode, stream)
-PG_HD void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+#ifndef PG_PHILOX_ATTR
+#define PG_PHILOX_ATTR PG_HD
+#endif
+PG_PHILOX_ATTR void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
     uint32_t h0 = pg_umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -300,6 +304,9 @@ struct MapView {
   const Lut& L;
   uint16_t* tiles;  // shared memory, this env's T descriptors
   uint32_t plan;
+  const uint16_t* edge_tab;      // shared-memory copies of the map-generation tables
+  const uint16_t* edge_rev;
+  const uint16_t* border_slots;
   PG_MEMBER bool inside(int x, int y) const { return !(x < 0 || y < 0 || x >= c.WS || y >= c.HS); }  // map.py:44-47
   PG_MEMBER int start_tile() const { return plan_sy(plan) * c.W + plan_sx(plan); }
   PG_MEMBER int goal_tile() const { return plan_gy(plan) * c.W + plan_gx(plan); }

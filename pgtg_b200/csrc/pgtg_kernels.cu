@@ -33,6 +33,9 @@ static int bk_stats_reset(pgtg_env*, void* stream);
 namespace pgtg {
 
 constexpr int STATS_STRIDE = 8;
+#ifndef PGTG_MIN_BLOCKS
+#define PGTG_MIN_BLOCKS 8
+#endif
 
 // per-CTA episode statistics row (no cross-CTA atomics on the hot path)
 struct StatsArgs {
@@ -40,7 +43,7 @@ struct StatsArgs {
 };
 
 template <int RNG, int MODE, int TMAX>
-__global__ void __launch_bounds__(128) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
+__global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
                                                         const void* __restrict__ actions, int action_bytes, StatsArgs sa) {
   extern __shared__ __align__(16) unsigned char smem[];

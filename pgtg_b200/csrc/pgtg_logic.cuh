@@ -34,7 +34,7 @@ PG_HD uint32_t col9(const uint32_t w[3], int lx) {  // the 9 bits of local colum
   return v & 0x1FFu;
 }
 // find == -1: count; else: coordinates of the find-th spawner
-PG_HDN int spawner_scan(const DevCfg& c, const MapView& m, int find, int& ox, int& oy) {
+PG_HDN int spawner_scan(const DevCfg& c, const MapView m, int find, int& ox, int& oy) {
   int n = 0;
   for (int tx = 0; tx < c.W; tx++)
     for (int lx = 0; lx < TILE; lx++) {
@@ -57,7 +57,7 @@ PG_HDN int spawner_scan(const DevCfg& c, const MapView& m, int find, int& ox, in
 }
 
 // the idx-th square with any car lane, x-major (traffic_spawnable_positions, map.py:35-38)
-PG_HDN void spawnable_at(const DevCfg& c, const MapView& m, int idx, int& ox, int& oy) {
+PG_HDN void spawnable_at(const DevCfg& c, const MapView m, int idx, int& ox, int& oy) {
   for (int tx = 0; tx < c.W; tx++)
     for (int lx = 0; lx < TILE; lx++)
       for (int ty = 0; ty < c.H; ty++) {
@@ -100,7 +100,7 @@ PG_HD bool any_car_at(const DevCfg& c, const DevPtrs& p, int env, unsigned xy, i
 
 // one car tick; returns false when the car leaves the map (None at environment.py:968)
 template <int RNG>
-PG_HDN bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env, Car& car,
+PG_HD bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env, Car& car,
                      int r, int w, int n, int s) {
   // _should_car_move (:678-691)
   bool move;
@@ -150,10 +150,19 @@ PG_HDN bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvReg
   return false;
 }
 
+// The traffic tick is a cold, self-contained unit: it is the only consumer of the car stream
+// during a tick, so it owns its Rng; the env registers travel by value so that the (hot,
+// traffic-free) caller keeps everything in registers.
+struct TrafficIO {
+  uint32_t next_car_id, err;
+  int64_t cursor;
+};
 template <int RNG>
-PG_HD void advance_cars(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env) {
+PG_HDN TrafficIO advance_cars(const DevCfg& c, const DevPtrs& p, const MapView m, const EnvRegs e_in, int env) {
   // environment.py:1121-1127. Order-stable in place: survivors are compacted to [0,w), replacements
   // are parked in the scratch half in spawn order and appended afterwards (w + s == n).
+  EnvRegs e = e_in;
+  Rng<RNG> rng(p, e, env);
   int n = misc_ncars(e.misc), w = 0, s = 0;
   for (int r = 0; r < n; r++) {
     Car car = car_unpack(car_slot(c, p, env, r));
@@ -172,6 +181,9 @@ PG_HD void advance_cars(const DevCfg& c, const DevPtrs& p, const MapView& m, Env
     }
   }
   for (int i = 0; i < s; i++) car_slot(c, p, env, w + i) = car_slot(c, p, env, c.max_cars + i);
+  TrafficIO io;
+  io.next_car_id = e.next_car_id; io.err = e.err; io.cursor = e.cursor;
+  return io;
 }
 
 template <int RNG>
@@ -215,7 +227,7 @@ PG_HD void create_initial_traffic(const DevCfg& c, const DevPtrs& p, const MapVi
 // rule engine (environment.py:162-294)
 PG_HD int floordiv9(int a) { return a >= 0 ? a / TILE : -((-a + TILE - 1) / TILE); }
 
-PG_HDN int agent_direction(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e) {
+PG_HDN int agent_direction(const DevCfg& c, const DevPtrs& p, const MapView m, const EnvRegs e) {
   // get_agent_direction (:185-206) over _get_subgoal_compass_directions (:1037-1090)
   int gx, gy;
   if (m.nearest_goal(e.x, e.y, gx, gy)) {
@@ -229,15 +241,10 @@ PG_HDN int agent_direction(const DevCfg& c, const DevPtrs& p, const MapView& m, 
   return (e.vx == 0 && e.vy == 0) ? PGTG_AGENT_STATIONARY : PGTG_AGENT_NEAR_GOAL;  // norm < 0.1
 }
 
-PG_HDN bool apply_braking(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env) {
+PG_HDN bool apply_braking(const DevCfg& c, const DevPtrs& p, const MapView m, const EnvRegs e, int env) {
   // apply_braking / evaluate_rule (:226-294)
   int n = misc_ncars(e.misc);
-  if (n == 0 || c.num_rules == 0) {
-    // min_traffic <= 0 rules could still fire without cars; handled below when rules ask for it
-    bool any0 = false;
-    for (int i = 0; i < c.num_rules; i++) any0 |= p.rules[i].min_traffic <= 0 && p.rules[i].min_matching_traffic <= 0;
-    if (!any0) return false;
-  }
+  if (c.num_rules == 0) return false;
   int tx = floordiv9(e.x), ty = floordiv9(e.y);
   tx = tx < 0 ? 0 : (tx > c.W - 1 ? c.W - 1 : tx);
   ty = ty < 0 ? 0 : (ty > c.H - 1 ? c.H - 1 : ty);
@@ -284,7 +291,6 @@ PG_HD bool visited_test_set(const DevCfg& c, const DevPtrs& p, int env, int x, i
 
 template <int RNG>
 PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env, int action) {
-  Rng<RNG> rng(p, e, env);
   StepResult r;
   r.reward = 0; r.cost = 0; r.terminated = 0; r.braking = 0; r.outcome = 0;
   double perf = 0;
@@ -293,10 +299,16 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
   e.misc = misc_pack(misc_flat(e.misc), light, misc_ncars(e.misc));
   int ax = action / 3 - 1, ay = action % 3 - 1;  // constants.py:6-16
   int n_cars = misc_ncars(e.misc);
-  if (n_cars > 0) advance_cars<RNG>(c, p, m, e, rng, env);  // :1121-1127
+  if (n_cars > 0) {  // :1121-1127
+    TrafficIO io = advance_cars<RNG>(c, p, m, e, env);
+    e.next_car_id = io.next_car_id; e.err |= io.err; e.cursor = io.cursor;
+  }
+  Rng<RNG> rng(p, e, env);  // ice / broken road / sand streams of this tick
   int cx = e.x, cy = e.y;
   e.vx += ax; e.vy += ay;  // :1139
-  if (apply_braking(c, p, m, e, env)) { r.braking = 1; e.vx = 0; e.vy = 0; }  // :1145
+  if (n_cars > 0 || c.rules_without_traffic) {  // :1145 (the default rules need traffic in the agent's tile)
+    if (apply_braking(c, p, m, e, env)) { r.braking = 1; e.vx = 0; e.vy = 0; }
+  }
 
   // _decompose_velocity (:693-748), produced lazily one unit sub-step at a time; the float64
   // rounding of _round(i * m) is reproduced with explicitly unfused IEEE operations
@@ -411,25 +423,27 @@ PG_HD int select32(uint32_t v, int n) {
   return pos;
 }
 
-// start/goal connectivity of the grid graph; E bit i: edge i<->i+1, S bit i: edge i<->i+W
+// Does removing edge (a, b) keep start and goal connected? E bit i: edge i<->i+1, S bit i: edge
+// i<->i+W (the edge is already cleared). Flood from a: reaching b means nothing changed (early
+// exit, typically after going round one grid face); otherwise the flood ends on a's whole
+// component and the graph stays start-goal connected iff s and g are on the same side.
 template <int TMAX>
-PG_HD bool grid_connected(const DevCfg& c, const Board<TMAX>& E, const Board<TMAX>& S, int s, int g) {
-  if (s == g) return true;
+PG_HD bool still_connected(const DevCfg& c, const Board<TMAX>& E, const Board<TMAX>& S, int a, int b, int s, int g) {
   if (TMAX <= 32) {  // whole board in one register: flood fill by shifts
-    uint32_t e = E.w[0], so = S.w[0], reach = 1u << s, goal = 1u << g;
+    uint32_t e = E.w[0], so = S.w[0], reach = 1u << a, tb = 1u << b;
     for (;;) {
       uint32_t nx = reach | ((reach & e) << 1) | ((reach >> 1) & e) | ((reach & so) << c.W) | ((reach >> c.W) & so);
-      if (nx & goal) return true;
-      if (nx == reach) return false;
+      if (nx & tb) return true;
+      if (nx == reach) return ((reach >> s) & 1u) == ((reach >> g) & 1u);
       reach = nx;
     }
   } else if (TMAX <= 64) {
     uint64_t e = (uint64_t)E.w[0] | (uint64_t)E.w[1] << 32, so = (uint64_t)S.w[0] | (uint64_t)S.w[1] << 32;
-    uint64_t reach = 1ull << s, goal = 1ull << g;
+    uint64_t reach = 1ull << a, tb = 1ull << b;
     for (;;) {
       uint64_t nx = reach | ((reach & e) << 1) | ((reach >> 1) & e) | ((reach & so) << c.W) | ((reach >> c.W) & so);
-      if (nx & goal) return true;
-      if (nx == reach) return false;
+      if (nx & tb) return true;
+      if (nx == reach) return ((reach >> s) & 1ull) == ((reach >> g) & 1ull);
       reach = nx;
     }
   } else {
@@ -437,16 +451,16 @@ PG_HD bool grid_connected(const DevCfg& c, const Board<TMAX>& E, const Board<TMA
     bzero(seen);
     uint8_t q[TMAX];
     int qh = 0, qt = 0;
-    bset(seen, s); q[qt++] = (uint8_t)s;
+    bset(seen, a); q[qt++] = (uint8_t)a;
     while (qh < qt) {
       int n = q[qh++];
-      if (n == g) return true;
+      if (n == b) return true;
       int cand[4] = {n - c.W, n + 1, n + c.W, n - 1};
       bool ok[4] = {n >= c.W && bget(S, n - c.W), bget(E, n), bget(S, n), n > 0 && bget(E, n - 1)};
       for (int k = 0; k < 4; k++)
         if (ok[k] && !bget(seen, cand[k])) { bset(seen, cand[k]); q[qt++] = (uint8_t)cand[k]; }
     }
-    return false;
+    return bget(seen, s) == bget(seen, g);
   }
 }
 
@@ -473,7 +487,7 @@ PG_HD int random_direction(const DevCfg& c, Rng<RNG>& rng, int x, int y) {
 }
 
 template <int RNG>
-PG_HDN void choose_start_goal(const DevCfg& c, Rng<RNG>& rng, int& sx, int& sy, int& sd, int& gx, int& gy, int& gd) {
+PG_HD void choose_start_goal(const DevCfg& c, Rng<RNG>& rng, int& sx, int& sy, int& sd, int& gx, int& gy, int& gd) {
   // chose_random_start_and_goal_position_and_direction (:475-568)
   if (c.start_mode == 2) random_border_position<RNG>(c, rng, sx, sy);
   if (c.goal_mode == 2) random_border_position<RNG>(c, rng, gx, gy);
@@ -523,7 +537,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
       for (;; wi++) { int pc = pg_popc(alive[wi]); if (idx < pc) break; idx -= pc; }
       i = wi * 32 + select32(alive[wi], idx);
     }
-    int j = pg_ldg(&p.edge_rev[i]);
+    int j = m.edge_rev[i];
     if (AW == 2) {
       uint64_t clr = ~((1ull << i) | (1ull << j));
       alive[0] &= (uint32_t)clr; alive[1] &= (uint32_t)(clr >> 32);
@@ -532,12 +546,16 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
       alive[j >> 5] &= ~(1u << (j & 31));
     }
     n_alive -= 2;
-    unsigned ab = pg_ldg(&p.edge_tab[i]);
+    unsigned ab = m.edge_tab[i];
     int a = ab & 255, b = ab >> 8;
     int lo = a < b ? a : b;
     bool horiz = (a > b ? a - b : b - a) == 1;
     if (horiz) bclr(E, lo); else bclr(S, lo);
-    if (grid_connected<TMAX>(c, E, S, st, gt)) cur -= 2;
+#ifdef PGTG_FLOOD_SG
+    if (still_connected<TMAX>(c, E, S, st, gt, st, gt)) cur -= 2;
+#else
+    if (still_connected<TMAX>(c, E, S, a, b, st, gt)) cur -= 2;
+#endif
     else { if (horiz) bset(E, lo); else bset(S, lo); }
   }
   // map_graph_to_tile_map_object (:269-334); an E bit is only ever set left of the last column
@@ -562,7 +580,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     int i = select32(hi ? hi32 : lo32, hi ? idx - pc0 : idx) + (hi ? 32 : 0);
     slots &= ~(1ull << i);
     n_slots--;
-    unsigned v = pg_ldg(&p.border_slots[i]);
+    unsigned v = m.border_slots[i];
     m.tiles[v & 255] |= (uint16_t)(1 << (v >> 8));
   }
   // add_obstacles_to_map (:374-472), row-major, one random() per tile whatever the outcome
@@ -666,7 +684,7 @@ PG_HD void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
 }
 
 template <int RNG, int TMAX>
-PG_HDN void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
+PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
   // PGTGEnv.reset (environment.py:581-656)
   e.episode++;
   e.elapsed = 0;
@@ -751,7 +769,7 @@ PG_HD void emit_bits(uint32_t* bits, uint32_t off, uint32_t v) {
 }
 
 // writes env's C*P*P observation bits at bit offset `base` of `bits`, plus position/velocity/nsd
-PG_HDN void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, uint32_t* bits,
+PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, uint32_t* bits,
                         uint32_t base, int32_t* pos, int32_t* vel, int32_t* nsd) {
   int pix = e.x < 0 ? 0 : (e.x > c.WS - 1 ? c.WS - 1 : e.x);  // :1352-1356
   int piy = e.y < 0 ? 0 : (e.y > c.HS - 1 ? c.HS - 1 : e.y);
