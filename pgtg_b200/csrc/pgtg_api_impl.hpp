@@ -6,7 +6,7 @@
 //   void* bk_alloc(size_t);  void bk_free(void*);  int bk_set_device(int);
 //   int bk_h2d(void* dst, const void* src, size_t n, void* stream);   (async on stream)
 //   int bk_d2h(void* dst, const void* src, size_t n, void* stream);   (async on stream)
-//   int bk_memset(void* dst, int v, size_t n);  int bk_sync(void* stream);
+//   int bk_memset(void* dst, int v, size_t n);  int bk_memset_async(void*, int, size_t, void* stream);  int bk_sync(void* stream);
 //   int bk_pick_block(const DevCfg&, int* block, size_t* smem);
 //   int bk_launch(pgtg_env*, int mode, const uint8_t* mask_dev, const int64_t* seeds_dev,
 //                 const void* actions_dev, int action_bytes, void* stream);
@@ -24,7 +24,7 @@
 
 using namespace pgtg;
 
-enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2, MODE_MAPGEN = 3 };
 
 struct pgtg_env {
   pgtg_config cfg;
@@ -182,6 +182,7 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   }
   if (c.already_visited_position_penalty != 0) { d.vis_w = d.HS + 2; d.vis_words = ((d.WS + 2) * (d.HS + 2) + 31) / 32; }
   d.obs_bits = d.C * d.P * d.P;
+  d.pregen = (c.rng_mode == PGTG_RNG_PHILOX && !c.fixed_map) ? 1 : 0;
   d.env_id_base = c.env_id_base; d.seed = c.seed;
   if (!c.fixed_map) {
     d.n_edge_tab = 2 * (d.W * (d.H - 1) + d.H * (d.W - 1));
@@ -212,7 +213,8 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   bool ok = true;
 #define A(field, type, count) ok = ok && ((p.field = dev_alloc<type>(e, (count))) != nullptr)
   A(agent, short4, N); A(misc, uint32_t, N); A(elapsed, uint32_t, N); A(episode, uint32_t, N); A(next_car_id, uint32_t, N);
-  A(plan, uint32_t, N); A(tiles, uint16_t, N * dc.T + 8); A(cars, uint64_t, 2 * (size_t)dc.max_cars * N);
+  A(plan, uint32_t, N); A(tiles, uint16_t, N * dc.T + 8);
+  if (dc.pregen) { A(next_tiles, uint16_t, N * dc.T + 8); A(next_plan, uint32_t, N); A(regen_list, int32_t, N); A(regen_count, uint32_t, 4); } A(cars, uint64_t, 2 * (size_t)dc.max_cars * N);
   if (dc.vis_words) A(visited, uint32_t, (size_t)dc.vis_words * N);
   A(key, uint64_t, N); A(error, uint32_t, N); A(ep_return, double, N);
   if (cfg->rng_mode == PGTG_RNG_TAPE) { A(cursor, int64_t, N); A(tape_end, int64_t, N); }
@@ -361,9 +363,14 @@ extern "C" int pgtg_reset(pgtg_env* e, const int64_t* seeds, const uint8_t* mask
   if (!e->did_reset && mask) return fail(PGTG_ERR_STATE, "the first reset must cover all envs");
   if (seeds) bk_h2d(e->seeds_dev, seeds, N * 8, stream);
   if (mask) bk_h2d(e->mask_dev, mask, N, stream);
+  if (e->dc.pregen && bk_memset_async(e->dp.regen_count, 0, 4, stream)) return fail(PGTG_ERR_CUDA, std::string("memset failed: ") + bk_error());
   if (bk_launch(e, MODE_RESET, mask ? e->mask_dev : nullptr, seeds ? e->seeds_dev : nullptr, nullptr, 0, stream))
     return fail(PGTG_ERR_CUDA, std::string("reset launch failed: ") + bk_error());
   e->launches++;
+  if (e->dc.pregen) {
+    if (bk_launch(e, MODE_MAPGEN, nullptr, nullptr, nullptr, 0, stream)) return fail(PGTG_ERR_CUDA, std::string("mapgen launch failed: ") + bk_error());
+    e->launches++;
+  }
   e->did_reset = true;
   return PGTG_OK;
 }
@@ -374,9 +381,14 @@ extern "C" int pgtg_step(pgtg_env* e, const void* actions_dev, int action_bytes,
   if (!e->did_reset) return fail(PGTG_ERR_STATE, "step before reset");
   if (!actions_dev || (action_bytes != 4 && action_bytes != 8)) return fail(PGTG_ERR_INVALID, "actions must be device int32 or int64");
   bk_set_device(e->device);
+  if (e->dc.pregen && bk_memset_async(e->dp.regen_count, 0, 4, stream)) return fail(PGTG_ERR_CUDA, std::string("memset failed: ") + bk_error());
   if (bk_launch(e, MODE_STEP, nullptr, nullptr, actions_dev, action_bytes, stream))
     return fail(PGTG_ERR_CUDA, std::string("step launch failed: ") + bk_error());
   e->launches++;
+  if (e->dc.pregen) {  // build the next map of every env that just consumed one
+    if (bk_launch(e, MODE_MAPGEN, nullptr, nullptr, nullptr, 0, stream)) return fail(PGTG_ERR_CUDA, std::string("mapgen launch failed: ") + bk_error());
+    e->launches++;
+  }
   return PGTG_OK;
 }
 

@@ -123,6 +123,7 @@ struct DevCfg {
       drv_speed_multiplier[5], drv_reaction_delay[5];
   int drv_min_following[5];
   int separate_reward_cost, num_rules, max_episode_steps, write_final_obs, max_cars, lut_radius;
+  int pregen;  // maps of the next episode are built ahead of time by the map-generation kernel
   int rules_without_traffic;  // some rule has min_traffic <= 0 and min_matching_traffic <= 0
   int tile_stride;   // uint16 elements per env in the shared-memory tile stage (odd word count)
   int vis_w, vis_words;  // visited bitmap geometry (0 when the penalty is off)
@@ -142,6 +143,10 @@ struct DevPtrs {
   uint32_t* next_car_id;  // [N]
   uint32_t* plan;       // [N]
   uint16_t* tiles;      // [N][T]
+  uint16_t* next_tiles; // [N][T] pre-generated map of each env's next episode (pregen mode)
+  uint32_t* next_plan;  // [N]
+  int32_t* regen_list;  // [N] envs whose next map must be generated after this launch
+  uint32_t* regen_count; // [1]
   uint64_t* cars;       // [2 * max_cars][N], second half = same-tick respawn scratch
   uint32_t* visited;    // [vis_words][N] or null
   uint64_t* key;        // [N] philox key (the env's seed)

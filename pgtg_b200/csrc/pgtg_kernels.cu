@@ -21,6 +21,7 @@ static int bk_set_device(int d) { return ck(cudaSetDevice(d)); }
 static int bk_h2d(void* d, const void* s, size_t n, void* st) { return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, (cudaStream_t)st)); }
 static int bk_d2h(void* d, const void* s, size_t n, void* st) { return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st)); }
 static int bk_memset(void* d, int v, size_t n) { return ck(cudaMemset(d, v, n)); }
+static int bk_memset_async(void* d, int v, size_t n, void* st) { return ck(cudaMemsetAsync(d, v, n, (cudaStream_t)st)); }
 static int bk_sync(void* st) { return ck(st ? cudaStreamSynchronize((cudaStream_t)st) : cudaDeviceSynchronize()); }
 static int bk_dl_device_type() { return 2; }  // kDLCUDA
 static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem);
@@ -42,7 +43,7 @@ struct StatsArgs {
   double* rows;  // [gridDim.x][8]
 };
 
-template <int RNG, int MODE, int TMAX>
+template <int RNG, int MODE, int TMAX, bool PREGEN>
 __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
                                                         const void* __restrict__ actions, int action_bytes, StatsArgs sa) {
@@ -112,6 +113,12 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
   }
   __syncthreads();
 
+  if (MODE != MODE_OBSERVE && c.pregen && n_done) {  // CTA-uniform: queue these envs for the map-generation kernel
+    if (tid == 0) sh.counters[20] = (int)atomicAdd(p.regen_count, (uint32_t)n_done);
+    __syncthreads();
+    if (tid < n_done) p.regen_list[sh.counters[20] + tid] = env0 + sh.done_list[tid];
+  }
+
   if (MODE == MODE_STEP && c.write_final_obs && n_done) {  // CTA-uniform condition
     if (done) phase_emit(c, p, sh, tid, env, true);
     __syncthreads();
@@ -124,13 +131,28 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
   if (MODE != MODE_OBSERVE) {
     if (tid < n_done) {
       int local = sh.done_list[tid];
-      phase_reset<RNG, TMAX>(c, p, sh, local, env0 + local);
+      phase_reset<RNG, TMAX, PREGEN>(c, p, sh, local, env0 + local);
     }
     __syncthreads();
   }
   if (valid) phase_emit(c, p, sh, tid, env, false);
   __syncthreads();
   phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid);
+}
+
+// Map generation ahead of time: dense over the envs queued by the tick that just ran (every lane
+// busy, no CTA barrier after the staging, tiny shared-memory footprint -> high occupancy).
+template <int TMAX>
+__global__ void __launch_bounds__(128) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t count = *p.regen_count;
+  const uint32_t i0 = blockIdx.x * blockDim.x;
+  if (i0 >= count) return;
+  BlockShared sh = carve_mapgen(smem, c, blockDim.x);
+  stage_tables(c, p, sh, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const uint32_t i = i0 + threadIdx.x;
+  if (i < count) phase_pregenerate<TMAX>(c, p, sh, threadIdx.x, p.regen_list[i]);
 }
 
 __global__ void pgtg_reduce_stats_kernel(const double* __restrict__ rows, int nrows, double* __restrict__ out) {
@@ -153,9 +175,9 @@ static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem) {
   return -1;
 }
 
-template <int RNG, int MODE, int TMAX>
+template <int RNG, int MODE, int TMAX, bool PREGEN>
 static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
-  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX>;
+  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN>;
   if (e->smem > 48 * 1024) {
     if (ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem))) return -1;
   }
@@ -165,11 +187,21 @@ static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, co
 }
 
 // TMAX = compile-time bound on the tile count (register-resident boards for the default 4x4 map)
-template <int RNG, int MODE>
+template <int RNG, int MODE, bool PREGEN>
 static int launch_sized(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
-  if (e->dc.T <= 16) return launch_one<RNG, MODE, 16>(e, mask, seeds, actions, action_bytes, st);
-  if (e->dc.T <= 64) return launch_one<RNG, MODE, 64>(e, mask, seeds, actions, action_bytes, st);
-  return launch_one<RNG, MODE, 256>(e, mask, seeds, actions, action_bytes, st);
+  if (e->dc.T <= 16) return launch_one<RNG, MODE, 16, PREGEN>(e, mask, seeds, actions, action_bytes, st);
+  if (e->dc.T <= 64) return launch_one<RNG, MODE, 64, PREGEN>(e, mask, seeds, actions, action_bytes, st);
+  return launch_one<RNG, MODE, 256, PREGEN>(e, mask, seeds, actions, action_bytes, st);
+}
+
+template <int TMAX>
+static int launch_mapgen(pgtg_env* e, cudaStream_t st) {
+  const int B = 128;
+  size_t smem = pgtg::mapgen_shared_bytes(e->dc, B);
+  auto kern = pgtg::pgtg_mapgen_kernel<TMAX>;
+  if (smem > 48 * 1024 && ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return -1;
+  kern<<<(e->dc.N + B - 1) / B, B, smem, st>>>(e->dc, e->dp);
+  return ck(cudaGetLastError());
 }
 
 static int bk_launch(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream) {
@@ -177,13 +209,18 @@ static int bk_launch(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* 
   bool tape = e->cfg.rng_mode == PGTG_RNG_TAPE;
   switch (mode) {
     case MODE_STEP:
-      return tape ? launch_sized<PGTG_RNG_TAPE, MODE_STEP>(e, mask, seeds, actions, action_bytes, st)
-                  : launch_sized<PGTG_RNG_PHILOX, MODE_STEP>(e, mask, seeds, actions, action_bytes, st);
+      if (tape) return launch_sized<PGTG_RNG_TAPE, MODE_STEP, false>(e, mask, seeds, actions, action_bytes, st);
+      return e->dc.pregen ? launch_sized<PGTG_RNG_PHILOX, MODE_STEP, true>(e, mask, seeds, actions, action_bytes, st)
+                          : launch_sized<PGTG_RNG_PHILOX, MODE_STEP, false>(e, mask, seeds, actions, action_bytes, st);
     case MODE_RESET:
-      return tape ? launch_sized<PGTG_RNG_TAPE, MODE_RESET>(e, mask, seeds, actions, action_bytes, st)
-                  : launch_sized<PGTG_RNG_PHILOX, MODE_RESET>(e, mask, seeds, actions, action_bytes, st);
+      return tape ? launch_sized<PGTG_RNG_TAPE, MODE_RESET, false>(e, mask, seeds, actions, action_bytes, st)
+                  : launch_sized<PGTG_RNG_PHILOX, MODE_RESET, false>(e, mask, seeds, actions, action_bytes, st);
+    case MODE_MAPGEN:
+      if (e->dc.T <= 16) return launch_mapgen<16>(e, st);
+      if (e->dc.T <= 64) return launch_mapgen<64>(e, st);
+      return launch_mapgen<256>(e, st);
     default:
-      return launch_one<PGTG_RNG_PHILOX, MODE_OBSERVE, 16>(e, mask, seeds, actions, action_bytes, st);
+      return launch_one<PGTG_RNG_PHILOX, MODE_OBSERVE, 16, false>(e, mask, seeds, actions, action_bytes, st);
   }
 }
 

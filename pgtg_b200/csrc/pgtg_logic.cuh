@@ -683,12 +683,15 @@ PG_HD void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
   e.plan = (e.plan & 0xFFFFFu) | (unsigned)ns << 20;
 }
 
+// plan word bits 29-30: index of the start square among map.starters (map_rng.choice, :635)
+PG_HOSTDEV int plan_start_index(unsigned pl) { return (pl >> 29) & 3; }
+
+// The map of one episode: tile descriptors with their subgoal directions, the plan word (start /
+// goal / number of subgoals) and the start-square draw -- everything PGTGEnv.reset takes from
+// map_rng (environment.py:601-635). It depends only on (seed, episode), never on the actions, so
+// it can be built ahead of time by the map-generation kernel.
 template <int RNG, int TMAX>
-PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
-  // PGTGEnv.reset (environment.py:581-656)
-  e.episode++;
-  e.elapsed = 0;
-  Rng<RNG> rng(p, e, env);
+PG_HD void build_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng) {
   if (c.fixed_map) {
     for (int t = 0; t < c.T; t++) m.tiles[t] = pg_ldg(&p.fixed_tiles[t]);
     e.plan = p.fixed_plan;
@@ -697,23 +700,30 @@ PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
   }
   assign_subgoals<TMAX>(c, m, e);
   m.plan = e.plan;
-  e.flags |= EF_TILES_DIRTY | EF_RESET;
-  // self.position = map_rng.choice(self.map.starters) (:635); starters in x-major order
+  // self.position = map_rng.choice(self.map.starters) (:635): 3 squares of the start line, x-major
   int stile = m.start_tile(), sd = plan_sd(e.plan);
   unsigned lab = (m.line_labels(stile, m.tiles[stile]) >> (4 * sd)) & 15;
+  if (lab == 3) e.plan |= (unsigned)rng.index(PGTG_STREAM_MAP, 3) << 29;
+  else e.err |= 64;
+  m.plan = e.plan;
+}
+
+// the rest of PGTGEnv.reset (environment.py:635-656) on a finished map
+template <int RNG>
+PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng, int env) {
+  e.flags |= EF_TILES_DIRTY | EF_RESET;
+  int stile = m.start_tile(), sd = plan_sd(e.plan);
+  int k = plan_start_index(e.plan);
+  int ox = (stile % c.W) * TILE, oy = (stile / c.W) * TILE;
   e.x = e.y = 0;
-  if (lab == 3) {
-    int k = rng.index(PGTG_STREAM_MAP, 3);
-    int ox = (stile % c.W) * TILE, oy = (stile / c.W) * TILE;
-    for (int w = 0; w < 3; w++) {
-      uint32_t bits = m.L.exit_line[sd][w];
-      while (bits) {
-        int sq = w * 32 + pg_ffs(bits) - 1;
-        bits &= bits - 1;
-        if (k-- == 0) { e.x = ox + sq / TILE; e.y = oy + sq % TILE; }
-      }
+  for (int w = 0; w < 3; w++) {
+    uint32_t bits = m.L.exit_line[sd][w];
+    while (bits) {
+      int sq = w * 32 + pg_ffs(bits) - 1;
+      bits &= bits - 1;
+      if (k-- == 0) { e.x = ox + sq / TILE; e.y = oy + sq % TILE; }
     }
-  } else e.err |= 64;
+  }
   e.vx = e.vy = 0;
   e.misc = 0;  // flat_tire, light counter, cars (:637-650)
   e.next_car_id = 0;
@@ -722,6 +732,35 @@ PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
     visited_test_set(c, p, env, e.x, e.y, true);  // positions_path = [position] (:643)
   }
   if (c.traffic_density > 0) create_initial_traffic<RNG>(c, p, m, e, rng, env);  // :652-653
+}
+
+// PGTGEnv.reset (environment.py:581-656), map built in place
+template <int RNG, int TMAX>
+PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
+  e.episode++;
+  e.elapsed = 0;
+  Rng<RNG> rng(p, e, env);
+  build_map<RNG, TMAX>(c, p, m, e, rng);
+  begin_episode<RNG>(c, p, m, e, rng, env);
+}
+
+// the same with the map taken from the pre-generated "next map" of this env
+template <int RNG>
+PG_HD void env_reset_pregenerated(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
+  e.episode++;
+  e.elapsed = 0;
+  Rng<RNG> rng(p, e, env);
+  const uint16_t* nt = p.next_tiles + (size_t)env * c.T;
+  if ((c.T & 7) == 0) {
+    const uint4* g4 = (const uint4*)nt;
+    uint32_t* s32 = (uint32_t*)m.tiles;
+    for (int k = 0; k < c.T / 8; k++) { uint4 v = g4[k]; s32[4 * k] = v.x; s32[4 * k + 1] = v.y; s32[4 * k + 2] = v.z; s32[4 * k + 3] = v.w; }
+  } else {
+    for (int t = 0; t < c.T; t++) m.tiles[t] = nt[t];
+  }
+  e.plan = p.next_plan[env];
+  m.plan = e.plan;
+  begin_episode<RNG>(c, p, m, e, rng, env);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@ static int bk_set_device(int) { return 0; }
 static int bk_h2d(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
 static int bk_d2h(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
 static int bk_memset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+static int bk_memset_async(void* d, int v, size_t n, void*) { memset(d, v, n); return 0; }
 static int bk_sync(void*) { return 0; }
 static const char* bk_error() { return "emu"; }
 static int bk_dl_device_type() { return 1; }  // kDLCPU
@@ -27,7 +28,7 @@ static int bk_stats_reset(pgtg_env*, void*);
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
-template <int RNG, int TMAX>
+template <int RNG, int TMAX, bool PREGEN>
 static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes,
                       int blk, unsigned char* smem) {
   const DevCfg& c = h->dc;
@@ -66,24 +67,53 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
   } else {
     for (int t = 0; t < nvalid; t++) sh.regs[t] = load_regs(c, p, env0 + t);
   }
-  for (int k = 0; k < n_done; k++) phase_reset<RNG, TMAX>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+  if (mode != MODE_OBSERVE && c.pregen && n_done) {  // queue for the map-generation pass
+    uint32_t base = *p.regen_count;
+    *p.regen_count += (uint32_t)n_done;
+    for (int k = 0; k < n_done; k++) p.regen_list[base + k] = env0 + sh.done_list[k];
+  }
+  for (int k = 0; k < n_done; k++) {
+    if (PREGEN && mode == MODE_STEP) phase_reset<RNG, TMAX, true>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+    else phase_reset<RNG, TMAX, false>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+  }
   for (int t = 0; t < nvalid; t++) phase_emit(c, p, sh, t, env0 + t, false);
   for (int t = 0; t < B; t++) phase_expand(c, p.obs_map, sh, t, B, env0, nvalid);
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
 }
 
+template <int TMAX>
+static void run_mapgen(pgtg_env* h) {
+  const DevCfg& c = h->dc;
+  const DevPtrs& p = h->dp;
+  const int B = 128;
+  size_t bytes = mapgen_shared_bytes(c, B);
+  unsigned char* smem = (unsigned char*)bk_alloc(bytes);
+  uint32_t count = *p.regen_count;
+  for (uint32_t i0 = 0; i0 < count; i0 += B) {
+    memset(smem, 0xA5, bytes);
+    BlockShared sh = carve_mapgen(smem, c, B);
+    for (int t = 0; t < B; t++) stage_tables(c, p, sh, t, B);
+    for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<TMAX>(c, p, sh, t, p.regen_list[i0 + t]);
+  }
+  free(smem);
+}
+
 static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void*) {
+  int T = h->dc.T;  // same TMAX dispatch as the CUDA backend
+  if (mode == MODE_MAPGEN) {
+    if (T <= 16) run_mapgen<16>(h); else if (T <= 64) run_mapgen<64>(h); else run_mapgen<256>(h);
+    return 0;
+  }
   size_t bytes = block_shared_bytes(h->dc, h->block);
   unsigned char* smem = (unsigned char*)bk_alloc(bytes);
   int nblk = (h->dc.N + h->block - 1) / h->block;
   for (int b = 0; b < nblk; b++) {
     memset(smem, 0xA5, bytes);  // shared memory starts undefined on the device too
     bool tape = h->cfg.rng_mode == PGTG_RNG_TAPE;
-    int T = h->dc.T;  // same TMAX dispatch as the CUDA backend
-#define RUN(R, M) run_block<R, M>(h, mode, mask, seeds, actions, action_bytes, b, smem)
-    if (T <= 16) { if (tape) RUN(PGTG_RNG_TAPE, 16); else RUN(PGTG_RNG_PHILOX, 16); }
-    else if (T <= 64) { if (tape) RUN(PGTG_RNG_TAPE, 64); else RUN(PGTG_RNG_PHILOX, 64); }
-    else { if (tape) RUN(PGTG_RNG_TAPE, 256); else RUN(PGTG_RNG_PHILOX, 256); }
+#define RUN(R, M, G) run_block<R, M, G>(h, mode, mask, seeds, actions, action_bytes, b, smem)
+#define RUN3(M) do { if (tape) RUN(PGTG_RNG_TAPE, M, false); else if (h->dc.pregen) RUN(PGTG_RNG_PHILOX, M, true); else RUN(PGTG_RNG_PHILOX, M, false); } while (0)
+    if (T <= 16) RUN3(16); else if (T <= 64) RUN3(64); else RUN3(256);
+#undef RUN3
 #undef RUN
   }
   free(smem);
