@@ -55,6 +55,7 @@ struct short4 { short x, y, z, w; };
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
 #endif
 
 #include "../../include/pgtg_b200.h"
@@ -243,15 +244,10 @@ struct Rng {
   const DevPtrs& p;
   EnvRegs& e;
   int env;
-  uint32_t k0, k1;
   uint32_t kcount[5];  // words consumed per stream this tick
   uint32_t b0, b1, b2, b3, cur_block;
   int cur_stream;
   PG_MEMBER Rng(const DevPtrs& p_, EnvRegs& e_, int env_) : p(p_), e(e_), env(env_) {
-    if (RNG == PGTG_RNG_PHILOX) {
-      uint64_t key = p.key[env];
-      k0 = (uint32_t)key; k1 = (uint32_t)(key >> 32);
-    }
 #pragma unroll
     for (int i = 0; i < 5; i++) kcount[i] = 0;
     cur_stream = -1; cur_block = 0; b0 = b1 = b2 = b3 = 0;
@@ -260,8 +256,9 @@ struct Rng {
     uint32_t pos = kcount[stream]++;
     uint32_t b = pos >> 2;
     if (stream != cur_stream || b != cur_block) {
+      uint64_t key = p.key[env];  // loaded on refill only: most ticks draw nothing
       b0 = b; b1 = e.elapsed; b2 = e.episode; b3 = (uint32_t)stream;
-      philox4x32_10(b0, b1, b2, b3, k0, k1);
+      philox4x32_10(b0, b1, b2, b3, (uint32_t)key, (uint32_t)(key >> 32));
       cur_stream = stream; cur_block = b;
     }
     uint32_t j = pos & 3u;
