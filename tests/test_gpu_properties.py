@@ -1,0 +1,97 @@
+"""Size-independent properties at the BASELINE.json sizes (where lock-step comparison with the
+oracle would take too long): determinism, structural invariants of every observation, reward
+support, statistics bookkeeping, invariance to the CTA decomposition."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rollout(n, ticks, seed, device="cuda:0", **kw):
+    import torch
+
+    from pgtg_b200 import PGTGVectorEnv
+
+    env = PGTGVectorEnv(n, device=device, seed=seed, **kw)
+    env.reset()
+    g = torch.Generator(device=device)
+    g.manual_seed(7)
+    digest = torch.zeros((), dtype=torch.int64, device=device)
+    w = torch.arange(1, 730, device=device, dtype=torch.int64)
+    rsum = torch.zeros((), dtype=torch.float64, device=device)
+    done = 0
+    for t in range(ticks):
+        a = torch.randint(0, 9, (n,), device=device, dtype=torch.int32, generator=g)
+        obs, rew, term, trunc, info = env.step(a)
+        m = env._t["obs_map"]
+        flat = m.reshape(n, -1).to(torch.int64)
+        if flat.shape[1] == 729:
+            digest = digest * 1000003 + (flat * w).sum()
+        else:
+            digest = digest * 1000003 + flat.sum()
+        rsum += rew.sum()
+        done += int((term | trunc).sum())
+        if t % 8 == 0:
+            assert int(m.min()) == 0 and int(m.max()) == 1
+            assert bool(((obs["position"] >= 0) & (obs["position"] < 9)).all())
+            # a fresh or running env always sees walls, and never more goal squares than one 3-square line
+            walls = obs["map"]["walls"].reshape(n, -1).sum(1)
+            goals = obs["map"]["goals"].reshape(n, -1).sum(1)
+            assert int(walls.min()) >= 30 and int(goals.max()) <= 6
+            assert bool((obs["velocity"][term | trunc] == 0).all())
+            support = torch.unique(rew)
+            assert all(v == 0 or v == -100 or (0 < v <= 100) for v in support.tolist())
+    stats = env.episode_stats()
+    assert stats["episodes"] == done
+    err = env.get_state()["error"]
+    assert not err.any()
+    env.close()
+    return int(digest.item()), float(rsum.item()), done
+
+
+def test_default_65536_envs_deterministic():
+    a = _rollout(65536, 24, seed=11)
+    b = _rollout(65536, 24, seed=11)
+    c = _rollout(65536, 24, seed=12)
+    assert a == b and a != c and a[2] > 400000
+
+
+def test_config3_65536_envs():
+    """BASELINE config 3 at full size: traffic 0.05, obstacles 0.2."""
+    a = _rollout(65536, 16, seed=5, traffic_density=0.05, random_map_obstacle_probability=0.2)
+    b = _rollout(65536, 16, seed=5, traffic_density=0.05, random_map_obstacle_probability=0.2)
+    assert a == b
+
+
+def test_config4_large_maps_dense_traffic_32k():
+    """BASELINE config 4 settings (8x8 tiles, 80 % connections, traffic 0.2, obstacles 0.5) at 32768 envs."""
+    a = _rollout(32768, 6, seed=8, random_map_width=8, random_map_height=8, random_map_percentage_of_connections=0.8,
+                 traffic_density=0.2, random_map_obstacle_probability=0.5)
+    assert a[2] > 0
+
+
+def test_results_do_not_depend_on_sharding():
+    """Global env ids: two half-size handles with env_id_base reproduce the full-size run (the
+    single-GPU analogue of the multi-GPU shards of SURVEY.md 8e)."""
+    import torch
+
+    from pgtg_b200 import PGTGVectorEnv
+
+    kw = dict(traffic_density=0.05, random_map_obstacle_probability=0.2, seed=21)
+    full = PGTGVectorEnv(1000, device="cuda:0", **kw)
+    lo = PGTGVectorEnv(600, device="cuda:0", env_id_base=0, **kw)
+    hi = PGTGVectorEnv(400, device="cuda:0", env_id_base=600, **kw)
+    for e in (full, lo, hi):
+        e.reset()
+    rng = np.random.default_rng(1)
+    for t in range(12):
+        act = torch.from_numpy(rng.integers(0, 9, 1000).astype(np.int32)).cuda()
+        of, rf, *_ = full.step(act)
+        ol, rl, *_ = lo.step(act[:600].contiguous())
+        oh, rh, *_ = hi.step(act[600:].contiguous())
+        assert torch.equal(full._t["obs_map"], torch.cat([lo._t["obs_map"], hi._t["obs_map"]]))
+        assert torch.equal(rf, torch.cat([rl, rh]))
+    s = np.array([lo.raw.stats(), hi.raw.stats()]).sum(0)
+    assert np.allclose(s, full.raw.stats())
+    for e in (full, lo, hi):
+        e.close()
