@@ -40,7 +40,7 @@ def _rollout(n, ticks, seed, device="cuda:0", **kw):
             assert int(walls.min()) >= 30 and int(goals.max()) <= 6
             assert bool((obs["velocity"][term | trunc] == 0).all())
             support = torch.unique(rew)
-            assert all(v == 0 or v == -100 or (0 < v <= 100) for v in support.tolist())
+            assert all(-100 <= v <= 100 for v in support.tolist())  # a tick can collect subgoal rewards and still crash
     stats = env.episode_stats()
     assert stats["episodes"] == done
     err = env.get_state()["error"]
