@@ -182,6 +182,7 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   }
   if (c.already_visited_position_penalty != 0) { d.vis_w = d.HS + 2; d.vis_words = ((d.WS + 2) * (d.HS + 2) + 31) / 32; }
   d.obs_bits = d.C * d.P * d.P;
+  if (c.traffic_density > 0) { d.occ_words = (d.WS * d.HS + 15) / 16;  /* 2-bit counters */ d.spawner_cap = 2 * (d.W + d.H) + d.T; }
   d.pregen = (c.rng_mode == PGTG_RNG_PHILOX && !c.fixed_map) ? 1 : 0;
   d.env_id_base = c.env_id_base; d.seed = c.seed;
   if (!c.fixed_map) {
@@ -216,6 +217,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   A(plan, uint32_t, N); A(tiles, uint16_t, N * dc.T + 8);
   if (dc.pregen) { A(next_tiles, uint16_t, N * dc.T + 8); A(next_plan, uint32_t, N); A(regen_list, int32_t, N); A(regen_count, uint32_t, 4); } A(cars, uint64_t, 2 * (size_t)dc.max_cars * N);
   if (dc.vis_words) A(visited, uint32_t, (size_t)dc.vis_words * N);
+  if (dc.occ_words) { A(occ, uint32_t, (size_t)dc.occ_words * N); A(spawners, uint16_t, (size_t)dc.spawner_cap * N); A(spawner_count, uint16_t, N); }
   A(key, uint64_t, N); A(error, uint32_t, N); A(ep_return, double, N);
   if (cfg->rng_mode == PGTG_RNG_TAPE) { A(cursor, int64_t, N); A(tape_end, int64_t, N); }
   A(obs_map, int8_t, N * dc.obs_bits + 16); A(obs_position, int32_t, 2 * N); A(obs_velocity, int32_t, 2 * N); A(obs_nsd, int32_t, N);

@@ -128,6 +128,7 @@ struct DevCfg {
   int rules_without_traffic;  // some rule has min_traffic <= 0 and min_matching_traffic <= 0
   int tile_stride;   // uint16 elements per env in the shared-memory tile stage (odd word count)
   int vis_w, vis_words;  // visited bitmap geometry (0 when the penalty is off)
+  int occ_words, spawner_cap;  // traffic helpers (0 without traffic)
   int obs_bits;      // C * P * P
   uint32_t full_e[8], full_s[8];  // full grid graph: bit t = edge t<->t+1 / t<->t+W exists
   int64_t env_id_base;
@@ -150,6 +151,10 @@ struct DevPtrs {
   uint32_t* regen_count; // [1]
   uint64_t* cars;       // [2 * max_cars][N], second half = same-tick respawn scratch
   uint32_t* visited;    // [vis_words][N] or null
+  // traffic helpers (allocated when traffic_density > 0)
+  uint32_t* occ;        // [occ_words][N] per-tick 2-bit car counters per square (cell x*HS+y), 3 = saturated
+  uint16_t* spawners;   // [spawner_cap][N] car_spawner squares in x-major order (x | y << 8), built at reset
+  uint16_t* spawner_count;  // [N]
   uint64_t* key;        // [N] philox key (the env's seed)
   int64_t* cursor;      // [N] tape cursor
   int64_t* tape_end;    // [N]

@@ -33,8 +33,9 @@ PG_HD uint32_t col9(const uint32_t w[3], int lx) {  // the 9 bits of local colum
   if (sh > 23 && wi < 2) v |= w[wi + 1] << (32 - sh);
   return v & 0x1FFu;
 }
-// find == -1: count; else: coordinates of the find-th spawner
-PG_HDN int spawner_scan(const DevCfg& c, const MapView m, int find, int& ox, int& oy) {
+// Build the env's car_spawner list (x-major order of EpisodeMap.__init__, map.py:31-42) once per
+// episode: _spawn_new_car (environment.py:977-979) then indexes it in O(1).
+PG_HDN void build_spawner_list(const DevCfg& c, const DevPtrs& p, const MapView m, int env) {
   int n = 0;
   for (int tx = 0; tx < c.W; tx++)
     for (int lx = 0; lx < TILE; lx++) {
@@ -43,42 +44,35 @@ PG_HDN int spawner_scan(const DevCfg& c, const MapView m, int find, int& ox, int
         uint32_t sb[3];
         spawner_bits(c, m.L, td_exits(m.tiles[ty * c.W + tx]), tx, ty, sb);
         uint32_t col = col9(sb, lx);
-        int cnt = pg_popc(col);
-        if (find >= 0 && find < n + cnt) {
-          int k = find - n;
-          while (k--) col &= col - 1;
-          ox = tx * TILE + lx; oy = ty * TILE + pg_ffs(col) - 1;
-          return n + cnt;
+        while (col) {
+          int ly = pg_ffs(col) - 1;
+          col &= col - 1;
+          if (n < c.spawner_cap) p.spawners[(size_t)n * c.N + env] = (uint16_t)((tx * TILE + lx) | (ty * TILE + ly) << 8);
+          n++;
         }
-        n += cnt;
       }
     }
-  return n;
+  p.spawner_count[env] = (uint16_t)(n < c.spawner_cap ? n : c.spawner_cap);
 }
 
-// the idx-th square with any car lane, x-major (traffic_spawnable_positions, map.py:35-38)
-PG_HDN void spawnable_at(const DevCfg& c, const MapView m, int idx, int& ox, int& oy) {
-  for (int tx = 0; tx < c.W; tx++)
-    for (int lx = 0; lx < TILE; lx++)
-      for (int ty = 0; ty < c.H; ty++) {
-        uint32_t col = col9(m.L.lane_any[td_exits(m.tiles[ty * c.W + tx])], lx);
-        int cnt = pg_popc(col);
-        if (idx < cnt) {
-          while (idx--) col &= col - 1;
-          ox = tx * TILE + lx; oy = ty * TILE + pg_ffs(col) - 1;
-          return;
-        }
-        idx -= cnt;
-      }
-  ox = oy = 0;
+// occupancy grid: per-tick 2-bit counters of the cars on every square (exact while < 3; the value 3
+// is sticky and means "unknown, scan the list"). "Is there a car on (x, y)?" becomes O(1) instead
+// of a scan over the car list -- the list scans were 70 % of the tick at ~230 cars per env.
+constexpr int OCC_MIN_CARS = 12;
+PG_HD int occ_get(const DevCfg& c, const DevPtrs& p, int env, int x, int y) {
+  int i = x * c.HS + y;
+  return (int)((p.occ[(size_t)(i >> 4) * c.N + env] >> ((i & 15) * 2)) & 3u);
 }
-PG_HD int spawnable_count(const DevCfg& c, const MapView& m) {
-  int n = 0;
-  for (int t = 0; t < c.T; t++) {
-    const uint32_t* w = m.L.lane_any[td_exits(m.tiles[t])];
-    n += pg_popc(w[0]) + pg_popc(w[1]) + pg_popc(w[2]);
-  }
-  return n;
+PG_HD void occ_add(const DevCfg& c, const DevPtrs& p, int env, int x, int y) {
+  int i = x * c.HS + y, sh = (i & 15) * 2;
+  uint32_t& w = p.occ[(size_t)(i >> 4) * c.N + env];
+  if (((w >> sh) & 3u) < 3u) w += 1u << sh;
+}
+PG_HD void occ_sub(const DevCfg& c, const DevPtrs& p, int env, int x, int y) {
+  int i = x * c.HS + y, sh = (i & 15) * 2;
+  uint32_t& w = p.occ[(size_t)(i >> 4) * c.N + env];
+  uint32_t v = (w >> sh) & 3u;
+  if (v == 1u || v == 2u) w -= 1u << sh;  // 3 stays 3
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -101,7 +95,7 @@ PG_HD bool any_car_at(const DevCfg& c, const DevPtrs& p, int env, unsigned xy, i
 // one car tick; returns false when the car leaves the map (None at environment.py:968)
 template <int RNG>
 PG_HD bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env, Car& car,
-                     int r, int w, int n, int s) {
+                     int r, int w, int n, int s, bool use_occ) {
   // _should_car_move (:678-691)
   bool move;
   if (car.delay > 0) { car.delay--; move = false; }
@@ -133,8 +127,11 @@ PG_HD bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs
       // cars_on_next_position over the live list: survivors [0,w), not-yet-moved (r,n), and the
       // replacements spawned earlier this tick (scratch half) (:944-948)
       unsigned xy = (unsigned)px | (unsigned)py << 8;
-      bool blocked = any_car_at<RNG>(c, p, env, xy, 0, w) || any_car_at<RNG>(c, p, env, xy, r + 1, n) ||
-                     any_car_at<RNG>(c, p, env, xy, c.max_cars, c.max_cars + s);
+      int occ = use_occ ? occ_get(c, p, env, px, py) : 3;
+      bool blocked = occ == 1 || occ == 2;
+      if (occ == 3)
+        blocked = any_car_at<RNG>(c, p, env, xy, 0, w) || any_car_at<RNG>(c, p, env, xy, r + 1, n) ||
+                  any_car_at<RNG>(c, p, env, xy, c.max_cars, c.max_cars + s);
       if (blocked) {  // :950-962
         if (c.drv_min_following[car.profile] == 0 || (double)car.patience > c.drv_patience_threshold[car.profile]) {
           if (rng.uniform(PGTG_STREAM_CAR) < c.drv_push_probability[car.profile]) { car.patience = 0; car.x = px; car.y = py; return true; }
@@ -164,14 +161,26 @@ PG_HDN TrafficIO advance_cars(const DevCfg& c, const DevPtrs& p, const MapView m
   EnvRegs e = e_in;
   Rng<RNG> rng(p, e, env);
   int n = misc_ncars(e.misc), w = 0, s = 0;
+  const bool use_occ = n >= OCC_MIN_CARS;
+  if (use_occ) {  // rebuild the occupancy counters for this tick
+    for (int i = 0; i < c.occ_words; i++) p.occ[(size_t)i * c.N + env] = 0;
+    for (int r = 0; r < n; r++) { unsigned xy = car_xy(car_slot(c, p, env, r)); occ_add(c, p, env, (int)(xy & 255), (int)(xy >> 8)); }
+  }
   for (int r = 0; r < n; r++) {
     Car car = car_unpack(car_slot(c, p, env, r));
-    if (car_next<RNG>(c, p, m, e, rng, env, car, r, w, n, s)) {
+    int ox = car.x, oy = car.y;
+    if (car_next<RNG>(c, p, m, e, rng, env, car, r, w, n, s, use_occ)) {
+      if (use_occ && (car.x != ox || car.y != oy)) { occ_sub(c, p, env, ox, oy); occ_add(c, p, env, car.x, car.y); }
       car_slot(c, p, env, w++) = car_pack(car);
     } else {  // _spawn_new_car (:970-1002)
+      if (use_occ) occ_sub(c, p, env, ox, oy);
       int sx = 0, sy = 0;
-      int ns = spawner_scan(c, m, -1, sx, sy);
-      if (ns > 0) spawner_scan(c, m, rng.index(PGTG_STREAM_CAR, ns), sx, sy);
+      int ns = p.spawner_count[env];
+      if (ns > 0) {
+        unsigned v = p.spawners[(size_t)rng.index(PGTG_STREAM_CAR, ns) * c.N + env];
+        sx = (int)(v & 255); sy = (int)(v >> 8);
+      }
+      if (use_occ) occ_add(c, p, env, sx, sy);
       Car nc;
       nc.profile = rng.choice_cdf(PGTG_STREAM_CAR, c.profile_cdf, PGTG_NUM_PROFILES);
       nc.route = random_route_at<RNG>(m, rng, e, sx, sy);
@@ -187,40 +196,64 @@ PG_HDN TrafficIO advance_cars(const DevCfg& c, const DevPtrs& p, const MapView m
 }
 
 template <int RNG>
-PG_HD void create_initial_traffic(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env) {
-  // _create_initial_traffic (environment.py:830-879)
-  int num_positions = spawnable_count(c, m);
+PG_HDN uint32_t create_initial_traffic(const DevCfg& c, const DevPtrs& p, const MapView m, const EnvRegs e_in, int env, uint32_t car_words,
+                                      int64_t* cursor_out, uint32_t* err_out) {
+  // _create_initial_traffic (environment.py:830-879). Cold, self-contained unit (registers by value).
+  EnvRegs e = e_in;
+  Rng<RNG> rng(p, e, env);
+  rng.kcount[PGTG_STREAM_CAR] = car_words;
+  // lane squares per global column, x-major (traffic_spawnable_positions, map.py:35-38)
+  uint16_t colpre[TILE * 16 + 1];
+  int ncol = c.W * TILE, num_positions = 0;
+  for (int X = 0; X < ncol; X++) {
+    colpre[X] = (uint16_t)num_positions;
+    int tx = X / TILE, lx = X - tx * TILE;
+    for (int ty = 0; ty < c.H; ty++) num_positions += pg_popc(col9(m.L.lane_any[td_exits(m.tiles[ty * c.W + tx])], lx));
+  }
+  colpre[ncol] = (uint16_t)num_positions;
   int num_cars = (int)((double)num_positions * c.traffic_density);
   if (num_cars > num_positions) num_cars = num_positions;
-  if (num_cars <= 0) return;
   if (num_cars > c.max_cars) { e.err |= 32; num_cars = c.max_cars; }
-  // car_rng.choice(n, size=k, replace=False): k distinct indices, kept raw in the car slots first
-  for (int j = 0; j < num_cars; j++) {
-    int v;
-    if (RNG == PGTG_RNG_TAPE) {
-      v = (int)rng.tape_next(PGTG_STREAM_CAR, PGTG_DRAW_INDEX);
-      if (v < 0 || v >= num_positions) { e.err |= 4; v = 0; }
-    } else {
-      for (;;) {  // sequential rejection sampling (spec shared with the oracle)
-        v = (int)pg_umulhi(rng.word(PGTG_STREAM_CAR), (uint32_t)num_positions);
-        bool dup = false;
-        for (int q = 0; q < j; q++) if ((int)car_slot(c, p, env, q) == v) { dup = true; break; }
-        if (!dup) break;
+  if (num_cars > 0) {
+    // car_rng.choice(n, size=k, replace=False): k distinct indices, kept raw in the car slots first;
+    // Philox mode draws with rejection against a bitmap of the indices already taken (the
+    // occupancy words double as that scratch)
+    if (RNG != PGTG_RNG_TAPE) for (int i = 0; i < (num_positions + 31) / 32; i++) p.occ[(size_t)i * c.N + env] = 0;
+    for (int j = 0; j < num_cars; j++) {
+      int v;
+      if (RNG == PGTG_RNG_TAPE) {
+        v = (int)rng.tape_next(PGTG_STREAM_CAR, PGTG_DRAW_INDEX);
+        if (v < 0 || v >= num_positions) { e.err |= 4; v = 0; }
+      } else {
+        for (;;) {  // sequential rejection sampling (spec shared with the oracle)
+          v = (int)pg_umulhi(rng.word(PGTG_STREAM_CAR), (uint32_t)num_positions);
+          uint32_t& wd = p.occ[(size_t)(v >> 5) * c.N + env];
+          if (!((wd >> (v & 31)) & 1u)) { wd |= 1u << (v & 31); break; }
+        }
       }
+      car_slot(c, p, env, j) = (uint64_t)(uint32_t)v;
     }
-    car_slot(c, p, env, j) = (uint64_t)(uint32_t)v;
+    for (int j = 0; j < num_cars; j++) {
+      int idx = (int)car_slot(c, p, env, j);
+      int lo = 0, hi = ncol;  // last column with colpre[X] <= idx
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)colpre[mid] <= idx) lo = mid; else hi = mid; }
+      int X = lo, tx = X / TILE, lx = X - tx * TILE, rest = idx - colpre[X], x = X, y = 0;
+      for (int ty = 0; ty < c.H; ty++) {
+        uint32_t col = col9(m.L.lane_any[td_exits(m.tiles[ty * c.W + tx])], lx);
+        int cnt = pg_popc(col);
+        if (rest < cnt) { while (rest--) col &= col - 1; y = ty * TILE + pg_ffs(col) - 1; break; }
+        rest -= cnt;
+      }
+      Car car;
+      car.profile = rng.choice_cdf(PGTG_STREAM_CAR, c.profile_cdf, PGTG_NUM_PROFILES);
+      car.route = random_route_at<RNG>(m, rng, e, x, y);
+      car.id = e.next_car_id++;
+      car.x = x; car.y = y; car.patience = 0; car.delay = 0;
+      car_slot(c, p, env, j) = car_pack(car);
+    }
   }
-  for (int j = 0; j < num_cars; j++) {
-    int x, y;
-    spawnable_at(c, m, (int)car_slot(c, p, env, j), x, y);
-    Car car;
-    car.profile = rng.choice_cdf(PGTG_STREAM_CAR, c.profile_cdf, PGTG_NUM_PROFILES);
-    car.route = random_route_at<RNG>(m, rng, e, x, y);
-    car.id = e.next_car_id++;
-    car.x = x; car.y = y; car.patience = 0; car.delay = 0;
-    car_slot(c, p, env, j) = car_pack(car);
-  }
-  e.misc = misc_pack(misc_flat(e.misc), misc_light(e.misc), num_cars);
+  *cursor_out = e.cursor; *err_out = e.err;
+  return (uint32_t)num_cars | e.next_car_id << 16;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -336,8 +369,11 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
     bool inside = m.inside(cx, cy);
     unsigned f = inside ? m.features(cx, cy) : (unsigned)SF_WALL;
     bool crash = !inside || (f & SF_WALL);
-    if (!crash && !c.ignore_traffic_collisions && n_cars > 0)
-      crash = any_car_at<RNG>(c, p, env, (unsigned)cx | (unsigned)cy << 8, 0, n_cars);
+    if (!crash && !c.ignore_traffic_collisions && n_cars > 0) {
+      int occ = n_cars >= OCC_MIN_CARS ? occ_get(c, p, env, cx, cy) : 3;
+      crash = occ == 1 || occ == 2;
+      if (occ == 3) crash = any_car_at<RNG>(c, p, env, (unsigned)cx | (unsigned)cy << 8, 0, n_cars);
+    }
     if (crash) {
       if (c.separate_reward_cost) r.cost += c.crash_penalty; else r.reward -= c.crash_penalty;
       r.terminated = 1; r.outcome = 1;
@@ -731,7 +767,13 @@ PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
     for (int i = 0; i < c.vis_words; i++) p.visited[(size_t)i * c.N + env] = 0;
     visited_test_set(c, p, env, e.x, e.y, true);  // positions_path = [position] (:643)
   }
-  if (c.traffic_density > 0) create_initial_traffic<RNG>(c, p, m, e, rng, env);  // :652-653
+  if (c.traffic_density > 0) {  // :652-653
+    build_spawner_list(c, p, m, env);
+    int64_t cur; uint32_t err;
+    uint32_t r = create_initial_traffic<RNG>(c, p, m, e, env, rng.kcount[PGTG_STREAM_CAR], &cur, &err);
+    e.misc = misc_pack(misc_flat(e.misc), misc_light(e.misc), (int)(r & 0xFFFFu));
+    e.next_car_id = r >> 16; e.cursor = cur; e.err |= err;
+  }
 }
 
 // PGTGEnv.reset (environment.py:581-656), map built in place
