@@ -58,7 +58,7 @@ PG_HDN void build_spawner_list(const DevCfg& c, const DevPtrs& p, const MapView 
 // occupancy grid: per-tick 2-bit counters of the cars on every square (exact while < 3; the value 3
 // is sticky and means "unknown, scan the list"). "Is there a car on (x, y)?" becomes O(1) instead
 // of a scan over the car list -- the list scans were 70 % of the tick at ~230 cars per env.
-constexpr int OCC_MIN_CARS = 12;
+constexpr int OCC_MIN_CARS = 32;
 PG_HD int occ_get(const DevCfg& c, const DevPtrs& p, int env, int x, int y) {
   int i = x * c.HS + y;
   return (int)((p.occ[(size_t)(i >> 4) * c.N + env] >> ((i & 15) * 2)) & 3u);
