@@ -258,6 +258,11 @@ int pgtg_reduce_stats(pgtg_env* env, void* stream);
 int pgtg_reset_stats(pgtg_env* env, void* stream);
 /* Reduces, then copies the 8 statistics doubles to the host (synchronises). */
 int pgtg_stats(pgtg_env* env, double* out8, int reset_after);
+/* Per-kernel device timing: while enabled (max_steps > 0), pgtg_step brackets each of its kernels
+ * with CUDA events on the launching stream; pgtg_timing synchronises and returns the summed
+ * durations in ms of the tick kernel and of the map-generation kernel over the recorded ticks. */
+int pgtg_enable_timing(pgtg_env* env, int max_steps);
+int pgtg_timing(pgtg_env* env, double* tick_ms, double* mapgen_ms, int* steps);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t pgtg_launch_count(pgtg_env* env);
 

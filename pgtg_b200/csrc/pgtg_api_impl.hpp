@@ -11,6 +11,8 @@
 //   int bk_launch(pgtg_env*, int mode, const uint8_t* mask_dev, const int64_t* seeds_dev,
 //                 const void* actions_dev, int action_bytes, void* stream);
 //   const char* bk_error();  int bk_dl_device_type();
+//   void* bk_event_create();  void bk_event_destroy(void*);  int bk_event_record(void* ev, void* stream);
+//   double bk_event_elapsed(void* a, void* b);
 //   int bk_stats_reduce(pgtg_env*, void* stream);  int bk_stats_reset(pgtg_env*, void* stream);
 #pragma once
 #include <math.h>
@@ -37,6 +39,8 @@ struct pgtg_env {
   std::vector<void*> allocs;
   bool have_fixed, have_tape, did_reset;
   int nblk;             // CTAs per launch
+  // optional per-kernel timing (CUDA events on the launching stream around each kernel of a tick)
+  bool timing; std::vector<void*> tev; int tev_used;
   double* stats_rows;   // [nblk][8] per-CTA episode statistics (CUDA backend)
   // device scratch for reset arguments and host-buffer steps
   uint8_t* mask_dev;
@@ -205,6 +209,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   pgtg_env* e = new pgtg_env();
   e->cfg = *cfg; e->dc = dc; e->device = device; e->launches = 0;
   e->have_fixed = e->have_tape = e->did_reset = false;
+  e->timing = false; e->tev_used = 0;
   memset(&e->dp, 0, sizeof e->dp);
   if (bk_pick_block(e->dc, &e->block, &e->smem)) { delete e; return fail(PGTG_ERR_INVALID, "observation window too large for shared memory"); }
   e->nblk = (dc.N + e->block - 1) / e->block;
@@ -279,6 +284,7 @@ extern "C" int pgtg_destroy(pgtg_env* e) {
   if (!e) return PGTG_OK;
   bk_set_device(e->device);
   bk_sync(nullptr);
+  for (void* ev : e->tev) bk_event_destroy(ev);
   for (void* a : e->allocs) bk_free(a);
   delete e;
   return PGTG_OK;
@@ -384,13 +390,17 @@ extern "C" int pgtg_step(pgtg_env* e, const void* actions_dev, int action_bytes,
   if (!actions_dev || (action_bytes != 4 && action_bytes != 8)) return fail(PGTG_ERR_INVALID, "actions must be device int32 or int64");
   bk_set_device(e->device);
   if (e->dc.pregen && bk_memset_async(e->dp.regen_count, 0, 4, stream)) return fail(PGTG_ERR_CUDA, std::string("memset failed: ") + bk_error());
+  bool timed = e->timing && e->tev_used + 3 <= (int)e->tev.size();
+  if (timed) bk_event_record(e->tev[e->tev_used], stream);
   if (bk_launch(e, MODE_STEP, nullptr, nullptr, actions_dev, action_bytes, stream))
     return fail(PGTG_ERR_CUDA, std::string("step launch failed: ") + bk_error());
   e->launches++;
+  if (timed) bk_event_record(e->tev[e->tev_used + 1], stream);
   if (e->dc.pregen) {  // build the next map of every env that just consumed one
     if (bk_launch(e, MODE_MAPGEN, nullptr, nullptr, nullptr, 0, stream)) return fail(PGTG_ERR_CUDA, std::string("mapgen launch failed: ") + bk_error());
     e->launches++;
   }
+  if (timed) { bk_event_record(e->tev[e->tev_used + 2], stream); e->tev_used += 3; }
   return PGTG_OK;
 }
 
@@ -601,3 +611,33 @@ extern "C" int pgtg_stats(pgtg_env* e, double* out8, int reset_after) {
 }
 
 extern "C" int64_t pgtg_launch_count(pgtg_env* e) { return e ? e->launches : 0; }
+
+// Per-kernel device timing: while enabled, pgtg_step brackets each of its kernels with CUDA events on
+// the launching stream (up to max_steps ticks). pgtg_timing synchronises and returns the summed
+// durations (ms) of the tick kernel and of the map-generation kernel over the recorded ticks.
+extern "C" int pgtg_enable_timing(pgtg_env* e, int max_steps) {
+  if (!e) return fail(PGTG_ERR_INVALID, "null handle");
+  bk_set_device(e->device);
+  e->timing = max_steps > 0;
+  e->tev_used = 0;
+  while ((int)e->tev.size() < 3 * max_steps) {
+    void* ev = bk_event_create();
+    if (!ev) return fail(PGTG_ERR_CUDA, std::string("event creation failed: ") + bk_error());
+    e->tev.push_back(ev);
+  }
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_timing(pgtg_env* e, double* tick_ms, double* mapgen_ms, int* steps) {
+  if (!e || !tick_ms || !mapgen_ms || !steps) return fail(PGTG_ERR_INVALID, "null argument");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  *tick_ms = *mapgen_ms = 0;
+  *steps = e->tev_used / 3;
+  for (int i = 0; i + 2 < e->tev_used; i += 3) {
+    *tick_ms += bk_event_elapsed(e->tev[i], e->tev[i + 1]);
+    *mapgen_ms += bk_event_elapsed(e->tev[i + 1], e->tev[i + 2]);
+  }
+  e->tev_used = 0;
+  return PGTG_OK;
+}

@@ -24,6 +24,10 @@ static int bk_memset(void* d, int v, size_t n) { return ck(cudaMemset(d, v, n));
 static int bk_memset_async(void* d, int v, size_t n, void* st) { return ck(cudaMemsetAsync(d, v, n, (cudaStream_t)st)); }
 static int bk_sync(void* st) { return ck(st ? cudaStreamSynchronize((cudaStream_t)st) : cudaDeviceSynchronize()); }
 static int bk_dl_device_type() { return 2; }  // kDLCUDA
+static void* bk_event_create() { cudaEvent_t ev; if (ck(cudaEventCreate(&ev))) return nullptr; return ev; }
+static void bk_event_destroy(void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
+static int bk_event_record(void* ev, void* st) { return ck(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st)); }
+static double bk_event_elapsed(void* a, void* b) { float ms = 0; cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b); return ms; }
 static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem);
 static int bk_launch(pgtg_env*, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream);
 static int bk_stats_reduce(pgtg_env*, void* stream);

@@ -98,6 +98,16 @@ class RawEnv:
         _lib.check(self.lib, self.lib.pgtg_stats(self._h, out.ctypes.data, int(reset_after)))
         return out
 
+    def enable_timing(self, max_steps: int):
+        _lib.check(self.lib, self.lib.pgtg_enable_timing(self._h, int(max_steps)))
+
+    def timing(self) -> dict:
+        """-> mean device time (ms) of the tick and map-generation kernels over the recorded ticks."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int()
+        _lib.check(self.lib, self.lib.pgtg_timing(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        k = max(n.value, 1)
+        return dict(tick_ms=a.value / k, mapgen_ms=b.value / k, steps=n.value)
+
     def launch_count(self) -> int:
         return int(self.lib.pgtg_launch_count(self._h))
 

@@ -21,6 +21,10 @@ static int bk_memset_async(void* d, int v, size_t n, void*) { memset(d, v, n); r
 static int bk_sync(void*) { return 0; }
 static const char* bk_error() { return "emu"; }
 static int bk_dl_device_type() { return 1; }  // kDLCPU
+static void* bk_event_create() { return malloc(1); }
+static void bk_event_destroy(void* ev) { free(ev); }
+static int bk_event_record(void*, void*) { return 0; }
+static double bk_event_elapsed(void*, void*) { return 0.0; }
 static int bk_pick_block(const pgtg::DevCfg&, int* block, size_t* smem) { *block = 128; *smem = 0; return 0; }
 static int bk_launch(pgtg_env*, int, const uint8_t*, const int64_t*, const void*, int, void*);
 static int bk_stats_reduce(pgtg_env*, void*);
