@@ -28,6 +28,33 @@ from ._names import ROUTE_NAMES
 from .raw import RawEnv
 
 
+class LazyInfo(dict):
+    """`info` of a step: entries that cost a kernel launch (bit tests on `step_flags`) are computed on
+    first access, so a rollout loop that ignores them pays nothing."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._lazy = {}
+
+    def lazy(self, key, fn):
+        self._lazy[key] = fn
+        dict.__setitem__(self, key, None)
+
+    def __getitem__(self, key):
+        if key in self._lazy:
+            dict.__setitem__(self, key, self._lazy.pop(key)())
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self]
+
+    def values(self):
+        return [self[k] for k in self]
+
+
 def _device_index(device) -> int:
     d = torch.device(device)
     if d.type != "cuda":
@@ -111,18 +138,19 @@ class PGTGVectorEnv:
 
     def _info(self, reset: bool = False) -> dict:
         ss = self._t["step_state"]
-        info: dict[str, Any] = {}
+        info = LazyInfo()
         if not reset:
             fl = self._t["step_flags"]
-            info.update(x=ss[:, 0], y=ss[:, 1], x_velocity=ss[:, 2], y_velocity=ss[:, 3],
-                        flat_tire=(fl & 1).bool(), braking_applied=(fl & 2).bool())
+            info.update(x=ss[:, 0], y=ss[:, 1], x_velocity=ss[:, 2], y_velocity=ss[:, 3], step_flags=fl)
+            info.lazy("flat_tire", lambda: (fl & 1).bool())
+            info.lazy("braking_applied", lambda: (fl & 2).bool())
             if self.separate_reward_cost:
                 info["cost"] = self._t["cost"]
                 info["safety_cost"] = self._t["cost"]
                 info["performance_reward"] = self._t["reward"]
             if self.hc.pod.write_final_obs:
                 info["final_observation"] = self._observation(final=True)
-                info["_final_observation"] = self._terminated | self._truncated
+                info.lazy("_final_observation", lambda: self._terminated | self._truncated)
         return info
 
     def step(self, actions):
