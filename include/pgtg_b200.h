@@ -258,6 +258,12 @@ int pgtg_reduce_stats(pgtg_env* env, void* stream);
 int pgtg_reset_stats(pgtg_env* env, void* stream);
 /* Reduces, then copies the 8 statistics doubles to the host (synchronises). */
 int pgtg_stats(pgtg_env* env, double* out8, int reset_after);
+/* Flattened float32 observation [N, D] in gymnasium 0.28.1 FlattenObservation order over the reference's
+ * Dict space (train.py:39-40): sorted map planes, next_subgoal_direction one-hot (if enabled), position
+ * one-hots, velocity. plane_order[i] = channel index of the i-th plane in sorted-key order. The buffer is
+ * allocated on first use, owned by the handle and also exported as DLPack "obs_flat". */
+int pgtg_flatten(pgtg_env* env, const int32_t* plane_order, void* stream, float** out_dev, int* out_dim);
+
 /* Per-kernel device timing: while enabled (max_steps > 0), pgtg_step brackets each of its kernels
  * with CUDA events on the launching stream; pgtg_timing synchronises and returns the summed
  * durations in ms of the tick kernel and of the map-generation kernel over the recorded ticks. */

@@ -41,6 +41,8 @@ struct pgtg_env {
   int nblk;             // CTAs per launch
   // optional per-kernel timing (CUDA events on the launching stream around each kernel of a tick)
   bool timing; std::vector<void*> tev; int tev_used;
+  // flattened observation (FlattenObservation view for SB3-style consumers), allocated on first use
+  float* flat; int flat_dim; int flat_order[PGTG_MAX_CHANNELS];
   double* stats_rows;   // [nblk][8] per-CTA episode statistics (CUDA backend)
   // device scratch for reset arguments and host-buffer steps
   uint8_t* mask_dev;
@@ -210,6 +212,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   e->cfg = *cfg; e->dc = dc; e->device = device; e->launches = 0;
   e->have_fixed = e->have_tape = e->did_reset = false;
   e->timing = false; e->tev_used = 0;
+  e->flat = nullptr; e->flat_dim = 0;
   memset(&e->dp, 0, sizeof e->dp);
   if (bk_pick_block(e->dc, &e->block, &e->smem)) { delete e; return fail(PGTG_ERR_INVALID, "observation window too large for shared memory"); }
   e->nblk = (dc.N + e->block - 1) / e->block;
@@ -465,6 +468,7 @@ extern "C" int pgtg_dlpack(pgtg_env* e, const char* name, void** out) {
       {"final_obs_velocity", p.f_obs_velocity, 0, 32, 2, {N, 2}},
       {"final_obs_next_subgoal_direction", p.f_obs_nsd, 0, 32, 1, {N}},
       {"stats", p.stats, 2, 64, 1, {8}},
+      {"obs_flat", e->flat, 2, 32, 2, {N, (int64_t)e->flat_dim}},
   };
   for (const Spec& s : specs) {
     if (strcmp(s.name, name)) continue;
@@ -607,6 +611,32 @@ extern "C" int pgtg_stats(pgtg_env* e, double* out8, int reset_after) {
   bk_d2h(out8, e->dp.stats, 64, nullptr);
   if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
   if (reset_after) { bk_stats_reset(e, nullptr); bk_sync(nullptr); }
+  return PGTG_OK;
+}
+
+// Flattened observation, float32 [N, D], in the order of gymnasium 0.28.1 `FlattenObservation` over the
+// reference's Dict space (train.py:39-40): Dict keys sorted -> "map" (sub-keys sorted, each plane
+// P*P cells, index [x][y]), "next_subgoal_direction" (one-hot 9, value + 1), "position" (two one-hots
+// of 9), "velocity" (2). `plane_order[i]` = channel index of the i-th plane in sorted-key order.
+extern "C" int pgtg_flatten(pgtg_env* e, const int32_t* plane_order, void* stream, float** out_dev, int* out_dim) {
+  if (!e || !plane_order) return fail(PGTG_ERR_INVALID, "null argument");
+  if (!e->did_reset) return fail(PGTG_ERR_STATE, "flatten before reset");
+  bk_set_device(e->device);
+  const DevCfg& c = e->dc;
+  int dim = c.C * c.P * c.P + (c.use_nsd ? 9 : 0) + 18 + 2;
+  if (!e->flat) {
+    e->flat = dev_alloc<float>(e, (size_t)c.N * dim, false);
+    if (!e->flat) return fail(PGTG_ERR_CUDA, std::string("device allocation failed: ") + bk_error());
+    e->flat_dim = dim;
+  }
+  for (int i = 0; i < c.C; i++) {
+    if (plane_order[i] < 0 || plane_order[i] >= c.C) return fail(PGTG_ERR_INVALID, "bad plane order");
+    e->flat_order[i] = plane_order[i];
+  }
+  if (bk_flatten(e, stream)) return fail(PGTG_ERR_CUDA, std::string("flatten launch failed: ") + bk_error());
+  e->launches++;
+  if (out_dev) *out_dev = e->flat;
+  if (out_dim) *out_dim = dim;
   return PGTG_OK;
 }
 

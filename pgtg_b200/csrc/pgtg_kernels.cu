@@ -32,6 +32,7 @@ static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem);
 static int bk_launch(pgtg_env*, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream);
 static int bk_stats_reduce(pgtg_env*, void* stream);
 static int bk_stats_reset(pgtg_env*, void* stream);
+static int bk_flatten(pgtg_env*, void* stream);
 
 #include "pgtg_api_impl.hpp"
 
@@ -159,6 +160,31 @@ __global__ void __launch_bounds__(128) pgtg_mapgen_kernel(const __grid_constant_
   if (i < count) phase_pregenerate<TMAX>(c, p, sh, threadIdx.x, p.regen_list[i]);
 }
 
+struct FlatOrder { int plane[PGTG_MAX_CHANNELS]; };
+
+// FlattenObservation view: one thread per output float, coalesced float32 stores; reads the int8
+// planes through L2 (they were just written by the tick).
+__global__ void pgtg_flatten_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, FlatOrder order,
+                                    float* __restrict__ out, int dim) {
+  const int PP = c.P * c.P, map_dim = c.C * PP, nsd_dim = c.use_nsd ? 9 : 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)c.N * dim; i += (size_t)gridDim.x * blockDim.x) {
+    int env = (int)(i / dim), j = (int)(i - (size_t)env * dim);
+    float v;
+    if (j < map_dim) {
+      int k = j / PP, cell = j - k * PP;
+      v = (float)p.obs_map[((size_t)env * c.C + order.plane[k]) * PP + cell];
+    } else if (j < map_dim + nsd_dim) {
+      v = (p.obs_nsd[env] + 1 == j - map_dim) ? 1.0f : 0.0f;  // Discrete(9, start=-1) one-hot
+    } else if (j < map_dim + nsd_dim + 18) {
+      int q = j - map_dim - nsd_dim;  // MultiDiscrete([9, 9]) -> two one-hots
+      v = (p.obs_position[2 * env + (q >= 9)] == (q >= 9 ? q - 9 : q)) ? 1.0f : 0.0f;
+    } else {
+      v = (float)p.obs_velocity[2 * env + (j - map_dim - nsd_dim - 18)];
+    }
+    out[i] = v;
+  }
+}
+
 __global__ void pgtg_reduce_stats_kernel(const double* __restrict__ rows, int nrows, double* __restrict__ out) {
   // out[k] = sum over CTAs of rows[.][k]; one warp per statistic
   int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,6 +267,14 @@ extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
 static int bk_stats_reduce(pgtg_env* e, void* stream) {
   pgtg::pgtg_reduce_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->stats_rows, e->nblk, e->dp.stats);
   e->launches++;
+  return ck(cudaGetLastError());
+}
+static int bk_flatten(pgtg_env* e, void* stream) {
+  pgtg::FlatOrder order;
+  for (int i = 0; i < PGTG_MAX_CHANNELS; i++) order.plane[i] = e->flat_order[i];
+  size_t total = (size_t)e->dc.N * e->flat_dim;
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  pgtg::pgtg_flatten_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(e->dc, e->dp, order, e->flat, e->flat_dim);
   return ck(cudaGetLastError());
 }
 static int bk_stats_reset(pgtg_env* e, void* stream) {

@@ -98,6 +98,14 @@ class RawEnv:
         _lib.check(self.lib, self.lib.pgtg_stats(self._h, out.ctypes.data, int(reset_after)))
         return out
 
+    def flatten(self, stream: int = 0):
+        """Launch the FlattenObservation kernel; -> (device pointer, D). Key order: sorted map keys."""
+        keys = self.hc.observation_keys
+        order = np.array([keys.index(k) for k in sorted(keys)], np.int32)
+        ptr, dim = C.c_void_p(), C.c_int()
+        _lib.check(self.lib, self.lib.pgtg_flatten(self._h, order.ctypes.data, stream, C.byref(ptr), C.byref(dim)))
+        return ptr.value, dim.value
+
     def enable_timing(self, max_steps: int):
         _lib.check(self.lib, self.lib.pgtg_enable_timing(self._h, int(max_steps)))
 

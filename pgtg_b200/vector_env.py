@@ -181,6 +181,43 @@ class PGTGVectorEnv:
             self.raw.step_host(actions, stream=self._stream(), **out)
         return out
 
+    def flat_observation(self):
+        """float32 [N, D] tensor equal to gymnasium 0.28.1 `FlattenObservation` applied to every env's
+        observation (what SB3's MlpPolicy consumes at train.py:39-61): sorted map planes, optional
+        next_subgoal_direction one-hot, position one-hots, velocity. One extra kernel per call."""
+        with torch.cuda.device(self.device):
+            self.raw.flatten(self._stream())
+            if "obs_flat" not in self._t:
+                self._t["obs_flat"] = torch.from_dlpack(self.raw.dlpack_capsule("obs_flat"))
+        return self._t["obs_flat"]
+
+    def save_map(self, path: str, env_index: int = 0) -> None:
+        """EpisodeMap.save_map (map.py:173-184): the current map plan of one env as reference JSON."""
+        import json
+
+        from ._names import CARDINALS, MASK_NAMES, OBSTACLE_NAMES
+
+        st = self.raw.get_state()
+        W, H = self.hc.pod.map_w, self.hc.pod.map_h
+        pl = st["plan"][env_index]
+        rows = []
+        for y in range(H):
+            row = []
+            for x in range(W):
+                td = int(st["tiles"][env_index, y * W + x])
+                tile = {"exits": [td & 1, (td >> 1) & 1, (td >> 2) & 1, (td >> 3) & 1]}
+                if (td >> 4) & 7:
+                    tile["obstacle_type"] = OBSTACLE_NAMES[((td >> 4) & 7) - 1]
+                    tile["obstacle_mask"] = MASK_NAMES[(td >> 7) & 15]
+                row.append(tile)
+            rows.append(row)
+        plan = {"width": W, "height": H, "map": rows, "start": [int(pl[0]), int(pl[1]), CARDINALS[pl[2]]],
+                "goal": [int(pl[3]), int(pl[4]), CARDINALS[pl[5]]]}
+        if not path.endswith(".json"):
+            path += ".json"
+        with open(path, "w", encoding="utf-8") as f:
+            json.dump(plan, f, ensure_ascii=False, indent=4)
+
     def close(self):
         self.raw.close()
 

@@ -29,6 +29,7 @@ static int bk_pick_block(const pgtg::DevCfg&, int* block, size_t* smem) { *block
 static int bk_launch(pgtg_env*, int, const uint8_t*, const int64_t*, const void*, int, void*);
 static int bk_stats_reduce(pgtg_env*, void*);
 static int bk_stats_reset(pgtg_env*, void*);
+static int bk_flatten(pgtg_env*, void*);
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
@@ -134,3 +135,20 @@ extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
 // the emulation accumulates straight into the 8-double stats buffer
 static int bk_stats_reduce(pgtg_env*, void*) { return 0; }
 static int bk_stats_reset(pgtg_env* e, void*) { memset(e->dp.stats, 0, 64); return 0; }
+
+// host loop of the flatten kernel (same index arithmetic)
+static int bk_flatten(pgtg_env* e, void*) {
+  const DevCfg& c = e->dc;
+  const DevPtrs& p = e->dp;
+  int dim = e->flat_dim, PP = c.P * c.P, map_dim = c.C * PP, nsd_dim = c.use_nsd ? 9 : 0;
+  for (size_t i = 0; i < (size_t)c.N * dim; i++) {
+    int env = (int)(i / dim), j = (int)(i - (size_t)env * dim);
+    float v;
+    if (j < map_dim) { int k = j / PP, cell = j - k * PP; v = (float)p.obs_map[((size_t)env * c.C + e->flat_order[k]) * PP + cell]; }
+    else if (j < map_dim + nsd_dim) v = (p.obs_nsd[env] + 1 == j - map_dim) ? 1.0f : 0.0f;
+    else if (j < map_dim + nsd_dim + 18) { int q = j - map_dim - nsd_dim; v = (p.obs_position[2 * env + (q >= 9)] == (q >= 9 ? q - 9 : q)) ? 1.0f : 0.0f; }
+    else v = (float)p.obs_velocity[2 * env + (j - map_dim - nsd_dim - 18)];
+    e->flat[i] = v;
+  }
+  return 0;
+}
