@@ -68,7 +68,9 @@ typedef enum pgtg_channel {
 /* Random-number source. */
 typedef enum pgtg_rng_mode {
   PGTG_RNG_PHILOX = 0, /* counter-based Philox4x32-10 per env (production) */
-  PGTG_RNG_TAPE = 1    /* conformance: consume draws recorded from the reference's np_random */
+  PGTG_RNG_TAPE = 1,   /* conformance: consume draws recorded from the reference's np_random */
+  PGTG_RNG_NUMPY = 2   /* numpy-exact: SeedSequence + PCG64 + Generator.random/integers/choice restated, so
+                          that seeds alone reproduce the reference (env i = SeedSequence(seed_i)) */
 } pgtg_rng_mode;
 
 /* Draw tags on a conformance tape: stream * 8 + kind. */

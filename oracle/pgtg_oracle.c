@@ -74,6 +74,8 @@ typedef struct {
   uint32_t draw_k[5];       /* words consumed per stream this tick */
   uint32_t blk[4], blk_index; /* cached Philox block of blk_stream */
   int blk_stream;
+  /* numpy mode: the five PCG64 children of this reset (environment.py:593-599) */
+  struct { unsigned __int128 state, inc; uint32_t buf; int has; } pcg[5];
   int64_t cursor, tape_end;
   int error;
   /* outputs of the last step */
@@ -134,6 +136,53 @@ static uint32_t philox_word(rctx* r, int stream) {
   return e->blk[pos & 3u];
 }
 
+/* ---- numpy mode (PGTG_RNG_NUMPY): SeedSequence + PCG64 + Generator methods, restated from numpy's
+ * published algorithms (bit_generator.pyx SeedSequence, pcg64.h, distributions.c bounded Lemire,
+ * _generator.pyx choice) for exactly the calls the reference makes; pinned against numpy itself by
+ * tests/test_numpy_rng.py through the golden traces. ------------------------------------------------ */
+static uint32_t ss_hashmix(uint32_t v, uint32_t* hc) { v ^= *hc; *hc *= 0x931e8875u; v *= *hc; v ^= v >> 16; return v; }
+static uint32_t ss_mix(uint32_t x, uint32_t y) { uint32_t q = 0xca01f9ddu * x - 0x4973f715u * y; q ^= q >> 16; return q; }
+#define PCG_MULT ((((unsigned __int128)0x2360ED051FC65DA4ull) << 64) | 0x4385DF649FCCF645ull)
+static void np_seed_child(ora_env* e, int stream, uint32_t child) {
+  uint32_t ent[5] = {(uint32_t)e->seed, (uint32_t)(e->seed >> 32), 0, 0, child}, pool[4], hc = 0x43b0d7e5u;
+  for (int i = 0; i < 4; i++) pool[i] = ss_hashmix(ent[i], &hc);
+  for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) if (a != b) pool[b] = ss_mix(pool[b], ss_hashmix(pool[a], &hc));
+  for (int b = 0; b < 4; b++) pool[b] = ss_mix(pool[b], ss_hashmix(ent[4], &hc));
+  uint32_t w[8], hb = 0x8b51f9ddu;
+  for (int i = 0; i < 8; i++) { uint32_t v = pool[i & 3] ^ hb; hb *= 0x58f38dedu; v *= hb; v ^= v >> 16; w[i] = v; }
+  unsigned __int128 initstate = ((unsigned __int128)((uint64_t)w[0] | (uint64_t)w[1] << 32) << 64) | ((uint64_t)w[2] | (uint64_t)w[3] << 32);
+  unsigned __int128 initseq = ((unsigned __int128)((uint64_t)w[4] | (uint64_t)w[5] << 32) << 64) | ((uint64_t)w[6] | (uint64_t)w[7] << 32);
+  e->pcg[stream].inc = (initseq << 1) | 1u;
+  e->pcg[stream].state = 0;
+  e->pcg[stream].state = e->pcg[stream].state * PCG_MULT + e->pcg[stream].inc;
+  e->pcg[stream].state += initstate;
+  e->pcg[stream].state = e->pcg[stream].state * PCG_MULT + e->pcg[stream].inc;
+  e->pcg[stream].has = 0; e->pcg[stream].buf = 0;
+}
+static uint64_t np_next64(ora_env* e, int s) {
+  e->pcg[s].state = e->pcg[s].state * PCG_MULT + e->pcg[s].inc;
+  uint64_t hi = (uint64_t)(e->pcg[s].state >> 64), lo = (uint64_t)e->pcg[s].state, x = hi ^ lo;
+  unsigned rot = (unsigned)(hi >> 58);
+  return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+static uint32_t np_next32(ora_env* e, int s) {
+  if (e->pcg[s].has) { e->pcg[s].has = 0; return e->pcg[s].buf; }
+  uint64_t n = np_next64(e, s);
+  e->pcg[s].has = 1; e->pcg[s].buf = (uint32_t)(n >> 32);
+  return (uint32_t)n;
+}
+static uint32_t np_bounded(ora_env* e, int s, uint32_t rng) { /* inclusive bound, Lemire 32-bit */
+  if (rng == 0) return 0;
+  uint32_t ex = rng + 1u;
+  uint64_t m = (uint64_t)np_next32(e, s) * ex;
+  uint32_t left = (uint32_t)m;
+  if (left < ex) {
+    uint32_t thr = (0u - ex) % ex;
+    while (left < thr) { m = (uint64_t)np_next32(e, s) * ex; left = (uint32_t)m; }
+  }
+  return (uint32_t)(m >> 32);
+}
+
 static double tape_next(rctx* r, int stream, int kind) {
   ora_env* e = r->e;
   if (e->cursor >= e->tape_end) { e->error |= 1; return 0.0; }
@@ -144,6 +193,7 @@ static double tape_next(rctx* r, int stream, int kind) {
 /* Generator.random() */
 static double rng_double(rctx* r, int stream) {
   if (r->b->cfg.rng_mode == PGTG_RNG_TAPE) return tape_next(r, stream, PGTG_DRAW_DOUBLE);
+  if (r->b->cfg.rng_mode == PGTG_RNG_NUMPY) return (double)(np_next64(r->e, stream) >> 11) * (1.0 / 9007199254740992.0);
   uint32_t w0 = philox_word(r, stream), w1 = philox_word(r, stream);
   return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) / 9007199254740992.0;
 }
@@ -156,6 +206,7 @@ static int rng_index(rctx* r, int stream, int n) {
     if (v < 0 || v >= n) { r->e->error |= 4; v = 0; }
     return v;
   }
+  if (r->b->cfg.rng_mode == PGTG_RNG_NUMPY) return (int)np_bounded(r->e, stream, (uint32_t)n - 1u);
   return (int)(((uint64_t)philox_word(r, stream) * (uint64_t)n) >> 32);
 }
 
@@ -175,6 +226,16 @@ static int rng_choice_cdf(rctx* r, int stream, const double* cdf, int n) {
 /* Generator.choice(n, size=k, replace=False): k distinct indices in returned order.
  * Philox mode: sequential rejection sampling (spec shared with the product). */
 static void rng_distinct(rctx* r, int stream, int n, int k, int* out) {
+  if (r->b->cfg.rng_mode == PGTG_RNG_NUMPY) { /* Floyd's sampling + shuffle (_generator.pyx choice) */
+    for (int t = 0; t < k; t++) {
+      uint32_t j = (uint32_t)(n - k + t), v = np_bounded(r->e, stream, j);
+      int dup = 0;
+      for (int q = 0; q < t; q++) if (out[q] == (int)v) { dup = 1; break; }
+      out[t] = dup ? (int)j : (int)v;
+    }
+    for (int i = k - 1; i >= 1; i--) { int jj = (int)np_bounded(r->e, stream, (uint32_t)i); int a = out[i]; out[i] = out[jj]; out[jj] = a; }
+    return;
+  }
   for (int j = 0; j < k; j++) {
     if (r->b->cfg.rng_mode == PGTG_RNG_TAPE) {
       int v = (int)tape_next(r, stream, PGTG_DRAW_INDEX);
@@ -803,6 +864,7 @@ static void env_reset(ora_batch* b, ora_env* e) {
   e->episode++;
   e->elapsed = 0;
   memset(e->draw_k, 0, sizeof e->draw_k); e->blk_stream = -1;
+  if (b->cfg.rng_mode == PGTG_RNG_NUMPY) for (int s = 0; s < 5; s++) np_seed_child(e, s, 5u * (e->episode - 1u) + (uint32_t)s);
   if (b->cfg.fixed_map) {
     e->W = b->fw; e->H = b->fh;
     for (int t = 0; t < b->fw * b->fh; t++) {

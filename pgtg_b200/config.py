@@ -31,7 +31,7 @@ CH_ZERO, CH_WALLS, CH_GOALS, CH_TRAFFIC, CH_ICE, CH_BROKEN, CH_SAND = range(7)
 CH_LIGHT_GREEN, CH_LIGHT_YELLOW, CH_LIGHT_RED = 7, 8, 9
 CH_SUBGOAL, CH_FINAL_GOAL, CH_START, CH_USED_SUBGOAL, CH_CAR_SPAWNER = 10, 11, 12, 13, 14
 
-RNG_PHILOX, RNG_TAPE = 0, 1
+RNG_PHILOX, RNG_TAPE, RNG_NUMPY = 0, 1, 2
 STREAM_MAP, STREAM_CAR, STREAM_ICE, STREAM_BROKEN, STREAM_SAND = range(5)
 DRAW_DOUBLE, DRAW_INDEX = 0, 1
 
@@ -357,7 +357,7 @@ def make_config(
     max_episode_steps: int | None = None,
     seed: int = 0,
     env_id_base: int = 0,
-    rng_mode: int = RNG_PHILOX,
+    rng_mode: int | str = RNG_PHILOX,
     final_observation: bool = False,
     map_plan: MapPlan | dict | None = None,
     traffic_rules: list | None = None,
@@ -389,7 +389,11 @@ def make_config(
     c.num_envs = int(num_envs)
     c.env_id_base = int(env_id_base)
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    if isinstance(rng_mode, str):
+        rng_mode = {"philox": RNG_PHILOX, "tape": RNG_TAPE, "numpy": RNG_NUMPY}[rng_mode]
     c.rng_mode = int(rng_mode)
+    if c.rng_mode == RNG_NUMPY and (int(seed) + int(env_id_base) < 0 or int(seed) + int(env_id_base) + int(num_envs) >= 2 ** 64):
+        raise ValueError("numpy rng mode needs seeds in [0, 2**64)")
 
     plan = None
     if map_plan is not None:

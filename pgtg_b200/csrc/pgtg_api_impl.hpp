@@ -149,7 +149,7 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   if (c.sliding && (c.window_k < 0 || c.window_k > 15)) { why = "sliding_observation_window_size must be in 0..15"; return -1; }
   if (c.num_rules < 0 || c.num_rules > PGTG_MAX_RULES) { why = "too many traffic rules"; return -1; }
   if (c.light_green + c.light_yellow + c.light_red <= 0 || c.light_green + c.light_yellow + c.light_red > 0x7FFF) { why = "traffic light durations out of range"; return -1; }
-  if (c.rng_mode != PGTG_RNG_PHILOX && c.rng_mode != PGTG_RNG_TAPE) { why = "unknown rng_mode"; return -1; }
+  if (c.rng_mode != PGTG_RNG_PHILOX && c.rng_mode != PGTG_RNG_TAPE && c.rng_mode != PGTG_RNG_NUMPY) { why = "unknown rng_mode"; return -1; }
   if (c.max_cars > 0xFFFF) { why = "max_cars too large"; return -1; }
   d.N = c.num_envs; d.W = c.map_w; d.H = c.map_h; d.T = c.map_w * c.map_h; d.WS = c.map_w * TILE; d.HS = c.map_h * TILE;
   d.C = c.num_channels; d.P = c.sliding ? 2 * c.window_k + 1 : TILE; d.sliding = c.sliding; d.window_k = c.window_k;
@@ -189,7 +189,7 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   if (c.already_visited_position_penalty != 0) { d.vis_w = d.HS + 2; d.vis_words = ((d.WS + 2) * (d.HS + 2) + 31) / 32; }
   d.obs_bits = d.C * d.P * d.P;
   if (c.traffic_density > 0) { d.occ_words = (d.WS * d.HS + 15) / 16;  /* 2-bit counters */ d.spawner_cap = 2 * (d.W + d.H) + d.T; }
-  d.pregen = (c.rng_mode == PGTG_RNG_PHILOX && !c.fixed_map) ? 1 : 0;
+  d.pregen = (c.rng_mode != PGTG_RNG_TAPE && !c.fixed_map) ? 1 : 0;
   d.env_id_base = c.env_id_base; d.seed = c.seed;
   if (!c.fixed_map) {
     d.n_edge_tab = 2 * (d.W * (d.H - 1) + d.H * (d.W - 1));
@@ -228,6 +228,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   if (dc.occ_words) { A(occ, uint32_t, (size_t)dc.occ_words * N); A(spawners, uint16_t, (size_t)dc.spawner_cap * N); A(spawner_count, uint16_t, N); }
   A(key, uint64_t, N); A(error, uint32_t, N); A(ep_return, double, N);
   if (cfg->rng_mode == PGTG_RNG_TAPE) { A(cursor, int64_t, N); A(tape_end, int64_t, N); }
+  if (cfg->rng_mode == PGTG_RNG_NUMPY) { A(pcg, PcgState, 4 * N); p.pcg_stride = N; }
   A(obs_map, int8_t, N * dc.obs_bits + 16); A(obs_position, int32_t, 2 * N); A(obs_velocity, int32_t, 2 * N); A(obs_nsd, int32_t, N);
   A(reward, double, N); A(cost, double, N); A(terminated, uint8_t, N); A(truncated, uint8_t, N);
   A(step_state, int32_t, 4 * N); A(step_flags, uint8_t, N);

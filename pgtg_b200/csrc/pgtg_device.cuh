@@ -135,6 +135,12 @@ struct DevCfg {
   uint64_t seed;
 };
 
+// numpy mode: one PCG64 stream (pgtg_device.cuh, 'numpy-exact generator')
+struct PcgState {
+  uint64_t st_lo, st_hi, inc_lo, inc_hi;
+  uint32_t buf, has;  // PCG64's buffered upper half of the last 64-bit output (next_uint32)
+};
+
 // Device pointers (all owned by the handle).
 struct DevPtrs {
   // state, SoA
@@ -155,7 +161,9 @@ struct DevPtrs {
   uint32_t* occ;        // [occ_words][N] per-tick 2-bit car counters per square (cell x*HS+y), 3 = saturated
   uint16_t* spawners;   // [spawner_cap][N] car_spawner squares in x-major order (x | y << 8), built at reset
   uint16_t* spawner_count;  // [N]
-  uint64_t* key;        // [N] philox key (the env's seed)
+  uint64_t* key;        // [N] philox key / numpy entropy (the env's seed)
+  PcgState* pcg;        // [4][pcg_stride] numpy mode: car, ice, broken road, sand PCG64 streams
+  size_t pcg_stride;
   int64_t* cursor;      // [N] tape cursor
   int64_t* tape_end;    // [N]
   const double* tape_values;
@@ -240,6 +248,71 @@ PG_PHILOX_ATTR void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint
   }
 }
 
+// ---- numpy-exact generator (PGTG_RNG_NUMPY) ----------------------------------------------------------
+// Restates, for exactly the calls the reference makes, numpy's SeedSequence (hash pool, spawn keys,
+// generate_state), PCG64 (128-bit LCG, XSL-RR output, the buffered 32-bit half) and the Generator
+// methods random(), integers()/choice(n) (Lemire's 32-bit rejection), choice(p=...) (cdf +
+// searchsorted) and choice(n, k, replace=False) (Floyd's sampling + shuffle), so that SEEDS ALONE
+// reproduce the reference: env = Generator(PCG64(SeedSequence(seed))) (gymnasium 0.28.1 seeding),
+// reset number r spawns children 5r..5r+4 = map, car, ice, broken road, sand streams
+// (environment.py:593-599). Pinned against numpy itself in tests/test_numpy_rng.py.
+typedef unsigned __int128 pg_u128;
+PG_HD uint32_t ss_hashmix(uint32_t v, uint32_t& hc) { v ^= hc; hc *= 0x931e8875u; v *= hc; v ^= v >> 16; return v; }
+PG_HD uint32_t ss_mix(uint32_t x, uint32_t y) { uint32_t r = 0xca01f9ddu * x - 0x4973f715u * y; r ^= r >> 16; return r; }
+// PCG64 seeded by SeedSequence(entropy = seed, spawn_key = (child,)): the child streams of one reset
+PG_HD void pcg_seed_child(uint64_t seed, uint32_t child, PcgState& s) {
+  uint32_t ent[5] = {(uint32_t)seed, (uint32_t)(seed >> 32), 0u, 0u, child};  // run entropy padded to the pool, then the spawn key
+  uint32_t pool[4], hc = 0x43b0d7e5u;
+#pragma unroll
+  for (int i = 0; i < 4; i++) pool[i] = ss_hashmix(ent[i], hc);
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+      if (a != b) pool[b] = ss_mix(pool[b], ss_hashmix(pool[a], hc));
+#pragma unroll
+  for (int b = 0; b < 4; b++) pool[b] = ss_mix(pool[b], ss_hashmix(ent[4], hc));
+  uint32_t w[8], hb = 0x8b51f9ddu;  // generate_state(4, uint64)
+#pragma unroll
+  for (int i = 0; i < 8; i++) { uint32_t v = pool[i & 3] ^ hb; hb *= 0x58f38dedu; v *= hb; v ^= v >> 16; w[i] = v; }
+  pg_u128 initstate = ((pg_u128)((uint64_t)w[0] | (uint64_t)w[1] << 32) << 64) | ((uint64_t)w[2] | (uint64_t)w[3] << 32);
+  pg_u128 initseq = ((pg_u128)((uint64_t)w[4] | (uint64_t)w[5] << 32) << 64) | ((uint64_t)w[6] | (uint64_t)w[7] << 32);
+  const pg_u128 mult = ((pg_u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+  pg_u128 inc = (initseq << 1) | 1u, st = 0;
+  st = st * mult + inc;  // pcg_setseq_128_srandom_r
+  st += initstate;
+  st = st * mult + inc;
+  s.st_lo = (uint64_t)st; s.st_hi = (uint64_t)(st >> 64); s.inc_lo = (uint64_t)inc; s.inc_hi = (uint64_t)(inc >> 64);
+  s.buf = 0; s.has = 0;
+}
+PG_HD uint64_t pcg_next64(PcgState& s) {
+  const pg_u128 mult = ((pg_u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+  pg_u128 st = ((pg_u128)s.st_hi << 64) | s.st_lo, inc = ((pg_u128)s.inc_hi << 64) | s.inc_lo;
+  st = st * mult + inc;
+  s.st_lo = (uint64_t)st; s.st_hi = (uint64_t)(st >> 64);
+  uint64_t x = s.st_hi ^ s.st_lo;
+  unsigned r = (unsigned)(s.st_hi >> 58);
+  return (x >> r) | (x << ((64u - r) & 63u));
+}
+PG_HD uint32_t pcg_next32(PcgState& s) {
+  if (s.has) { s.has = 0; return s.buf; }
+  uint64_t n = pcg_next64(s);
+  s.has = 1; s.buf = (uint32_t)(n >> 32);
+  return (uint32_t)n;
+}
+// random_bounded_uint64(0, rng) for rng < 2^32 - 1: Lemire's method on 32-bit draws, inclusive bound
+PG_HD uint32_t pcg_bounded(PcgState& s, uint32_t rng) {
+  if (rng == 0) return 0;
+  uint32_t ex = rng + 1u;
+  uint64_t m = (uint64_t)pcg_next32(s) * ex;
+  uint32_t left = (uint32_t)m;
+  if (left < ex) {
+    uint32_t thr = (0u - ex) % ex;
+    while (left < thr) { m = (uint64_t)pcg_next32(s) * ex; left = (uint32_t)m; }
+  }
+  return (uint32_t)(m >> 32);
+}
+
 // Philox word stream (specification shared with the oracle): for a given (stream, tick, episode)
 // the 32-bit words come from consecutive Philox4x32-10 blocks, block b = philox(counter =
 // (b, tick, episode, stream), key = env seed), 4 words per block. An index draw takes ONE word
@@ -252,11 +325,42 @@ struct Rng {
   uint32_t kcount[5];  // words consumed per stream this tick
   uint32_t b0, b1, b2, b3, cur_block;
   int cur_stream;
+  PcgState pcg;        // numpy mode: the stream currently held in registers
+  bool pcg_dirty;
   PG_MEMBER Rng(const DevPtrs& p_, EnvRegs& e_, int env_) : p(p_), e(e_), env(env_) {
 #pragma unroll
     for (int i = 0; i < 5; i++) kcount[i] = 0;
     cur_stream = -1; cur_block = 0; b0 = b1 = b2 = b3 = 0;
+    pcg_dirty = false;
   }
+  // ---- numpy mode: stream residency --------------------------------------------------------------
+  // The map stream of an episode is a pure function of (seed, episode) and lives only while the map
+  // is built; the car / ice / broken-road / sand streams persist in HBM (p.pcg) across ticks.
+  PG_MEMBER void np_release() {
+    if (cur_stream > 0 && pcg_dirty) p.pcg[(size_t)(cur_stream - 1) * p.pcg_stride + env] = pcg;
+    pcg_dirty = false;
+  }
+  PG_MEMBER void np_acquire(int stream) {
+    if (cur_stream == stream) return;
+    np_release();
+    if (stream == PGTG_STREAM_MAP) pcg_seed_child(p.key[env], 5u * (e.episode - 1u), pcg);
+    else pcg = p.pcg[(size_t)(stream - 1) * p.pcg_stride + env];
+    cur_stream = stream;
+  }
+  // seed the four persistent streams of the episode that starts now (children 5r+1 .. 5r+4)
+  PG_MEMBER void np_begin_episode() {
+    np_release();
+    cur_stream = -1;
+    uint64_t seed = p.key[env];
+    for (int s = 1; s < 5; s++) {
+      PcgState st;
+      pcg_seed_child(seed, 5u * (e.episode - 1u) + (uint32_t)s, st);
+      p.pcg[(size_t)(s - 1) * p.pcg_stride + env] = st;
+    }
+  }
+  // must be called before the Rng goes out of scope (no-op outside numpy mode)
+  PG_MEMBER void flush() { if (RNG == PGTG_RNG_NUMPY) { np_release(); cur_stream = -1; } }
+
   PG_MEMBER uint32_t word(int stream) {
     uint32_t pos = kcount[stream]++;
     uint32_t b = pos >> 2;
@@ -277,8 +381,13 @@ struct Rng {
   // Generator.random()
   PG_MEMBER double uniform(int stream) {
     if (RNG == PGTG_RNG_TAPE) return tape_next(stream, PGTG_DRAW_DOUBLE);
+    if (RNG == PGTG_RNG_NUMPY) {
+      np_acquire(stream); pcg_dirty = true;
+      return pg_dmul((double)(pcg_next64(pcg) >> 11), 1.0 / 9007199254740992.0);
+    }
     uint32_t w0 = word(stream), w1 = word(stream);
-    return pg_ddiv(pg_dadd(pg_dmul((double)(w0 >> 5), 67108864.0), (double)(w1 >> 6)), 9007199254740992.0);
+    // (a * 2^26 + b) / 2^53: every step is exact in float64, so scaling by 2^-53 equals the division
+    return pg_dmul(pg_dadd(pg_dmul((double)(w0 >> 5), 67108864.0), (double)(w1 >> 6)), 1.0 / 9007199254740992.0);
   }
   // Generator.integers(0, n) / choice over n items; nothing is consumed for n == 1
   PG_MEMBER int index(int stream, int n) {
@@ -288,7 +397,16 @@ struct Rng {
       if (v < 0 || v >= n) { e.err |= 4; v = 0; }
       return v;
     }
+    if (RNG == PGTG_RNG_NUMPY) {
+      np_acquire(stream); pcg_dirty = true;
+      return (int)pcg_bounded(pcg, (uint32_t)n - 1u);
+    }
     return (int)pg_umulhi(word(stream), (uint32_t)n);
+  }
+  // numpy mode only: random_bounded_uint64(0, rng_inclusive) on `stream`
+  PG_MEMBER uint32_t np_bounded(int stream, uint32_t rng_inclusive) {
+    np_acquire(stream); pcg_dirty = true;
+    return pcg_bounded(pcg, rng_inclusive);
   }
   // Generator.choice(items, p=...): cdf.searchsorted(u, side="right")
   PG_MEMBER int choice_cdf(int stream, const double* cdf, int n) {

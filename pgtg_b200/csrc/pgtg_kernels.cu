@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
 
 // Map generation ahead of time: dense over the envs queued by the tick that just ran (every lane
 // busy, no CTA barrier after the staging, tiny shared-memory footprint -> high occupancy).
-template <int TMAX>
+template <int RNG, int TMAX>
 __global__ void __launch_bounds__(128) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t count = *p.regen_count;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128) pgtg_mapgen_kernel(const __grid_constant_
   stage_tables(c, p, sh, threadIdx.x, blockDim.x);
   __syncthreads();
   const uint32_t i = i0 + threadIdx.x;
-  if (i < count) phase_pregenerate<TMAX>(c, p, sh, threadIdx.x, p.regen_list[i]);
+  if (i < count) phase_pregenerate<RNG, TMAX>(c, p, sh, threadIdx.x, p.regen_list[i]);
 }
 
 struct FlatOrder { int plane[PGTG_MAX_CHANNELS]; };
@@ -224,33 +224,40 @@ static int launch_sized(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, 
   return launch_one<RNG, MODE, 256, PREGEN>(e, mask, seeds, actions, action_bytes, st);
 }
 
-template <int TMAX>
+template <int RNG, int TMAX>
 static int launch_mapgen(pgtg_env* e, cudaStream_t st) {
   const int B = 128;
   size_t smem = pgtg::mapgen_shared_bytes(e->dc, B);
-  auto kern = pgtg::pgtg_mapgen_kernel<TMAX>;
+  auto kern = pgtg::pgtg_mapgen_kernel<RNG, TMAX>;
   if (smem > 48 * 1024 && ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return -1;
   kern<<<(e->dc.N + B - 1) / B, B, smem, st>>>(e->dc, e->dp);
   return ck(cudaGetLastError());
 }
 
-static int bk_launch(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  bool tape = e->cfg.rng_mode == PGTG_RNG_TAPE;
+template <int RNG>
+static int launch_mode(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
   switch (mode) {
     case MODE_STEP:
-      if (tape) return launch_sized<PGTG_RNG_TAPE, MODE_STEP, false>(e, mask, seeds, actions, action_bytes, st);
-      return e->dc.pregen ? launch_sized<PGTG_RNG_PHILOX, MODE_STEP, true>(e, mask, seeds, actions, action_bytes, st)
-                          : launch_sized<PGTG_RNG_PHILOX, MODE_STEP, false>(e, mask, seeds, actions, action_bytes, st);
+      if (RNG != PGTG_RNG_TAPE && e->dc.pregen) return launch_sized<RNG, MODE_STEP, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
+      return launch_sized<RNG, MODE_STEP, false>(e, mask, seeds, actions, action_bytes, st);
     case MODE_RESET:
-      return tape ? launch_sized<PGTG_RNG_TAPE, MODE_RESET, false>(e, mask, seeds, actions, action_bytes, st)
-                  : launch_sized<PGTG_RNG_PHILOX, MODE_RESET, false>(e, mask, seeds, actions, action_bytes, st);
+      return launch_sized<RNG, MODE_RESET, false>(e, mask, seeds, actions, action_bytes, st);
     case MODE_MAPGEN:
-      if (e->dc.T <= 16) return launch_mapgen<16>(e, st);
-      if (e->dc.T <= 64) return launch_mapgen<64>(e, st);
-      return launch_mapgen<256>(e, st);
+      if (RNG == PGTG_RNG_TAPE) return -1;
+      if (e->dc.T <= 16) return launch_mapgen<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, 16>(e, st);
+      if (e->dc.T <= 64) return launch_mapgen<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, 64>(e, st);
+      return launch_mapgen<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, 256>(e, st);
     default:
       return launch_one<PGTG_RNG_PHILOX, MODE_OBSERVE, 16, false>(e, mask, seeds, actions, action_bytes, st);
+  }
+}
+
+static int bk_launch(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (e->cfg.rng_mode) {
+    case PGTG_RNG_TAPE: return launch_mode<PGTG_RNG_TAPE>(e, mode, mask, seeds, actions, action_bytes, st);
+    case PGTG_RNG_NUMPY: return launch_mode<PGTG_RNG_NUMPY>(e, mode, mask, seeds, actions, action_bytes, st);
+    default: return launch_mode<PGTG_RNG_PHILOX>(e, mode, mask, seeds, actions, action_bytes, st);
   }
 }
 

@@ -190,6 +190,7 @@ PG_HDN TrafficIO advance_cars(const DevCfg& c, const DevPtrs& p, const MapView m
     }
   }
   for (int i = 0; i < s; i++) car_slot(c, p, env, w + i) = car_slot(c, p, env, c.max_cars + i);
+  rng.flush();
   TrafficIO io;
   io.next_car_id = e.next_car_id; io.err = e.err; io.cursor = e.cursor;
   return io;
@@ -201,7 +202,7 @@ PG_HDN uint32_t create_initial_traffic(const DevCfg& c, const DevPtrs& p, const 
   // _create_initial_traffic (environment.py:830-879). Cold, self-contained unit (registers by value).
   EnvRegs e = e_in;
   Rng<RNG> rng(p, e, env);
-  rng.kcount[PGTG_STREAM_CAR] = car_words;
+  if (RNG == PGTG_RNG_PHILOX) rng.kcount[PGTG_STREAM_CAR] = car_words;
   // lane squares per global column, x-major (traffic_spawnable_positions, map.py:35-38)
   uint16_t colpre[TILE * 16 + 1];
   int ncol = c.W * TILE, num_positions = 0;
@@ -219,6 +220,24 @@ PG_HDN uint32_t create_initial_traffic(const DevCfg& c, const DevPtrs& p, const 
     // Philox mode draws with rejection against a bitmap of the indices already taken (the
     // occupancy words double as that scratch)
     if (RNG != PGTG_RNG_TAPE) for (int i = 0; i < (num_positions + 31) / 32; i++) p.occ[(size_t)i * c.N + env] = 0;
+    if (RNG == PGTG_RNG_NUMPY) {
+      // Generator.choice(n, size=k, replace=False): Floyd's sampling (membership via the bitmap,
+      // numpy uses a hash set) followed by the in-place shuffle of the k values
+      for (int t = 0; t < num_cars; t++) {
+        uint32_t j = (uint32_t)(num_positions - num_cars + t);
+        uint32_t v = rng.np_bounded(PGTG_STREAM_CAR, j);
+        uint32_t& wv = p.occ[(size_t)(v >> 5) * c.N + env];
+        if ((wv >> (v & 31)) & 1u) { v = j; p.occ[(size_t)(j >> 5) * c.N + env] |= 1u << (j & 31); }
+        else wv |= 1u << (v & 31);
+        car_slot(c, p, env, t) = (uint64_t)v;
+      }
+      for (int i = num_cars - 1; i >= 1; i--) {
+        int jj = (int)rng.np_bounded(PGTG_STREAM_CAR, (uint32_t)i);
+        uint64_t a = car_slot(c, p, env, i);
+        car_slot(c, p, env, i) = car_slot(c, p, env, jj);
+        car_slot(c, p, env, jj) = a;
+      }
+    } else
     for (int j = 0; j < num_cars; j++) {
       int v;
       if (RNG == PGTG_RNG_TAPE) {
@@ -252,6 +271,7 @@ PG_HDN uint32_t create_initial_traffic(const DevCfg& c, const DevPtrs& p, const 
       car_slot(c, p, env, j) = car_pack(car);
     }
   }
+  rng.flush();
   *cursor_out = e.cursor; *err_out = e.err;
   return (uint32_t)num_cars | e.next_car_id << 16;
 }
@@ -419,6 +439,7 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
     if (c.separate_reward_cost) r.cost += c.standing_penalty; else r.reward -= c.standing_penalty;
   }
   e.x = cx; e.y = cy;
+  rng.flush();
   if (c.separate_reward_cost) r.reward = perf;  // :1271-1281
   return r;
 }
@@ -767,6 +788,7 @@ PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
     for (int i = 0; i < c.vis_words; i++) p.visited[(size_t)i * c.N + env] = 0;
     visited_test_set(c, p, env, e.x, e.y, true);  // positions_path = [position] (:643)
   }
+  if (RNG == PGTG_RNG_NUMPY) rng.np_begin_episode();  // children 5r+1..5r+4 of this reset (:593-599)
   if (c.traffic_density > 0) {  // :652-653
     build_spawner_list(c, p, m, env);
     int64_t cur; uint32_t err;

@@ -86,7 +86,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
 }
 
-template <int TMAX>
+template <int RNG, int TMAX>
 static void run_mapgen(pgtg_env* h) {
   const DevCfg& c = h->dc;
   const DevPtrs& p = h->dp;
@@ -98,7 +98,7 @@ static void run_mapgen(pgtg_env* h) {
     memset(smem, 0xA5, bytes);
     BlockShared sh = carve_mapgen(smem, c, B);
     for (int t = 0; t < B; t++) stage_tables(c, p, sh, t, B);
-    for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<TMAX>(c, p, sh, t, p.regen_list[i0 + t]);
+    for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<RNG, TMAX>(c, p, sh, t, p.regen_list[i0 + t]);
   }
   free(smem);
 }
@@ -106,7 +106,8 @@ static void run_mapgen(pgtg_env* h) {
 static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void*) {
   int T = h->dc.T;  // same TMAX dispatch as the CUDA backend
   if (mode == MODE_MAPGEN) {
-    if (T <= 16) run_mapgen<16>(h); else if (T <= 64) run_mapgen<64>(h); else run_mapgen<256>(h);
+    if (h->cfg.rng_mode == PGTG_RNG_NUMPY) { if (T <= 16) run_mapgen<PGTG_RNG_NUMPY, 16>(h); else if (T <= 64) run_mapgen<PGTG_RNG_NUMPY, 64>(h); else run_mapgen<PGTG_RNG_NUMPY, 256>(h); }
+    else { if (T <= 16) run_mapgen<PGTG_RNG_PHILOX, 16>(h); else if (T <= 64) run_mapgen<PGTG_RNG_PHILOX, 64>(h); else run_mapgen<PGTG_RNG_PHILOX, 256>(h); }
     return 0;
   }
   size_t bytes = block_shared_bytes(h->dc, h->block);
@@ -116,7 +117,9 @@ static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* 
     memset(smem, 0xA5, bytes);  // shared memory starts undefined on the device too
     bool tape = h->cfg.rng_mode == PGTG_RNG_TAPE;
 #define RUN(R, M, G) run_block<R, M, G>(h, mode, mask, seeds, actions, action_bytes, b, smem)
-#define RUN3(M) do { if (tape) RUN(PGTG_RNG_TAPE, M, false); else if (h->dc.pregen) RUN(PGTG_RNG_PHILOX, M, true); else RUN(PGTG_RNG_PHILOX, M, false); } while (0)
+#define RUN3(M) do { bool np = h->cfg.rng_mode == PGTG_RNG_NUMPY; if (tape) RUN(PGTG_RNG_TAPE, M, false); \
+    else if (np) { if (h->dc.pregen) RUN(PGTG_RNG_NUMPY, M, true); else RUN(PGTG_RNG_NUMPY, M, false); } \
+    else if (h->dc.pregen) RUN(PGTG_RNG_PHILOX, M, true); else RUN(PGTG_RNG_PHILOX, M, false); } while (0)
     if (T <= 16) RUN3(16); else if (T <= 64) RUN3(64); else RUN3(256);
 #undef RUN3
 #undef RUN

@@ -65,10 +65,15 @@ def check_live(env, tr, t, get_state=True):
         assert not st["error"].any(), f"tick {t}: env error flags {st['error'][st['error'] != 0][:5]}"
 
 
-def replay(env, tr, get_state=True, ticks=None):
-    """env must be constructed with rng_mode=RNG_TAPE, final_observation=True and the trace's kwargs."""
-    env.load_draws(tr["tape_values"], tr["tape_tags"], tr["tape_offsets"])
-    env.reset()
+def replay(env, tr, get_state=True, ticks=None, from_seeds=False):
+    """env must be constructed with final_observation=True and the trace's kwargs, and either
+    rng_mode=RNG_TAPE (the recorded draws are loaded) or, with from_seeds=True, rng_mode=RNG_NUMPY:
+    then nothing but the reference's seeds (seed + i) goes in."""
+    if from_seeds:
+        env.reset(seeds=tr["meta"]["seed"] + np.arange(tr["meta"]["num_envs"], dtype=np.int64))
+    else:
+        env.load_draws(tr["tape_values"], tr["tape_tags"], tr["tape_offsets"])
+        env.reset()
     check_live(env, tr, 0, get_state)
     T = tr["actions"].shape[0] if ticks is None else ticks
     for t in range(T):
@@ -86,6 +91,6 @@ def replay(env, tr, get_state=True, ticks=None):
             _eq("final_obs_velocity", env.final_obs_velocity[done], tr["final_obs_velocity"][t][done], t)
             _eq("final_obs_nsd", env.final_obs_nsd[done], tr["final_obs_nsd"][t][done], t)
         check_live(env, tr, t + 1, get_state)
-    if ticks is None:
+    if ticks is None and not from_seeds:
         st = env.get_state()
         _eq("draw_cursor (all recorded draws consumed)", st["draw_cursor"], tr["tape_offsets"][1:], T)

@@ -71,3 +71,27 @@ def test_default_64k_envs():
     env, ora = _pair(65536, seed=99)
     assert pc.compare(env, ora, 12, check_obs_every=3) > 100000
     env.close(); ora.close()
+
+
+@pytest.mark.gpu
+def test_numpy_mode_config2_4096_envs_from_seeds():
+    """BASELINE config 2 in numpy-exact mode: 4096 envs on the fixed map, seeds s+i only; the oracle runs
+    the same numpy restatement (itself pinned against the reference's traces from seeds)."""
+    import json, os
+
+    tr = json.loads(bytes(np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_config2_fixed_map.npz"))["meta"]).decode())
+    env, ora = _pair(4096, rng_mode="numpy", map_plan=tr["maps"]["serpentine_5x3"])
+    seeds = 1000 + np.arange(4096, dtype=np.int64)
+    # both sides take the seeds through reset(seed) like the reference
+    env_reset, ora_reset = env.reset, ora.reset
+    env.reset = lambda: env_reset(seeds=seeds)
+    ora.reset = lambda: ora_reset(seeds=seeds)
+    assert pc.compare(env, ora, 128, state_every=64) > 1000
+    env.close(); ora.close()
+
+
+@pytest.mark.gpu
+def test_numpy_mode_traffic_obstacles_procedural():
+    env, ora = _pair(2048, rng_mode="numpy", traffic_density=0.05, random_map_obstacle_probability=0.3, seed=77)
+    assert pc.compare(env, ora, 40, state_every=20) > 500
+    env.close(); ora.close()
