@@ -270,6 +270,9 @@ int pgtg_flatten(pgtg_env* env, const int32_t* plane_order, void* stream, float*
  * with CUDA events on the launching stream; pgtg_timing synchronises and returns the summed
  * durations in ms of the tick kernel and of the map-generation kernel over the recorded ticks. */
 int pgtg_enable_timing(pgtg_env* env, int max_steps);
+/* Map generation normally overlaps the next tick (side stream, small persistent grid). on = 0 runs the two
+ * kernels back to back on the caller's stream instead, e.g. to time each kernel alone. Synchronises. */
+int pgtg_set_overlap(pgtg_env* env, int on);
 int pgtg_timing(pgtg_env* env, double* tick_ms, double* mapgen_ms, int* steps);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t pgtg_launch_count(pgtg_env* env);

@@ -52,6 +52,7 @@ EXPORTS = {
     "pgtg_launch_count": (C.c_int64, [C.c_void_p]),
     "pgtg_flatten": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "pgtg_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "pgtg_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "pgtg_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }
 

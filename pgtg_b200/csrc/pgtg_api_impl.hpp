@@ -11,12 +11,15 @@
 //   int bk_launch(pgtg_env*, int mode, const uint8_t* mask_dev, const int64_t* seeds_dev,
 //                 const void* actions_dev, int action_bytes, void* stream);
 //   const char* bk_error();  int bk_dl_device_type();
+//   int bk_side_create(void** stream, void** ev_tick, void** ev_map0, void** ev_map1, int* sm_count);
+//   void bk_side_destroy(void*, void*, void*, void*);  int bk_stream_wait(void* stream, void* ev);
 //   void* bk_event_create();  void bk_event_destroy(void*);  int bk_event_record(void* ev, void* stream);
 //   double bk_event_elapsed(void* a, void* b);
 //   int bk_stats_reduce(pgtg_env*, void* stream);  int bk_stats_reset(pgtg_env*, void* stream);
 #pragma once
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -39,6 +42,11 @@ struct pgtg_env {
   std::vector<void*> allocs;
   bool have_fixed, have_tape, did_reset;
   int nblk;             // CTAs per launch
+  // pregen pipeline: the persistent map-generation kernel runs on a side stream and overlaps the next tick
+  void* side_stream; void* ev_tick; void* ev_map[2];
+  uint64_t launch_index;
+  int mapgen_grid;      // CTAs of the persistent map-generation kernel (0 = one per 128 requests)
+  int mapgen_grid_overlap; bool overlap;  // overlap on: side stream + small grid; off: same stream, full grid
   // optional per-kernel timing (CUDA events on the launching stream around each kernel of a tick)
   bool timing; std::vector<void*> tev; int tev_used;
   // flattened observation (FlattenObservation view for SB3-style consumers), allocated on first use
@@ -212,6 +220,8 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   e->cfg = *cfg; e->dc = dc; e->device = device; e->launches = 0;
   e->have_fixed = e->have_tape = e->did_reset = false;
   e->timing = false; e->tev_used = 0;
+  e->side_stream = e->ev_tick = e->ev_map[0] = e->ev_map[1] = nullptr;
+  e->launch_index = 0; e->mapgen_grid = 0;
   e->flat = nullptr; e->flat_dim = 0;
   memset(&e->dp, 0, sizeof e->dp);
   if (bk_pick_block(e->dc, &e->block, &e->smem)) { delete e; return fail(PGTG_ERR_INVALID, "observation window too large for shared memory"); }
@@ -223,7 +233,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
 #define A(field, type, count) ok = ok && ((p.field = dev_alloc<type>(e, (count))) != nullptr)
   A(agent, short4, N); A(misc, uint32_t, N); A(elapsed, uint32_t, N); A(episode, uint32_t, N); A(next_car_id, uint32_t, N);
   A(plan, uint32_t, N); A(tiles, uint16_t, N * dc.T + 8);
-  if (dc.pregen) { A(next_tiles, uint16_t, N * dc.T + 8); A(next_plan, uint32_t, N); A(regen_list, int32_t, N); A(regen_count, uint32_t, 4); } A(cars, uint64_t, 2 * (size_t)dc.max_cars * N);
+  if (dc.pregen) { A(next_tiles, uint16_t, 2 * N * dc.T + 8); A(next_plan, uint32_t, 2 * N); A(regen_list, uint2, 4 * N); A(regen_count, uint32_t, 4); } A(cars, uint64_t, 2 * (size_t)dc.max_cars * N);
   if (dc.vis_words) A(visited, uint32_t, (size_t)dc.vis_words * N);
   if (dc.occ_words) { A(occ, uint32_t, (size_t)dc.occ_words * N); A(spawners, uint16_t, (size_t)dc.spawner_cap * N); A(spawner_count, uint16_t, N); }
   A(key, uint64_t, N); A(error, uint32_t, N); A(ep_return, double, N);
@@ -279,6 +289,17 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     bk_h2d(r, cfg->rules, sizeof(pgtg_rule) * PGTG_MAX_RULES, nullptr);
     p.dirlut = d; p.rules = r;
   }
+  if (e->dc.pregen) {
+    int sms = 0;
+    if (bk_side_create(&e->side_stream, &e->ev_tick, &e->ev_map[0], &e->ev_map[1], &sms)) {
+      pgtg_destroy(e);
+      return fail(PGTG_ERR_CUDA, std::string("cannot create the map-generation stream: ") + bk_error());
+    }
+    const char* env_ctas = getenv("PGTG_MAPGEN_CTAS_PER_SM");
+    int per_sm = env_ctas ? atoi(env_ctas) : 4;
+    e->mapgen_grid = per_sm > 0 ? sms * per_sm : 0;
+    e->mapgen_grid_overlap = e->mapgen_grid; e->overlap = true;
+  }
   bk_sync(nullptr);
   *out = e;
   return PGTG_OK;
@@ -287,6 +308,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
 extern "C" int pgtg_destroy(pgtg_env* e) {
   if (!e) return PGTG_OK;
   bk_set_device(e->device);
+  bk_side_destroy(e->side_stream, e->ev_tick, e->ev_map[0], e->ev_map[1]);
   bk_sync(nullptr);
   for (void* ev : e->tev) bk_event_destroy(ev);
   for (void* a : e->allocs) bk_free(a);
@@ -360,6 +382,46 @@ extern "C" int pgtg_load_draws(pgtg_env* e, const double* values, const uint8_t*
   return PGTG_OK;
 }
 
+// One launch of the pregen pipeline. Launch L appends its map requests to queue L&1 and
+// reads only ring slots filled by map generations <= L-2, so the map generation of launch L-1 (side
+// stream, small persistent grid) runs concurrently with the tick of launch L. `join` makes the caller's
+// stream wait for the generation just enqueued (full resets rewrite both ring slots).
+static int run_pipeline(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream, bool join) {
+  if (!e->dc.pregen) {
+    if (bk_launch(e, mode, mask, seeds, actions, action_bytes, stream)) return -1;
+    e->launches++;
+    return 0;
+  }
+  int par = (int)(e->launch_index & 1);
+  e->dp.parity = par;
+  // queue `par` was last read, and its ring slots last written, by the map generation of launch L-2
+  if (e->launch_index >= 2 && bk_stream_wait(stream, e->ev_map[par])) return -1;
+  if (bk_memset_async(e->dp.regen_count + par, 0, 4, stream)) return -1;
+  bool timed = mode == MODE_STEP && e->timing && e->tev_used + 4 <= (int)e->tev.size();
+  if (timed) bk_event_record(e->tev[e->tev_used], stream);
+  if (bk_launch(e, mode, mask, seeds, actions, action_bytes, stream)) return -1;
+  e->launches++;
+  if (timed) bk_event_record(e->tev[e->tev_used + 1], stream);
+  void* ms = e->overlap ? e->side_stream : stream;  // overlap off: the generation follows the tick on the caller's stream
+  if (e->overlap && (bk_event_record(e->ev_tick, stream) || bk_stream_wait(e->side_stream, e->ev_tick))) return -1;
+  if (timed) bk_event_record(e->tev[e->tev_used + 2], ms);
+  if (bk_launch(e, MODE_MAPGEN, nullptr, nullptr, nullptr, 0, ms)) return -1;
+  e->launches++;
+  if (timed) { bk_event_record(e->tev[e->tev_used + 3], ms); e->tev_used += 4; }
+  if (bk_event_record(e->ev_map[par], ms)) return -1;
+  if (join && bk_stream_wait(stream, e->ev_map[par])) return -1;
+  e->launch_index++;
+  return 0;
+}
+
+// make `stream` wait for every map generation in flight (before resets, host reads and timing joins)
+static int join_side(pgtg_env* e, void* stream) {
+  if (!e->dc.pregen || e->launch_index == 0) return 0;
+  if (bk_stream_wait(stream, e->ev_map[0])) return -1;
+  if (e->launch_index >= 2 && bk_stream_wait(stream, e->ev_map[1])) return -1;
+  return 0;
+}
+
 static int check_ready(pgtg_env* e) {
   if (!e) return fail(PGTG_ERR_INVALID, "null handle");
   if (e->cfg.fixed_map && !e->have_fixed) return fail(PGTG_ERR_STATE, "fixed_map config: call pgtg_load_fixed_map first");
@@ -375,14 +437,10 @@ extern "C" int pgtg_reset(pgtg_env* e, const int64_t* seeds, const uint8_t* mask
   if (!e->did_reset && mask) return fail(PGTG_ERR_STATE, "the first reset must cover all envs");
   if (seeds) bk_h2d(e->seeds_dev, seeds, N * 8, stream);
   if (mask) bk_h2d(e->mask_dev, mask, N, stream);
-  if (e->dc.pregen && bk_memset_async(e->dp.regen_count, 0, 4, stream)) return fail(PGTG_ERR_CUDA, std::string("memset failed: ") + bk_error());
-  if (bk_launch(e, MODE_RESET, mask ? e->mask_dev : nullptr, seeds ? e->seeds_dev : nullptr, nullptr, 0, stream))
+  // a reset rewrites both ring slots of the envs it touches: let every map generation in flight finish first
+  if (join_side(e, stream)) return fail(PGTG_ERR_CUDA, std::string("stream wait failed: ") + bk_error());
+  if (run_pipeline(e, MODE_RESET, mask ? e->mask_dev : nullptr, seeds ? e->seeds_dev : nullptr, nullptr, 0, stream, true))
     return fail(PGTG_ERR_CUDA, std::string("reset launch failed: ") + bk_error());
-  e->launches++;
-  if (e->dc.pregen) {
-    if (bk_launch(e, MODE_MAPGEN, nullptr, nullptr, nullptr, 0, stream)) return fail(PGTG_ERR_CUDA, std::string("mapgen launch failed: ") + bk_error());
-    e->launches++;
-  }
   e->did_reset = true;
   return PGTG_OK;
 }
@@ -393,18 +451,17 @@ extern "C" int pgtg_step(pgtg_env* e, const void* actions_dev, int action_bytes,
   if (!e->did_reset) return fail(PGTG_ERR_STATE, "step before reset");
   if (!actions_dev || (action_bytes != 4 && action_bytes != 8)) return fail(PGTG_ERR_INVALID, "actions must be device int32 or int64");
   bk_set_device(e->device);
-  if (e->dc.pregen && bk_memset_async(e->dp.regen_count, 0, 4, stream)) return fail(PGTG_ERR_CUDA, std::string("memset failed: ") + bk_error());
-  bool timed = e->timing && e->tev_used + 3 <= (int)e->tev.size();
-  if (timed) bk_event_record(e->tev[e->tev_used], stream);
-  if (bk_launch(e, MODE_STEP, nullptr, nullptr, actions_dev, action_bytes, stream))
-    return fail(PGTG_ERR_CUDA, std::string("step launch failed: ") + bk_error());
-  e->launches++;
-  if (timed) bk_event_record(e->tev[e->tev_used + 1], stream);
-  if (e->dc.pregen) {  // build the next map of every env that just consumed one
-    if (bk_launch(e, MODE_MAPGEN, nullptr, nullptr, nullptr, 0, stream)) return fail(PGTG_ERR_CUDA, std::string("mapgen launch failed: ") + bk_error());
+  if (e->dc.pregen) {
+    if (run_pipeline(e, MODE_STEP, nullptr, nullptr, actions_dev, action_bytes, stream, false))
+      return fail(PGTG_ERR_CUDA, std::string("step launch failed: ") + bk_error());
+  } else {
+    bool timed = e->timing && e->tev_used + 4 <= (int)e->tev.size();
+    if (timed) bk_event_record(e->tev[e->tev_used], stream);
+    if (bk_launch(e, MODE_STEP, nullptr, nullptr, actions_dev, action_bytes, stream))
+      return fail(PGTG_ERR_CUDA, std::string("step launch failed: ") + bk_error());
     e->launches++;
+    if (timed) { for (int k = 1; k < 4; k++) bk_event_record(e->tev[e->tev_used + k], stream); e->tev_used += 4; }
   }
-  if (timed) { bk_event_record(e->tev[e->tev_used + 2], stream); e->tev_used += 3; }
   return PGTG_OK;
 }
 
@@ -594,6 +651,7 @@ extern "C" int pgtg_set_state(pgtg_env* e, const pgtg_state* s) {
 extern "C" int pgtg_reduce_stats(pgtg_env* e, void* stream) {
   if (!e) return fail(PGTG_ERR_INVALID, "null handle");
   bk_set_device(e->device);
+  if (join_side(e, stream)) return fail(PGTG_ERR_CUDA, std::string("stream wait failed: ") + bk_error());
   if (bk_stats_reduce(e, stream)) return fail(PGTG_ERR_CUDA, std::string("stats reduction failed: ") + bk_error());
   return PGTG_OK;
 }
@@ -651,11 +709,22 @@ extern "C" int pgtg_enable_timing(pgtg_env* e, int max_steps) {
   bk_set_device(e->device);
   e->timing = max_steps > 0;
   e->tev_used = 0;
-  while ((int)e->tev.size() < 3 * max_steps) {
+  while ((int)e->tev.size() < 4 * max_steps) {
     void* ev = bk_event_create();
     if (!ev) return fail(PGTG_ERR_CUDA, std::string("event creation failed: ") + bk_error());
     e->tev.push_back(ev);
   }
+  return PGTG_OK;
+}
+
+// Overlap of map generation with the next tick (default on). Off = the two kernels run back to back on
+// the caller's stream with a full-size generation grid: used to time each kernel alone.
+extern "C" int pgtg_set_overlap(pgtg_env* e, int on) {
+  if (!e) return fail(PGTG_ERR_INVALID, "null handle");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  e->overlap = on != 0;
+  e->mapgen_grid = on ? e->mapgen_grid_overlap : 0;
   return PGTG_OK;
 }
 
@@ -664,10 +733,10 @@ extern "C" int pgtg_timing(pgtg_env* e, double* tick_ms, double* mapgen_ms, int*
   bk_set_device(e->device);
   if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
   *tick_ms = *mapgen_ms = 0;
-  *steps = e->tev_used / 3;
-  for (int i = 0; i + 2 < e->tev_used; i += 3) {
+  *steps = e->tev_used / 4;
+  for (int i = 0; i + 3 < e->tev_used; i += 4) {  // [tick begin, tick end] on the caller's stream, [mapgen begin, end] on the side stream
     *tick_ms += bk_event_elapsed(e->tev[i], e->tev[i + 1]);
-    *mapgen_ms += bk_event_elapsed(e->tev[i + 1], e->tev[i + 2]);
+    *mapgen_ms += bk_event_elapsed(e->tev[i + 2], e->tev[i + 3]);
   }
   e->tev_used = 0;
   return PGTG_OK;

@@ -151,10 +151,13 @@ struct DevPtrs {
   uint32_t* next_car_id;  // [N]
   uint32_t* plan;       // [N]
   uint16_t* tiles;      // [N][T]
-  uint16_t* next_tiles; // [N][T] pre-generated map of each env's next episode (pregen mode)
-  uint32_t* next_plan;  // [N]
-  int32_t* regen_list;  // [N] envs whose next map must be generated after this launch
-  uint32_t* regen_count; // [1]
+  // pregen mode: a ring of two pre-generated maps per env; slot (k & 1) holds the map of episode k
+  uint16_t* next_tiles; // [2][N][T]
+  uint32_t* next_plan;  // [2][N]
+  // map requests (env, episode), double-buffered by launch parity
+  uint2* regen_list;    // [2][2N]
+  uint32_t* regen_count; // [2]
+  int parity;           // launch index & 1: this launch appends to queue `parity`
   uint64_t* cars;       // [2 * max_cars][N], second half = same-tick respawn scratch
   uint32_t* visited;    // [vis_words][N] or null
   // traffic helpers (allocated when traffic_density > 0)

@@ -8,6 +8,7 @@
 // (observation write + SoA state scan), see DESIGN.md for the byte accounting.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "pgtg_phases.cuh"
 
@@ -23,6 +24,27 @@ static int bk_d2h(void* d, const void* s, size_t n, void* st) { return ck(cudaMe
 static int bk_memset(void* d, int v, size_t n) { return ck(cudaMemset(d, v, n)); }
 static int bk_memset_async(void* d, int v, size_t n, void* st) { return ck(cudaMemsetAsync(d, v, n, (cudaStream_t)st)); }
 static int bk_sync(void* st) { return ck(st ? cudaStreamSynchronize((cudaStream_t)st) : cudaDeviceSynchronize()); }
+// side stream (highest priority) for the persistent map-generation kernel, and its events
+static int bk_side_create(void** stream, void** ev_tick, void** ev_map0, void** ev_map1, int* sm_count) {
+  int lo = 0, hi = 0, dev = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaStream_t s; cudaEvent_t a, b, c;
+  const char* pr = getenv("PGTG_MAPGEN_PRIORITY");  // experiment knob: hi (default) | lo
+  if (ck(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, (pr && pr[0] == 'l') ? lo : hi))) return -1;
+  if (ck(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)) || ck(cudaEventCreateWithFlags(&b, cudaEventDisableTiming)) ||
+      ck(cudaEventCreateWithFlags(&c, cudaEventDisableTiming))) return -1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev);
+  *stream = s; *ev_tick = a; *ev_map0 = b; *ev_map1 = c;
+  return 0;
+}
+static void bk_side_destroy(void* stream, void* a, void* b, void* c) {
+  if (stream) { cudaStreamSynchronize((cudaStream_t)stream); cudaStreamDestroy((cudaStream_t)stream); }
+  if (a) cudaEventDestroy((cudaEvent_t)a);
+  if (b) cudaEventDestroy((cudaEvent_t)b);
+  if (c) cudaEventDestroy((cudaEvent_t)c);
+}
+static int bk_stream_wait(void* st, void* ev) { return ck(cudaStreamWaitEvent((cudaStream_t)st, (cudaEvent_t)ev, 0)); }
 static int bk_dl_device_type() { return 2; }  // kDLCUDA
 static void* bk_event_create() { cudaEvent_t ev; if (ck(cudaEventCreate(&ev))) return nullptr; return ev; }
 static void bk_event_destroy(void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
@@ -118,10 +140,20 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
   }
   __syncthreads();
 
-  if (MODE != MODE_OBSERVE && c.pregen && n_done) {  // CTA-uniform: queue these envs for the map-generation kernel
-    if (tid == 0) sh.counters[20] = (int)atomicAdd(p.regen_count, (uint32_t)n_done);
+  if (MODE != MODE_OBSERVE && c.pregen && n_done) {
+    // CTA-uniform: queue map requests for the map-generation kernel. An env that starts episode k
+    // frees ring slot (k & 1): ask for the map of episode k + 2 (a full reset also needs k + 1).
+    const int per = MODE == MODE_RESET ? 2 : 1;
+    if (tid == 0) sh.counters[20] = (int)atomicAdd(p.regen_count + p.parity, (uint32_t)(n_done * per));
     __syncthreads();
-    if (tid < n_done) p.regen_list[sh.counters[20] + tid] = env0 + sh.done_list[tid];
+    if (tid < n_done) {
+      int local = sh.done_list[tid];
+      uint32_t k = sh.regs[local].episode + 1u;  // the episode this env is about to start
+      uint2* q = p.regen_list + (size_t)p.parity * 2 * c.N + sh.counters[20] + tid * per;
+      uint2 r; r.x = (uint32_t)(env0 + local);
+      if (MODE == MODE_RESET) { r.y = k + 1u; q[0] = r; r.y = k + 2u; q[1] = r; }
+      else { r.y = k + 2u; q[0] = r; }
+    }
   }
 
   if (MODE == MODE_STEP && c.write_final_obs && n_done) {  // CTA-uniform condition
@@ -147,17 +179,22 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
 
 // Map generation ahead of time: dense over the envs queued by the tick that just ran (every lane
 // busy, no CTA barrier after the staging, tiny shared-memory footprint -> high occupancy).
+// Map generation ahead of time: a small PERSISTENT grid (a few CTAs per SM, grid-stride over the
+// request queue) so that it only occupies a slice of each SM's registers and the tick kernel of the
+// next launch co-resides with it: this kernel is ALU-bound, the tick is HBM-bound.
 template <int RNG, int TMAX>
-__global__ void __launch_bounds__(128) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p) {
+__global__ void __launch_bounds__(128) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const uint32_t count = *p.regen_count;
-  const uint32_t i0 = blockIdx.x * blockDim.x;
-  if (i0 >= count) return;
+  const uint32_t count = p.regen_count[parity];
+  if (blockIdx.x * blockDim.x >= count) return;
   BlockShared sh = carve_mapgen(smem, c, blockDim.x);
   stage_tables(c, p, sh, threadIdx.x, blockDim.x);
   __syncthreads();
-  const uint32_t i = i0 + threadIdx.x;
-  if (i < count) phase_pregenerate<RNG, TMAX>(c, p, sh, threadIdx.x, p.regen_list[i]);
+  const uint2* list = p.regen_list + (size_t)parity * 2 * c.N;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    uint2 r = list[i];
+    phase_pregenerate<RNG, TMAX>(c, p, sh, threadIdx.x, (int)r.x, r.y);
+  }
 }
 
 struct FlatOrder { int plane[PGTG_MAX_CHANNELS]; };
@@ -208,6 +245,10 @@ static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem) {
 template <int RNG, int MODE, int TMAX, bool PREGEN>
 static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
   auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN>;
+  // same L1/shared carveout as the map-generation kernel: an SM cannot host CTAs of two kernels with
+  // different carveouts, which would serialise the two (measured: no overlap at all without this)
+  static bool carve_set = false;
+  if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve_set = true; }
   if (e->smem > 48 * 1024) {
     if (ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem))) return -1;
   }
@@ -229,8 +270,12 @@ static int launch_mapgen(pgtg_env* e, cudaStream_t st) {
   const int B = 128;
   size_t smem = pgtg::mapgen_shared_bytes(e->dc, B);
   auto kern = pgtg::pgtg_mapgen_kernel<RNG, TMAX>;
+  static bool carve_set = false;
+  if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve_set = true; }
   if (smem > 48 * 1024 && ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return -1;
-  kern<<<(e->dc.N + B - 1) / B, B, smem, st>>>(e->dc, e->dp);
+  int full = (2 * e->dc.N + B - 1) / B;
+  int grid = e->mapgen_grid > 0 && e->mapgen_grid < full ? e->mapgen_grid : full;
+  kern<<<grid, B, smem, st>>>(e->dc, e->dp, e->dp.parity);
   return ck(cudaGetLastError());
 }
 

@@ -814,7 +814,8 @@ PG_HD void env_reset_pregenerated(const DevCfg& c, const DevPtrs& p, MapView& m,
   e.episode++;
   e.elapsed = 0;
   Rng<RNG> rng(p, e, env);
-  const uint16_t* nt = p.next_tiles + (size_t)env * c.T;
+  const size_t slot = e.episode & 1u;  // ring slot of this episode's pre-generated map
+  const uint16_t* nt = p.next_tiles + (slot * c.N + (size_t)env) * c.T;
   if ((c.T & 7) == 0) {
     const uint4* g4 = (const uint4*)nt;
     uint32_t* s32 = (uint32_t*)m.tiles;
@@ -822,7 +823,7 @@ PG_HD void env_reset_pregenerated(const DevCfg& c, const DevPtrs& p, MapView& m,
   } else {
     for (int t = 0; t < c.T; t++) m.tiles[t] = nt[t];
   }
-  e.plan = p.next_plan[env];
+  e.plan = p.next_plan[slot * c.N + env];
   m.plan = e.plan;
   begin_episode<RNG>(c, p, m, e, rng, env);
 }

@@ -106,6 +106,9 @@ class RawEnv:
         _lib.check(self.lib, self.lib.pgtg_flatten(self._h, order.ctypes.data, stream, C.byref(ptr), C.byref(dim)))
         return ptr.value, dim.value
 
+    def set_overlap(self, on: bool):
+        _lib.check(self.lib, self.lib.pgtg_set_overlap(self._h, int(bool(on))))
+
     def enable_timing(self, max_steps: int):
         _lib.check(self.lib, self.lib.pgtg_enable_timing(self._h, int(max_steps)))
 

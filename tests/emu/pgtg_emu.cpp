@@ -19,6 +19,10 @@ static int bk_d2h(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); re
 static int bk_memset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
 static int bk_memset_async(void* d, int v, size_t n, void*) { memset(d, v, n); return 0; }
 static int bk_sync(void*) { return 0; }
+// the emulation runs everything in program order: streams and events are no-ops
+static int bk_side_create(void** s, void** a, void** b, void** c, int* sms) { *s = *a = *b = *c = nullptr; *sms = 1; return 0; }
+static void bk_side_destroy(void*, void*, void*, void*) {}
+static int bk_stream_wait(void*, void*) { return 0; }
 static const char* bk_error() { return "emu"; }
 static int bk_dl_device_type() { return 1; }  // kDLCPU
 static void* bk_event_create() { return malloc(1); }
@@ -72,10 +76,18 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
   } else {
     for (int t = 0; t < nvalid; t++) sh.regs[t] = load_regs(c, p, env0 + t);
   }
-  if (mode != MODE_OBSERVE && c.pregen && n_done) {  // queue for the map-generation pass
-    uint32_t base = *p.regen_count;
-    *p.regen_count += (uint32_t)n_done;
-    for (int k = 0; k < n_done; k++) p.regen_list[base + k] = env0 + sh.done_list[k];
+  if (mode != MODE_OBSERVE && c.pregen && n_done) {  // queue map requests (same rule as the kernel)
+    const int per = mode == MODE_RESET ? 2 : 1;
+    uint32_t base = p.regen_count[p.parity];
+    p.regen_count[p.parity] += (uint32_t)(n_done * per);
+    uint2* q = p.regen_list + (size_t)p.parity * 2 * c.N + base;
+    for (int k = 0; k < n_done; k++) {
+      int local = sh.done_list[k];
+      uint32_t ep = sh.regs[local].episode + 1u;
+      uint2 r; r.x = (uint32_t)(env0 + local);
+      if (mode == MODE_RESET) { r.y = ep + 1u; q[2 * k] = r; r.y = ep + 2u; q[2 * k + 1] = r; }
+      else { r.y = ep + 2u; q[k] = r; }
+    }
   }
   for (int k = 0; k < n_done; k++) {
     if (PREGEN && mode == MODE_STEP) phase_reset<RNG, TMAX, true>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
@@ -93,12 +105,13 @@ static void run_mapgen(pgtg_env* h) {
   const int B = 128;
   size_t bytes = mapgen_shared_bytes(c, B);
   unsigned char* smem = (unsigned char*)bk_alloc(bytes);
-  uint32_t count = *p.regen_count;
+  uint32_t count = p.regen_count[p.parity];
+  const uint2* list = p.regen_list + (size_t)p.parity * 2 * c.N;
   for (uint32_t i0 = 0; i0 < count; i0 += B) {
     memset(smem, 0xA5, bytes);
     BlockShared sh = carve_mapgen(smem, c, B);
     for (int t = 0; t < B; t++) stage_tables(c, p, sh, t, B);
-    for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<RNG, TMAX>(c, p, sh, t, p.regen_list[i0 + t]);
+    for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<RNG, TMAX>(c, p, sh, t, (int)list[i0 + t].x, list[i0 + t].y);
   }
   free(smem);
 }
