@@ -199,6 +199,7 @@ struct Lut {
   uint8_t native_spawner[16];
   uint8_t entry_sq[4];
   uint32_t spawner_cols;  // local columns that can hold a car_spawner (derived when staging)
+  uint32_t exit_any[3];   // union of the four exit lines (derived when staging)
 };
 struct LutInit { uint32_t wall[16][3], exit_line[4][3], mask[PGTG_NUM_MASKS][3], lane_any[16][3]; uint8_t native_spawner[16], entry_sq[4]; };
 PG_DEVCONST LutInit g_lut = {PGTG_TAB_WALL, PGTG_TAB_EXIT_LINE, PGTG_TAB_MASK, PGTG_TAB_LANE_ANY, PGTG_TAB_NATIVE_SPAWNER, PGTG_TAB_ENTRY_SQ};
@@ -458,12 +459,15 @@ struct MapView {
     unsigned f = 0;
     int ot = td_otype(td);
     if (ot && bit81(L.mask[td_omask(td)], sq)) f |= (SF_ICE >> 1) << ot;  // 1 ice .. 4 light
-    if (td_sg(td) || t == start_tile()) {
-      unsigned lab = line_labels(t, td);
-#pragma unroll
-      for (int d = 0; d < 4; d++) {
-        unsigned l = (lab >> (4 * d)) & 15;
-        if (l && bit81(L.exit_line[d], sq)) f |= (l == 1 ? SF_SUBGOAL : l == 2 ? SF_USED : l == 3 ? SF_START : SF_FINAL);
+    if (bit81(L.exit_any, sq) && (td_sg(td) || t == start_tile())) {
+      // the square lies on exactly one exit line d: label that line only, in the order of
+      // parser.py:55-77 (subgoal, then start, then final goal)
+      int d = bit81(L.exit_line[0], sq) ? 0 : bit81(L.exit_line[1], sq) ? 1 : bit81(L.exit_line[2], sq) ? 2 : 3;
+      if ((ex >> d) & 1) {
+        int sg = td_sg(td), gt = goal_tile();
+        if (sg && t != gt && d == sg - 1) f |= (td & TD_USED) ? SF_USED : SF_SUBGOAL;
+        else if (t == start_tile() && d == plan_sd(plan)) f |= SF_START;
+        else if (t == gt && d == plan_gd(plan)) f |= SF_FINAL;
       }
     }
     return f;
