@@ -235,6 +235,12 @@ __global__ void pgtg_reduce_stats_kernel(const double* __restrict__ rows, int nr
 
 // ---- CUDA backend: launch ----------------------------------------------------------------------
 static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem) {
+  const char* forced = getenv("PGTG_BLOCK");  // experiment knob: CTA size of the tick kernel (32 / 64 / 128)
+  int fb = forced ? atoi(forced) : 0;
+  if (fb == 32 || fb == 64 || fb == 128) {
+    size_t s = pgtg::block_shared_bytes(c, fb);
+    if (s <= 200 * 1024) { *block = fb; *smem = s; return 0; }
+  }
   for (int B : {128, 64, 32}) {
     size_t s = pgtg::block_shared_bytes(c, B);
     if (s <= 200 * 1024) { *block = B; *smem = s; return 0; }
