@@ -29,8 +29,7 @@ static int bk_side_create(void** stream, void** ev_tick, void** ev_map0, void** 
   int lo = 0, hi = 0, dev = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   cudaStream_t s; cudaEvent_t a, b, c;
-  const char* pr = getenv("PGTG_MAPGEN_PRIORITY");  // experiment knob: hi (default) | lo
-  if (ck(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, (pr && pr[0] == 'l') ? lo : hi))) return -1;
+  if (ck(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi))) return -1;  // priority made no measurable difference
   if (ck(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)) || ck(cudaEventCreateWithFlags(&b, cudaEventDisableTiming)) ||
       ck(cudaEventCreateWithFlags(&c, cudaEventDisableTiming))) return -1;
   cudaGetDevice(&dev);
@@ -63,6 +62,9 @@ namespace pgtg {
 constexpr int STATS_STRIDE = 8;
 #ifndef PGTG_MIN_BLOCKS
 #define PGTG_MIN_BLOCKS 8
+#endif
+#ifndef PGTG_MAPGEN_MIN_BLOCKS
+#define PGTG_MAPGEN_MIN_BLOCKS 12
 #endif
 
 // per-CTA episode statistics row (no cross-CTA atomics on the hot path)
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
 // request queue) so that it only occupies a slice of each SM's registers and the tick kernel of the
 // next launch co-resides with it: this kernel is ALU-bound, the tick is HBM-bound.
 template <int RNG, int TMAX>
-__global__ void __launch_bounds__(128) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity) {
+__global__ void __launch_bounds__(128, PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t count = p.regen_count[parity];
   if (blockIdx.x * blockDim.x >= count) return;
