@@ -606,7 +606,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     unsigned ab = m.edge_tab[i];
     int a = ab & 255, b = ab >> 8;
     int lo = a < b ? a : b;
-    bool horiz = (a > b ? a - b : b - a) == 1;
+    bool horiz = (a > b ? a - b : b - a) == 1 && W != 1;  // on a 1-wide map every edge is vertical (t <-> t + W = t + 1)
     if (horiz) bclr(E, lo); else bclr(S, lo);
 #ifdef PGTG_FLOOD_SG
     if (still_connected<TMAX>(c, E, S, st, gt, st, gt)) cur -= 2;
@@ -706,7 +706,7 @@ PG_HD void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
       int cur = gt;
       while (cur != st) {
         int pr = (int)((prev >> (4 * cur)) & 15u);
-        int d = cur == pr - W ? 0 : cur == pr + 1 ? 1 : cur == pr + W ? 2 : 3;  // find_direction (parser.py:279-306)
+        int d = cur == pr - W ? 0 : cur == pr + W ? 2 : cur == pr + 1 ? 1 : 3;  // vertical first: on a 1-wide map t + W == t + 1  // find_direction (parser.py:279-306)
         m.tiles[pr] |= (uint16_t)((1 + d) << 11);
         cur = pr; ns++;
       }
@@ -730,7 +730,7 @@ PG_HD void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
       int cur = gt;
       while (cur != st) {
         int pr = prev[cur];
-        int d = cur == pr - W ? 0 : cur == pr + 1 ? 1 : cur == pr + W ? 2 : 3;
+        int d = cur == pr - W ? 0 : cur == pr + W ? 2 : cur == pr + 1 ? 1 : 3;  // vertical first: on a 1-wide map t + W == t + 1
         m.tiles[pr] |= (uint16_t)((1 + d) << 11);
         cur = pr; ns++;
       }

@@ -81,6 +81,13 @@ TRACES = {
     "literal_features": (dict(features_to_include_in_observation=["walls", "goals", "traffic", "traffic_light", "start", "used subgoal",
                                                                   "car_spawner", "subgoal", "final goal", "wall", "ice", "bogus"],
                               random_map_obstacle_probability=0.9, random_map_traffic_light_probability_weight=6, traffic_density=0.1), dict(policy="seek")),
+    # 1-wide / 1-high maps: t + W == t + 1, found by tools/fuzz_reference.py
+    "narrow_1x4": (dict(random_map_width=1, random_map_height=4, random_map_percentage_of_connections=0.5,
+                        random_map_start_position=(0, 0, "north"), random_map_goal_position=(0, 3, "south"), use_next_subgoal_direction=True,
+                        random_map_obstacle_probability=0.5, traffic_density=0.2), dict(policy="seek", ticks=60)),
+    "narrow_5x1_random_ends": (dict(random_map_width=5, random_map_height=1, random_map_start_position="random", random_map_goal_position="random",
+                                    traffic_density=0.1, use_sliding_observation_window=True, sliding_observation_window_size=2),
+                               dict(policy="seek", ticks=60)),
     "driver_mix": (dict(traffic_density=0.25, conservative_driver_percentage=0.0, normal_driver_percentage=0.1, aggressive_driver_percentage=0.5,
                         elderly_driver_percentage=0.1, reckless_driver_percentage=0.3, random_map_percentage_of_connections=0.7,
                         random_map_obstacle_probability=0.6, random_map_traffic_light_probability_weight=3, ignore_traffic_collisions=True),
