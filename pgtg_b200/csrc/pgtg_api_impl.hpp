@@ -11,6 +11,7 @@
 //   int bk_launch(pgtg_env*, int mode, const uint8_t* mask_dev, const int64_t* seeds_dev,
 //                 const void* actions_dev, int action_bytes, void* stream);
 //   const char* bk_error();  int bk_dl_device_type();
+//   int bk_conn_table_max_bits();  int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
 //   int bk_side_create(void** stream, void** ev_tick, void** ev_map0, void** ev_map1, int* sm_count);
 //   void bk_side_destroy(void*, void*, void*, void*);  int bk_stream_wait(void* stream, void* ev);
 //   void* bk_event_create();  void bk_event_destroy(void*);  int bk_event_record(void* ev, void* stream);
@@ -202,6 +203,13 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   if (!c.fixed_map) {
     d.n_edge_tab = 2 * (d.W * (d.H - 1) + d.H * (d.W - 1));
     d.n_border_slots = 2 * d.W + 2 * d.H - 2;
+    // connectivity table: fixed start/goal, single-register boards, <= 24 undirected grid edges
+    // (2^24 bits = 2 MB); the emulation build caps it lower to keep CPU tests fast
+    int n_he = d.H * (d.W - 1), n_ve = d.W * (d.H - 1);
+    if (c.start_mode == 0 && c.goal_mode == 0 && d.T <= 32 && n_he + n_ve >= 1 && n_he + n_ve <= bk_conn_table_max_bits() &&
+        !(c.start_x == c.goal_x && c.start_y == c.goal_y)) {
+      d.conn_bits = n_he + n_ve; d.conn_ne = n_he;
+    }
     int n_slots = 2 * d.W + 2 * d.H - 2;
     if (c.border_connections < 0 || c.border_connections > n_slots) { why = "random_map_percentage_of_connections must be in [0, 1]"; return -1; }
     if (c.edges_to_keep < 0) { why = "random_map_percentage_of_connections must be in [0, 1]"; return -1; }
@@ -296,9 +304,15 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
       return fail(PGTG_ERR_CUDA, std::string("cannot create the map-generation stream: ") + bk_error());
     }
     const char* env_ctas = getenv("PGTG_MAPGEN_CTAS_PER_SM");
-    int per_sm = env_ctas ? atoi(env_ctas) : 4;
+    int per_sm = env_ctas ? atoi(env_ctas) : 0;  // 0 = full grid (best with the connectivity table)
     e->mapgen_grid = per_sm > 0 ? sms * per_sm : 0;
     e->mapgen_grid_overlap = e->mapgen_grid; e->overlap = true;
+  }
+  if (e->dc.conn_bits) {
+    size_t words = ((size_t)1 << e->dc.conn_bits) / 32 + 1;
+    uint32_t* t = dev_alloc<uint32_t>(e, words, false);
+    if (!t || bk_build_conn_table(e, t)) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, std::string("connectivity table: ") + bk_error()); }
+    p.conn_table = t;
   }
   bk_sync(nullptr);
   *out = e;

@@ -33,6 +33,7 @@
 #define pg_dadd(a, b) __dadd_rn((a), (b))
 #define pg_ddiv(a, b) __ddiv_rn((a), (b))
 #define pg_atomic_or(p, v) atomicOr((p), (v))
+#define pg_store_streaming(ptr, v) __stcs((ptr), (v))  /* written once, never re-read by the kernel: evict-first */
 #else
 #include <math.h>
 #include <string.h>
@@ -51,6 +52,7 @@ static inline uint32_t pg_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((u
 #define pg_dadd(a, b) ((a) + (b))
 #define pg_ddiv(a, b) ((a) / (b))
 #define pg_atomic_or(p, v) (*(p) |= (v))
+#define pg_store_streaming(ptr, v) (*(ptr) = (v))
 struct short4 { short x, y, z, w; };
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
@@ -131,6 +133,9 @@ struct DevCfg {
   int occ_words, spawner_cap;  // traffic helpers (0 without traffic)
   int obs_bits;      // C * P * P
   uint32_t full_e[8], full_s[8];  // full grid graph: bit t = edge t<->t+1 / t<->t+W exists
+  // start-goal connectivity table (procedural maps with fixed start/goal and <= 24 grid edges):
+  // bit [compress(E) | S << conn_ne] = start and goal connected in the subgraph (E, S)
+  int conn_bits, conn_ne;
   int64_t env_id_base;
   uint64_t seed;
 };
@@ -180,6 +185,7 @@ struct DevPtrs {
   const uint16_t* edge_rev;     // [n_edge_tab] index of the reverse edge
   const uint16_t* border_slots; // [n_border_slots] tile | dir << 8
   const uint8_t* dirlut;        // (2R+1)^2
+  const uint32_t* conn_table;   // [2^conn_bits / 32] or null
   const pgtg_rule* rules;
   // outputs
   int8_t* obs_map; int32_t* obs_position; int32_t* obs_velocity; int32_t* obs_nsd;

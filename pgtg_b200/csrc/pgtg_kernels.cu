@@ -54,6 +54,8 @@ static int bk_launch(pgtg_env*, int mode, const uint8_t* mask, const int64_t* se
 static int bk_stats_reduce(pgtg_env*, void* stream);
 static int bk_stats_reset(pgtg_env*, void* stream);
 static int bk_flatten(pgtg_env*, void* stream);
+static int bk_conn_table_max_bits() { return 24; }
+static int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
 
 #include "pgtg_api_impl.hpp"
 
@@ -199,6 +201,21 @@ __global__ void __launch_bounds__(128, PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kerne
   }
 }
 
+// one thread per 32-bit word of the start-goal connectivity table (32 subgraphs each)
+__global__ void pgtg_build_conn_table_kernel(const __grid_constant__ DevCfg c, uint32_t* __restrict__ table, int s, int g) {
+  const uint32_t words = (1u << c.conn_bits) / 32u + ((1u << c.conn_bits) < 32u ? 1u : 0u);
+  const uint32_t rowmask = (1u << (c.W - 1)) - 1u, emask = (1u << c.conn_ne) - 1u;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+    uint32_t bits = 0;
+    for (uint32_t b = 0; b < 32; b++) {
+      uint32_t idx = w * 32u + b, ec = idx & emask, so = idx >> c.conn_ne, e = 0;
+      for (int r = 0; r < c.H; r++) e |= ((ec >> (r * (c.W - 1))) & rowmask) << (r * c.W);
+      if (flood_connected32(c.W, e, so, s, g)) bits |= 1u << b;
+    }
+    table[w] = bits;
+  }
+}
+
 struct FlatOrder { int plane[PGTG_MAX_CHANNELS]; };
 
 // FlattenObservation view: one thread per output float, coalesced float32 stores; reads the int8
@@ -327,6 +344,11 @@ extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
 static int bk_stats_reduce(pgtg_env* e, void* stream) {
   pgtg::pgtg_reduce_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->stats_rows, e->nblk, e->dp.stats);
   e->launches++;
+  return ck(cudaGetLastError());
+}
+static int bk_build_conn_table(pgtg_env* e, uint32_t* table_dev) {
+  int s = e->dc.start_y * e->dc.W + e->dc.start_x, g = e->dc.goal_y * e->dc.W + e->dc.goal_x;
+  pgtg::pgtg_build_conn_table_kernel<<<148 * 8, 256>>>(e->dc, table_dev, s, g);
   return ck(cudaGetLastError());
 }
 static int bk_flatten(pgtg_env* e, void* stream) {

@@ -484,8 +484,34 @@ PG_HD int select32(uint32_t v, int n) {
 // i<->i+W (the edge is already cleared). Flood from a: reaching b means nothing changed (early
 // exit, typically after going round one grid face); otherwise the flood ends on a's whole
 // component and the graph stays start-goal connected iff s and g are on the same side.
+// start-goal connectivity of a <= 32-tile subgraph by flood fill (builds the connectivity table)
+PG_HD bool flood_connected32(int W, uint32_t e, uint32_t so, int s, int g) {
+  if (s == g) return true;
+  uint32_t reach = 1u << s, goal = 1u << g;
+  for (;;) {
+    uint32_t nx = reach | ((reach & e) << 1) | ((reach >> 1) & e) | ((reach & so) << W) | ((reach >> W) & so);
+    if (nx & goal) return true;
+    if (nx == reach) return false;
+    reach = nx;
+  }
+}
+
+// index of the subgraph (E, S) in the connectivity table: the E board has a hole after every row
+// (no edge from the last column), the S board is contiguous
+PG_HD uint32_t conn_index(const DevCfg& c, uint32_t e, uint32_t so) {
+  uint32_t idx = 0, rowmask = (1u << (c.W - 1)) - 1u;
+  for (int r = 0; r < c.H; r++) idx |= ((e >> (r * c.W)) & rowmask) << (r * (c.W - 1));
+  return idx | so << c.conn_ne;
+}
+
 template <int TMAX>
-PG_HD bool still_connected(const DevCfg& c, const Board<TMAX>& E, const Board<TMAX>& S, int a, int b, int s, int g) {
+PG_HD bool still_connected(const DevCfg& c, const DevPtrs& p, const Board<TMAX>& E, const Board<TMAX>& S, int a, int b, int s, int g) {
+  if (TMAX <= 32 && c.conn_bits) {
+    // "start and goal connected?" is a pure function of the edge set: one lookup in a table built once
+    // per handle (2 MB for the 4x4 grid, L2-resident) instead of a divergent flood fill
+    uint32_t idx = conn_index(c, E.w[0], S.w[0]);
+    return (pg_ldg(&p.conn_table[idx >> 5]) >> (idx & 31)) & 1u;
+  }
   if (TMAX <= 32) {  // whole board in one register: flood fill by shifts
     uint32_t e = E.w[0], so = S.w[0], reach = 1u << a, tb = 1u << b;
     for (;;) {
@@ -608,11 +634,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     int lo = a < b ? a : b;
     bool horiz = (a > b ? a - b : b - a) == 1 && W != 1;  // on a 1-wide map every edge is vertical (t <-> t + W = t + 1)
     if (horiz) bclr(E, lo); else bclr(S, lo);
-#ifdef PGTG_FLOOD_SG
-    if (still_connected<TMAX>(c, E, S, st, gt, st, gt)) cur -= 2;
-#else
-    if (still_connected<TMAX>(c, E, S, a, b, st, gt)) cur -= 2;
-#endif
+    if (still_connected<TMAX>(c, p, E, S, a, b, st, gt)) cur -= 2;
     else { if (horiz) bset(E, lo); else bset(S, lo); }
   }
   // map_graph_to_tile_map_object (:269-334); an E bit is only ever set left of the last column

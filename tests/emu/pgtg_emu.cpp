@@ -34,6 +34,8 @@ static int bk_launch(pgtg_env*, int, const uint8_t*, const int64_t*, const void*
 static int bk_stats_reduce(pgtg_env*, void*);
 static int bk_stats_reset(pgtg_env*, void*);
 static int bk_flatten(pgtg_env*, void*);
+static int bk_conn_table_max_bits() { return 13; }  // CPU tests: tables up to 8192 entries (e.g. 3x3 maps)
+static int bk_build_conn_table(pgtg_env*, uint32_t*);
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
@@ -165,6 +167,20 @@ static int bk_flatten(pgtg_env* e, void*) {
     else if (j < map_dim + nsd_dim + 18) { int q = j - map_dim - nsd_dim; v = (p.obs_position[2 * env + (q >= 9)] == (q >= 9 ? q - 9 : q)) ? 1.0f : 0.0f; }
     else v = (float)p.obs_velocity[2 * env + (j - map_dim - nsd_dim - 18)];
     e->flat[i] = v;
+  }
+  return 0;
+}
+
+// host loop of the connectivity-table builder (same index arithmetic as the kernel)
+static int bk_build_conn_table(pgtg_env* e, uint32_t* table) {
+  const DevCfg& c = e->dc;
+  int s = c.start_y * c.W + c.start_x, g = c.goal_y * c.W + c.goal_x;
+  uint32_t total = 1u << c.conn_bits, rowmask = (1u << (c.W - 1)) - 1u, emask = (1u << c.conn_ne) - 1u;
+  for (uint32_t w = 0; w < total / 32 + 1; w++) table[w] = 0;
+  for (uint32_t idx = 0; idx < total; idx++) {
+    uint32_t ec = idx & emask, so = idx >> c.conn_ne, ed = 0;
+    for (int r = 0; r < c.H; r++) ed |= ((ec >> (r * (c.W - 1))) & rowmask) << (r * c.W);
+    if (flood_connected32(c.W, ed, so, s, g)) table[idx >> 5] |= 1u << (idx & 31);
   }
   return 0;
 }
