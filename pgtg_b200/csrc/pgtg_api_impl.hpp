@@ -278,6 +278,14 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
       pgtg_destroy(e);
       return fail(PGTG_ERR_INVALID, "internal: map table sizes");
     }
+    for (size_t i = 0; i < e->edge_tab.size(); i++) {
+      // bit of this (undirected) edge in the connectivity-table index: horizontal edges compressed row by
+      // row (W - 1 per row), then the vertical edges by tile index
+      int a = e->edge_tab[i] & 255, b = e->edge_tab[i] >> 8, lo = a < b ? a : b;
+      bool horiz = (a > b ? a - b : b - a) == 1 && dc.W != 1;
+      int pos = horiz ? (lo / dc.W) * (dc.W - 1) + lo % dc.W : dc.H * (dc.W - 1) + lo;
+      e->edge_rev[i] = (uint16_t)(e->edge_rev[i] | (pos & 63) << 10);
+    }
     uint16_t* t1 = dev_alloc<uint16_t>(e, e->edge_tab.size() + 1);
     uint16_t* t2 = dev_alloc<uint16_t>(e, e->edge_rev.size() + 1);
     uint16_t* t3 = dev_alloc<uint16_t>(e, e->border_slots.size() + 1);

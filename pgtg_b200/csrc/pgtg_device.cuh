@@ -182,7 +182,7 @@ struct DevPtrs {
   const uint16_t* fixed_tiles;  // [T] (fixed map)
   uint32_t fixed_plan;
   const uint16_t* edge_tab;     // [n_edge_tab] a | b << 8  (edges() order)
-  const uint16_t* edge_rev;     // [n_edge_tab] index of the reverse edge
+  const uint16_t* edge_rev;     // [n_edge_tab] index of the reverse edge | connectivity-table bit of the edge << 10
   const uint16_t* border_slots; // [n_border_slots] tile | dir << 8
   const uint8_t* dirlut;        // (2R+1)^2
   const uint32_t* conn_table;   // [2^conn_bits / 32] or null

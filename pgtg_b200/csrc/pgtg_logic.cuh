@@ -506,12 +506,6 @@ PG_HD uint32_t conn_index(const DevCfg& c, uint32_t e, uint32_t so) {
 
 template <int TMAX>
 PG_HD bool still_connected(const DevCfg& c, const DevPtrs& p, const Board<TMAX>& E, const Board<TMAX>& S, int a, int b, int s, int g) {
-  if (TMAX <= 32 && c.conn_bits) {
-    // "start and goal connected?" is a pure function of the edge set: one lookup in a table built once
-    // per handle (2 MB for the 4x4 grid, L2-resident) instead of a divergent flood fill
-    uint32_t idx = conn_index(c, E.w[0], S.w[0]);
-    return (pg_ldg(&p.conn_table[idx >> 5]) >> (idx & 31)) & 1u;
-  }
   if (TMAX <= 32) {  // whole board in one register: flood fill by shifts
     uint32_t e = E.w[0], so = S.w[0], reach = 1u << a, tb = 1u << b;
     for (;;) {
@@ -608,6 +602,9 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
   int n_tab = c.n_edge_tab, n_alive = n_tab, cur = n_tab;
 #pragma unroll
   for (int i = 0; i < AW; i++) alive[i] = (i * 32 + 32 <= n_tab) ? 0xFFFFFFFFu : (i * 32 < n_tab ? ((1u << (n_tab & 31)) - 1u) : 0u);
+  // with the connectivity table the graph is kept as the table index itself (one bit per grid edge)
+  const bool tabled = TMAX <= 32 && c.conn_bits != 0;
+  uint32_t graph = tabled ? ((c.conn_bits >= 32 ? 0u : (1u << c.conn_bits)) - 1u) : 0u;
   while (cur > c.edges_to_keep && n_alive > 0) {  // :245
     int idx = rng.index(PGTG_STREAM_MAP, n_alive);  // :249
     int i;
@@ -620,7 +617,8 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
       for (;; wi++) { int pc = pg_popc(alive[wi]); if (idx < pc) break; idx -= pc; }
       i = wi * 32 + select32(alive[wi], idx);
     }
-    int j = m.edge_rev[i];
+    unsigned rv = m.edge_rev[i];
+    int j = rv & 1023;
     if (AW == 2) {
       uint64_t clr = ~((1ull << i) | (1ull << j));
       alive[0] &= (uint32_t)clr; alive[1] &= (uint32_t)(clr >> 32);
@@ -629,6 +627,15 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
       alive[j >> 5] &= ~(1u << (j & 31));
     }
     n_alive -= 2;
+    if (tabled) {
+      // "start and goal still connected?" is a pure function of the edge set: one lookup in the 2^E-bit
+      // table built once per handle (2 MB for the 4x4 grid, L2-resident) instead of a divergent flood
+      uint32_t bit = 1u << (rv >> 10), g2 = graph & ~bit;
+      bool keep = (pg_ldg(&p.conn_table[g2 >> 5]) >> (g2 & 31)) & 1u;
+      graph = keep ? g2 : graph;
+      cur -= keep ? 2 : 0;
+      continue;
+    }
     unsigned ab = m.edge_tab[i];
     int a = ab & 255, b = ab >> 8;
     int lo = a < b ? a : b;
@@ -636,6 +643,11 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     if (horiz) bclr(E, lo); else bclr(S, lo);
     if (still_connected<TMAX>(c, p, E, S, a, b, st, gt)) cur -= 2;
     else { if (horiz) bset(E, lo); else bset(S, lo); }
+  }
+  if (tabled) {  // back to the boards: E has a hole after every row, S is contiguous
+    uint32_t e = 0, rowmask = (1u << (W - 1)) - 1u;
+    for (int r = 0; r < c.H; r++) e |= ((graph >> (r * (W - 1))) & rowmask) << (r * W);
+    E.w[0] = e; S.w[0] = graph >> c.conn_ne;
   }
   // map_graph_to_tile_map_object (:269-334); an E bit is only ever set left of the last column
   for (int t = 0; t < T; t++) {
