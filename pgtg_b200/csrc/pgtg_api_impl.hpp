@@ -12,6 +12,7 @@
 //                 const void* actions_dev, int action_bytes, void* stream);
 //   const char* bk_error();  int bk_dl_device_type();
 //   int bk_conn_table_max_bits();  int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
+//   int bk_build_path_table(pgtg_env*, uint64_t* table_dev);
 //   int bk_side_create(void** stream, void** ev_tick, void** ev_map0, void** ev_map1, int* sm_count);
 //   void bk_side_destroy(void*, void*, void*, void*);  int bk_stream_wait(void* stream, void* ev);
 //   void* bk_event_create();  void bk_event_destroy(void*);  int bk_event_record(void* ev, void* stream);
@@ -209,6 +210,7 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
     if (c.start_mode == 0 && c.goal_mode == 0 && d.T <= 32 && n_he + n_ve >= 1 && n_he + n_ve <= bk_conn_table_max_bits() &&
         !(c.start_x == c.goal_x && c.start_y == c.goal_y)) {
       d.conn_bits = n_he + n_ve; d.conn_ne = n_he;
+      d.path_tab = d.T <= 16 ? 1 : 0;  // 8 bytes per edge set: 128 MB for the 4x4 grid
     }
     int n_slots = 2 * d.W + 2 * d.H - 2;
     if (c.border_connections < 0 || c.border_connections > n_slots) { why = "random_map_percentage_of_connections must be in [0, 1]"; return -1; }
@@ -321,6 +323,11 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     uint32_t* t = dev_alloc<uint32_t>(e, words, false);
     if (!t || bk_build_conn_table(e, t)) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, std::string("connectivity table: ") + bk_error()); }
     p.conn_table = t;
+  }
+  if (e->dc.path_tab) {
+    uint64_t* t = dev_alloc<uint64_t>(e, (size_t)1 << e->dc.conn_bits, false);
+    if (!t || bk_build_path_table(e, t)) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, std::string("path table: ") + bk_error()); }
+    p.path_table = t;
   }
   bk_sync(nullptr);
   *out = e;

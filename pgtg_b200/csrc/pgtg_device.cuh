@@ -136,6 +136,7 @@ struct DevCfg {
   // start-goal connectivity table (procedural maps with fixed start/goal and <= 24 grid edges):
   // bit [compress(E) | S << conn_ne] = start and goal connected in the subgraph (E, S)
   int conn_bits, conn_ne;
+  int path_tab;                 // 1: subgoal paths come from DevPtrs.path_table (T <= 16, same index as conn_table)
   int64_t env_id_base;
   uint64_t seed;
 };
@@ -186,6 +187,7 @@ struct DevPtrs {
   const uint16_t* border_slots; // [n_border_slots] tile | dir << 8
   const uint8_t* dirlut;        // (2R+1)^2
   const uint32_t* conn_table;   // [2^conn_bits / 32] or null
+  const uint64_t* path_table;   // [2^conn_bits] or null: 3-bit subgoal direction of every tile | ns << 48 | unreachable << 63
   const pgtg_rule* rules;
   // outputs
   int8_t* obs_map; int32_t* obs_position; int32_t* obs_velocity; int32_t* obs_nsd;
@@ -442,6 +444,8 @@ struct MapView {
   const uint16_t* edge_tab;      // shared-memory copies of the map-generation tables
   const uint16_t* edge_rev;
   const uint16_t* border_slots;
+  uint32_t graph;      // connectivity-table index of the generated map's edge set (valid when graph_valid)
+  bool graph_valid;
   PG_MEMBER bool inside(int x, int y) const { return !(x < 0 || y < 0 || x >= c.WS || y >= c.HS); }  // map.py:44-47
   PG_MEMBER int start_tile() const { return plan_sy(plan) * c.W + plan_sx(plan); }
   PG_MEMBER int goal_tile() const { return plan_gy(plan) * c.W + plan_gx(plan); }

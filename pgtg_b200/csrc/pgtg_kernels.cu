@@ -56,6 +56,7 @@ static int bk_stats_reset(pgtg_env*, void* stream);
 static int bk_flatten(pgtg_env*, void* stream);
 static int bk_conn_table_max_bits() { return 24; }
 static int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
+static int bk_build_path_table(pgtg_env*, uint64_t* table_dev);
 
 #include "pgtg_api_impl.hpp"
 
@@ -112,9 +113,37 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
       for (int o = 16; o > 0; o >>= 1) rs += __shfl_down_sync(0xffffffffu, rs, o);
       if (lane == 0) {
         atomicAdd(&sh.counters[8], __popc(g)); atomicAdd(&sh.counters[9], __popc(cr)); atomicAdd(&sh.counters[10], __popc(tr));
-        atomicAdd(&sh.counters[11], lsum);
+        atomicAdd(&sh.counters[11], lsum); atomicAdd(&sh.counters[12], __popc(any));
         atomicAdd(&sh.dsum[0], rs);
       }
+    }
+    if (PREGEN && !c.write_final_obs) {
+      // Hot configuration (next maps come from the ring, no terminal-observation output): the
+      // reset is a cheap swap, so every finished env is reset by its own thread and the CTA
+      // needs one barrier only, the one in front of the byte expansion. Map requests are queued
+      // per warp; the atomic's round trip hides behind the observation emit.
+      uint32_t k = 0, qbase = 0;
+      if (any && lane == 0) qbase = atomicAdd(p.regen_count + p.parity, (uint32_t)__popc(any));
+      if (done) {
+        k = sh.regs[tid].episode + 1u;  // the episode this env is about to start
+        phase_reset<RNG, TMAX, true>(c, p, sh, tid, env);
+      }
+      if (valid) phase_emit(c, p, sh, tid, env, false);
+      if (any) {
+        qbase = __shfl_sync(0xffffffffu, qbase, 0);
+        if (done) {
+          uint2 q; q.x = (uint32_t)env; q.y = k + 2u;
+          p.regen_list[(size_t)p.parity * 2 * c.N + qbase + __popc(any & ((1u << lane) - 1u))] = q;
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && sh.counters[12]) {
+        double* row = sa.rows + (size_t)blockIdx.x * STATS_STRIDE;
+        row[0] += sh.counters[12]; row[1] += sh.dsum[0]; row[2] += sh.counters[11];
+        row[3] += sh.counters[8]; row[4] += sh.counters[9]; row[5] += sh.counters[10];
+      }
+      phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid);
+      return;
     }
   } else if (MODE == MODE_RESET) {
     if (valid) {
@@ -218,6 +247,17 @@ __global__ void pgtg_build_conn_table_kernel(const __grid_constant__ DevCfg c, u
 
 struct FlatOrder { int plane[PGTG_MAX_CHANNELS]; };
 
+// one thread per entry of the subgoal-path table
+__global__ void __launch_bounds__(128) pgtg_build_path_table_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, uint64_t* __restrict__ table) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BlockShared sh = carve_mapgen(smem, c, blockDim.x);
+  stage_tables(c, p, sh, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const uint32_t total = 1u << c.conn_bits;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x)
+    table[g] = path_table_entry(c, *sh.lut, g, sh.tiles + threadIdx.x * c.tile_stride);
+}
+
 // FlattenObservation view: one thread per output float, coalesced float32 stores; reads the int8
 // planes through L2 (they were just written by the tick).
 __global__ void pgtg_flatten_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, FlatOrder order,
@@ -274,11 +314,12 @@ static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, co
   // different carveouts, which would serialise the two (measured: no overlap at all without this)
   static bool carve_set = false;
   if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve_set = true; }
-  if (e->smem > 48 * 1024) {
-    if (ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem))) return -1;
+  const size_t smem = e->smem;
+  if (smem > 48 * 1024) {
+    if (ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return -1;
   }
   pgtg::StatsArgs sa = {e->stats_rows};
-  kern<<<e->nblk, e->block, e->smem, st>>>(e->dc, e->dp, mask, seeds, actions, action_bytes, sa);
+  kern<<<e->nblk, e->block, smem, st>>>(e->dc, e->dp, mask, seeds, actions, action_bytes, sa);
   return ck(cudaGetLastError());
 }
 
@@ -349,6 +390,14 @@ static int bk_stats_reduce(pgtg_env* e, void* stream) {
 static int bk_build_conn_table(pgtg_env* e, uint32_t* table_dev) {
   int s = e->dc.start_y * e->dc.W + e->dc.start_x, g = e->dc.goal_y * e->dc.W + e->dc.goal_x;
   pgtg::pgtg_build_conn_table_kernel<<<148 * 8, 256>>>(e->dc, table_dev, s, g);
+  return ck(cudaGetLastError());
+}
+static int bk_build_path_table(pgtg_env* e, uint64_t* table_dev) {
+  const int B = 128;
+  size_t smem = pgtg::mapgen_shared_bytes(e->dc, B);
+  uint32_t total = 1u << e->dc.conn_bits;
+  int blocks = (int)((total + B - 1) / B < 148u * 12u ? (total + B - 1) / B : 148u * 12u);
+  pgtg::pgtg_build_path_table_kernel<<<blocks, B, smem>>>(e->dc, e->dp, table_dev);
   return ck(cudaGetLastError());
 }
 static int bk_flatten(pgtg_env* e, void* stream) {

@@ -16,21 +16,30 @@ PG_HD int light_phase(const DevCfg& c, int counter) {  // environment.py:1004-10
 // ---------------------------------------------------------------------------------------------
 // car spawners: squares carrying "car_spawner", enumerated in the x-major order of
 // EpisodeMap.__init__ (map.py:31-42) without materialising the list.
+// sets bit sq of an 81-bit bitmap held in three registers (no dynamic indexing: that would push the
+// array into local memory)
+PG_HD void or_bit81(uint32_t w[3], int sq) {
+  uint32_t b = 1u << (sq & 31);
+  int i = sq >> 5;
+  w[0] |= i == 0 ? b : 0u; w[1] |= i == 1 ? b : 0u; w[2] |= i == 2 ? b : 0u;
+}
+
 PG_HD void spawner_bits(const DevCfg& c, const Lut& L, int ex, int tx, int ty, uint32_t out[3]) {
   out[0] = out[1] = out[2] = 0;
   if (ex == 0) return;  // no lanes on wall-only tiles (parser.py:113-118)
   int ns = L.native_spawner[ex];
-  if (ns != 255) out[ns >> 5] |= 1u << (ns & 31);
+  if (ns != 255) or_bit81(out, ns);
   // border tiles: tile-entry squares 'car_lane all <inward>' (parser.py:120-148)
-  if (tx == 0) { int sq = L.entry_sq[3]; if (ld_all(lane_desc(ex, sq)) == 4) out[sq >> 5] |= 1u << (sq & 31); }
-  if (tx == c.W - 1) { int sq = L.entry_sq[2]; if (ld_all(lane_desc(ex, sq)) == 3) out[sq >> 5] |= 1u << (sq & 31); }
-  if (ty == 0) { int sq = L.entry_sq[1]; if (ld_all(lane_desc(ex, sq)) == 2) out[sq >> 5] |= 1u << (sq & 31); }
-  if (ty == c.H - 1) { int sq = L.entry_sq[0]; if (ld_all(lane_desc(ex, sq)) == 1) out[sq >> 5] |= 1u << (sq & 31); }
+  if (tx == 0) { int sq = L.entry_sq[3]; if (ld_all(lane_desc(ex, sq)) == 4) or_bit81(out, sq); }
+  if (tx == c.W - 1) { int sq = L.entry_sq[2]; if (ld_all(lane_desc(ex, sq)) == 3) or_bit81(out, sq); }
+  if (ty == 0) { int sq = L.entry_sq[1]; if (ld_all(lane_desc(ex, sq)) == 2) or_bit81(out, sq); }
+  if (ty == c.H - 1) { int sq = L.entry_sq[0]; if (ld_all(lane_desc(ex, sq)) == 1) or_bit81(out, sq); }
 }
 PG_HD uint32_t col9(const uint32_t w[3], int lx) {  // the 9 bits of local column lx
-  int b = lx * TILE, wi = b >> 5, sh = b & 31;
-  uint32_t v = w[wi] >> sh;
-  if (sh > 23 && wi < 2) v |= w[wi + 1] << (32 - sh);
+  int b = lx * TILE, wi = b >> 5, sh = b & 31;  // selects, not w[wi]: keeps the bitmap in registers
+  uint32_t lo = wi == 0 ? w[0] : wi == 1 ? w[1] : w[2], hi = wi == 0 ? w[1] : wi == 1 ? w[2] : 0u;
+  uint32_t v = lo >> sh;
+  if (sh > 23) v |= hi << (32 - sh);
   return v & 0x1FFu;
 }
 // Build the env's car_spawner list (x-major order of EpisodeMap.__init__, map.py:31-42) once per
@@ -583,6 +592,13 @@ PG_HD void choose_start_goal(const DevCfg& c, Rng<RNG>& rng, int& sx, int& sy, i
   }
 }
 
+// connectivity-table index -> E / S boards (E has a hole after every row, S is contiguous)
+PG_HD void graph_to_boards(const DevCfg& c, uint32_t graph, uint32_t& E, uint32_t& S) {
+  uint32_t e = 0, rowmask = (1u << (c.W - 1)) - 1u;
+  for (int r = 0; r < c.H; r++) e |= ((graph >> (r * (c.W - 1))) & rowmask) << (r * c.W);
+  E = e; S = graph >> c.conn_ne;
+}
+
 template <int RNG, int TMAX>
 PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng) {
   int sx = c.start_x, sy = c.start_y, sd = c.start_dir, gx = c.goal_x, gy = c.goal_y, gd = c.goal_dir;
@@ -645,9 +661,8 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     else { if (horiz) bset(E, lo); else bset(S, lo); }
   }
   if (tabled) {  // back to the boards: E has a hole after every row, S is contiguous
-    uint32_t e = 0, rowmask = (1u << (W - 1)) - 1u;
-    for (int r = 0; r < c.H; r++) e |= ((graph >> (r * (W - 1))) & rowmask) << (r * W);
-    E.w[0] = e; S.w[0] = graph >> c.conn_ne;
+    graph_to_boards(c, graph, E.w[0], S.w[0]);
+    m.graph = graph; m.graph_valid = true;
   }
   // map_graph_to_tile_map_object (:269-334); an E bit is only ever set left of the last column
   for (int t = 0; t < T; t++) {
@@ -705,7 +720,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
 // (cost, push counter) keys == FIFO BFS, successors in N, E, S, W insertion order
 // (parse_tile_map_to_graph, parser.py:244-276), first-discovered predecessor.
 template <int TMAX>
-PG_HD void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
+PG_HD void assign_subgoals_bfs(const DevCfg& c, MapView& m, EnvRegs& e) {
   int W = c.W, T = c.T;
   int st = plan_sy(e.plan) * W + plan_sx(e.plan), gt = plan_gy(e.plan) * W + plan_gx(e.plan);
   for (int t = 0; t < T; t++) m.tiles[t] &= 0x07FF;  // clear subgoal dir + used
@@ -774,6 +789,45 @@ PG_HD void assign_subgoals(const DevCfg& c, MapView& m, EnvRegs& e) {
   e.plan = (e.plan & 0xFFFFFu) | (unsigned)ns << 20;
 }
 
+// The path is a pure function of the inner edge set when start and goal are fixed: with the
+// connectivity table on and T <= 16 it is read from a table built once per handle by running
+// assign_subgoals_bfs on every edge set (path_table_entry), 8 bytes per map instead of a BFS.
+template <int TMAX>
+PG_HD void assign_subgoals(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e) {
+  if (TMAX <= 16 && c.path_tab && m.graph_valid) {
+    uint64_t v = pg_ldg(&p.path_table[m.graph]);
+    for (int t = 0; t < c.T; t++) m.tiles[t] = (uint16_t)((m.tiles[t] & 0x07FF) | (unsigned)((v >> (3 * t)) & 7u) << 11);
+    if (v >> 63) e.err |= 8;
+    e.plan = (e.plan & 0xFFFFFu) | (unsigned)((v >> 48) & 0x1FFu) << 20;
+    return;
+  }
+  assign_subgoals_bfs<TMAX>(c, m, e);
+}
+
+// one entry of the path table: edge set `graph` -> packed subgoal directions (scratch: T descriptors)
+PG_HD uint64_t path_table_entry(const DevCfg& c, const Lut& L, uint32_t graph, uint16_t* scratch) {
+  uint32_t E, S;
+  graph_to_boards(c, graph, E, S);
+  for (int t = 0; t < c.T; t++) {
+    int ex = 0;
+    if (t >= c.W && ((S >> (t - c.W)) & 1u)) ex |= 1;
+    if ((E >> t) & 1u) ex |= 2;
+    if ((S >> t) & 1u) ex |= 4;
+    if (t > 0 && ((E >> (t - 1)) & 1u)) ex |= 8;
+    scratch[t] = (uint16_t)ex;
+  }
+  EnvRegs e;
+  e.x = e.y = e.vx = e.vy = 0; e.misc = 0; e.next_car_id = 0; e.err = 0; e.cursor = 0; e.flags = 0; e.elapsed = 0; e.episode = 0;
+  e.plan = plan_pack(c.start_x, c.start_y, c.start_dir, c.goal_x, c.goal_y, c.goal_dir, 0);
+  MapView m = {c, L, scratch, e.plan, nullptr, nullptr, nullptr, 0u, false};
+  assign_subgoals_bfs<16>(c, m, e);
+  uint64_t v = 0;
+  for (int t = 0; t < c.T; t++) v |= (uint64_t)td_sg(scratch[t]) << (3 * t);
+  v |= (uint64_t)((e.plan >> 20) & 0x1FFu) << 48;
+  if (e.err & 8) v |= 1ull << 63;
+  return v;
+}
+
 // plan word bits 29-30: index of the start square among map.starters (map_rng.choice, :635)
 PG_HOSTDEV int plan_start_index(unsigned pl) { return (pl >> 29) & 3; }
 
@@ -789,7 +843,7 @@ PG_HD void build_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
   } else {
     generate_map<RNG, TMAX>(c, p, m, e, rng);
   }
-  assign_subgoals<TMAX>(c, m, e);
+  assign_subgoals<TMAX>(c, p, m, e);
   m.plan = e.plan;
   // self.position = map_rng.choice(self.map.starters) (:635): 3 squares of the start line, x-major
   int stile = m.start_tile(), sd = plan_sd(e.plan);
@@ -925,7 +979,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
         for (int k = 0; k < ncars; k++) {
           unsigned xy = car_xy(car_slot(c, p, env, k));
           int lx = (int)(xy & 255) - tx * TILE, ly = (int)(xy >> 8) - ty * TILE;
-          if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE) { int sq = lx * TILE + ly; w[sq >> 5] |= 1u << (sq & 31); }
+          if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE) or_bit81(w, lx * TILE + ly);
         }
       } else if (kind == PGTG_CH_ZERO) continue;
       else tile_plane(c, m, kind, t, phase, w);

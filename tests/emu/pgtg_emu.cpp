@@ -36,6 +36,7 @@ static int bk_stats_reset(pgtg_env*, void*);
 static int bk_flatten(pgtg_env*, void*);
 static int bk_conn_table_max_bits() { return 13; }  // CPU tests: tables up to 8192 entries (e.g. 3x3 maps)
 static int bk_build_conn_table(pgtg_env*, uint32_t*);
+static int bk_build_path_table(pgtg_env*, uint64_t*);
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
@@ -168,6 +169,16 @@ static int bk_flatten(pgtg_env* e, void*) {
     else v = (float)p.obs_velocity[2 * env + (j - map_dim - nsd_dim - 18)];
     e->flat[i] = v;
   }
+  return 0;
+}
+
+// host loop of the path-table builder
+static int bk_build_path_table(pgtg_env* e, uint64_t* table) {
+  const DevCfg& c = e->dc;
+  std::vector<uint16_t> scratch(c.T + 8);
+  Lut lut;
+  memset(&lut, 0, sizeof(lut));
+  for (uint32_t g = 0; g < (1u << c.conn_bits); g++) table[g] = path_table_entry(c, lut, g, scratch.data());
   return 0;
 }
 
