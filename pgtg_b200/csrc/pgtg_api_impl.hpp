@@ -165,6 +165,14 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   d.C = c.num_channels; d.P = c.sliding ? 2 * c.window_k + 1 : TILE; d.sliding = c.sliding; d.window_k = c.window_k;
   d.use_nsd = c.use_next_subgoal_direction;
   for (int i = 0; i < PGTG_MAX_CHANNELS; i++) d.channel_kind[i] = c.channel_kind[i];
+  for (int k = 0; k < 16; k++) d.kind_channel[k] = -1;
+  d.obs_fast = 1;
+  for (int i = 0; i < c.num_channels; i++) {
+    int k = c.channel_kind[i];
+    if (k <= 0 || k >= 16) continue;  // PGTG_CH_ZERO planes stay zero
+    if (d.kind_channel[k] >= 0) d.obs_fast = 0;  // listed twice: generic channel loop
+    d.kind_channel[k] = i;
+  }
   d.fixed_map = c.fixed_map; d.edges_to_keep = c.edges_to_keep; d.border_connections = c.border_connections;
   d.start_mode = c.start_mode; d.goal_mode = c.goal_mode;
   d.start_x = c.start_x; d.start_y = c.start_y; d.start_dir = c.start_dir;

@@ -918,6 +918,16 @@ PG_HD void env_reset_pregenerated(const DevCfg& c, const DevPtrs& p, MapView& m,
 
 // ---------------------------------------------------------------------------------------------
 // observation (environment.py:1344-1506): planes as bitmaps
+// exit lines of a tile whose label (line_labels: 1 subgoal, 2 used subgoal, 3 start, 4 final goal) belongs to `kind`
+PG_HD void label_plane(const MapView& m, unsigned lab, int kind, uint32_t out[3]) {
+  for (int d = 0; d < 4; d++) {
+    unsigned l = (lab >> (4 * d)) & 15;
+    bool on = kind == PGTG_CH_GOALS ? (l == 1 || l == 4) : kind == PGTG_CH_SUBGOAL ? l == 1 : kind == PGTG_CH_FINAL_GOAL ? l == 4
+            : kind == PGTG_CH_START ? l == 3 : l == 2;
+    if (on) { out[0] |= m.L.exit_line[d][0]; out[1] |= m.L.exit_line[d][1]; out[2] |= m.L.exit_line[d][2]; }
+  }
+}
+
 PG_HD void tile_plane(const DevCfg& c, const MapView& m, int kind, int t, int phase, uint32_t out[3]) {
   out[0] = out[1] = out[2] = 0;
   unsigned td = m.tiles[t];
@@ -939,13 +949,7 @@ PG_HD void tile_plane(const DevCfg& c, const MapView& m, int kind, int t, int ph
     }
     case PGTG_CH_GOALS: case PGTG_CH_SUBGOAL: case PGTG_CH_FINAL_GOAL: case PGTG_CH_START: case PGTG_CH_USED_SUBGOAL: {
       if (!td_sg(td) && t != m.start_tile()) return;
-      unsigned lab = m.line_labels(t, td);
-      for (int d = 0; d < 4; d++) {
-        unsigned l = (lab >> (4 * d)) & 15;
-        bool on = kind == PGTG_CH_GOALS ? (l == 1 || l == 4) : kind == PGTG_CH_SUBGOAL ? l == 1 : kind == PGTG_CH_FINAL_GOAL ? l == 4
-                : kind == PGTG_CH_START ? l == 3 : l == 2;
-        if (on) { out[0] |= m.L.exit_line[d][0]; out[1] |= m.L.exit_line[d][1]; out[2] |= m.L.exit_line[d][2]; }
-      }
+      label_plane(m, m.line_labels(t, td), kind, out);
       return;
     }
     case PGTG_CH_CAR_SPAWNER: spawner_bits(c, m.L, ex, t % c.W, t / c.W, out); return;
@@ -969,7 +973,55 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
   int phase = light_phase(c, misc_light(e.misc));
   int ncars = misc_ncars(e.misc);
   int PP = c.P * c.P;
-  if (!c.sliding) {
+  if (!c.sliding && c.obs_fast) {
+    // Fixed window, kind by kind: a tile has walls, at most ONE obstacle / light plane, goal-ish
+    // lines only on path tiles; everything else stays zero and costs nothing (same bits as the
+    // channel loop below, which remains for feature lists that name a kind twice).
+    int t = ty * c.W + tx, ch;
+    unsigned td = m.tiles[t];
+    int ex = td_exits(td);
+    const uint32_t* wall = m.L.wall[ex];
+    if ((ch = c.kind_channel[PGTG_CH_WALLS]) >= 0) {
+      uint32_t off = base + ch * 81;
+      emit_bits(bits, off, wall[0]); emit_bits(bits, off + 32, wall[1]); emit_bits(bits, off + 64, wall[2]);
+    }
+    int ot = td_otype(td);
+    if (ot) {
+      ch = ot <= 3 ? c.kind_channel[PGTG_CH_ICE + ot - 1] : ot == 4 ? c.kind_channel[PGTG_CH_LIGHT_GREEN + phase] : -1;
+      if (ch >= 0) {
+        const uint32_t* mk = m.L.mask[td_omask(td)];
+        uint32_t off = base + ch * 81;
+        emit_bits(bits, off, mk[0] & ~wall[0]); emit_bits(bits, off + 32, mk[1] & ~wall[1]); emit_bits(bits, off + 64, mk[2] & ~wall[2]);
+      }
+    }
+    if (td_sg(td) || t == m.start_tile()) {
+      unsigned lab = m.line_labels(t, td);
+      for (int kind = PGTG_CH_GOALS; kind <= PGTG_CH_USED_SUBGOAL; kind = kind == PGTG_CH_GOALS ? PGTG_CH_SUBGOAL : kind + 1) {
+        if ((ch = c.kind_channel[kind]) < 0) continue;
+        uint32_t w[3] = {0u, 0u, 0u};
+        label_plane(m, lab, kind, w);
+        uint32_t off = base + ch * 81;
+        emit_bits(bits, off, w[0]); emit_bits(bits, off + 32, w[1]); emit_bits(bits, off + 64, w[2]);
+      }
+    }
+    if (ncars && (ch = c.kind_channel[PGTG_CH_TRAFFIC]) >= 0) {  // :1397-1409
+      uint32_t w[3] = {0u, 0u, 0u};
+      for (int k = 0; k < ncars; k++) {
+        unsigned xy = car_xy(car_slot(c, p, env, k));
+        int lx = (int)(xy & 255) - tx * TILE, ly = (int)(xy >> 8) - ty * TILE;
+        if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE) or_bit81(w, lx * TILE + ly);
+      }
+      uint32_t off = base + ch * 81;
+      emit_bits(bits, off, w[0]); emit_bits(bits, off + 32, w[1]); emit_bits(bits, off + 64, w[2]);
+    }
+    if ((ch = c.kind_channel[PGTG_CH_CAR_SPAWNER]) >= 0) {
+      uint32_t w[3] = {0u, 0u, 0u};
+      spawner_bits(c, m.L, ex, t % c.W, t / c.W, w);
+      uint32_t off = base + ch * 81;
+      emit_bits(bits, off, w[0]); emit_bits(bits, off + 32, w[1]); emit_bits(bits, off + 64, w[2]);
+    }
+    pos[0] = pix - tx * TILE; pos[1] = piy - ty * TILE;  // :1448-1461
+  } else if (!c.sliding) {
     int t = ty * c.W + tx;
     for (int ch = 0; ch < c.C; ch++) {
       int kind = c.channel_kind[ch];
