@@ -78,7 +78,8 @@ struct StatsArgs {
 template <int RNG, int MODE, int TMAX, bool PREGEN>
 __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
-                                                        const void* __restrict__ actions, int action_bytes, StatsArgs sa) {
+                                                        const void* __restrict__ actions, int action_bytes, StatsArgs sa,
+                                                        const __grid_constant__ SharedLayout layout) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int B = blockDim.x, tid = threadIdx.x;
   const int env0 = blockIdx.x * B;
@@ -86,9 +87,9 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
   const int env = env0 + tid;
   const bool valid = tid < nvalid;
   const int lane = tid & 31, warp = tid >> 5, nwarps = B >> 5;
-  BlockShared sh = carve_shared(smem, c, B);
+  BlockShared sh = carve_layout(smem, layout);
 
-  phase_stage(c, p, sh, tid, B, env0, nvalid, true);
+  phase_stage(c, p, sh, tid, B, env0, nvalid, true, !(PREGEN && MODE == MODE_STEP));
   if (tid < 8) { sh.counters[8 + tid] = 0; sh.dsum[tid] = 0.0; }
   __syncthreads();
 
@@ -216,11 +217,12 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
 // request queue) so that it only occupies a slice of each SM's registers and the tick kernel of the
 // next launch co-resides with it: this kernel is ALU-bound, the tick is HBM-bound.
 template <int RNG, int TMAX>
-__global__ void __launch_bounds__(128, PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity) {
+__global__ void __launch_bounds__(128, PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity,
+                                                                                const __grid_constant__ SharedLayout layout) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t count = p.regen_count[parity];
   if (blockIdx.x * blockDim.x >= count) return;
-  BlockShared sh = carve_mapgen(smem, c, blockDim.x);
+  BlockShared sh = carve_layout(smem, layout);
   stage_tables(c, p, sh, threadIdx.x, blockDim.x);
   __syncthreads();
   const uint2* list = p.regen_list + (size_t)parity * 2 * c.N;
@@ -319,7 +321,9 @@ static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, co
     if (ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return -1;
   }
   pgtg::StatsArgs sa = {e->stats_rows};
-  kern<<<e->nblk, e->block, smem, st>>>(e->dc, e->dp, mask, seeds, actions, action_bytes, sa);
+  unsigned char* const origin = (unsigned char*)4096;  // any 16-byte-aligned address: only differences are used
+  const pgtg::SharedLayout layout = pgtg::layout_of(pgtg::carve_shared(origin, e->dc, e->block), origin);
+  kern<<<e->nblk, e->block, smem, st>>>(e->dc, e->dp, mask, seeds, actions, action_bytes, sa, layout);
   return ck(cudaGetLastError());
 }
 
@@ -341,7 +345,9 @@ static int launch_mapgen(pgtg_env* e, cudaStream_t st) {
   if (smem > 48 * 1024 && ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return -1;
   int full = (2 * e->dc.N + B - 1) / B;
   int grid = e->mapgen_grid > 0 && e->mapgen_grid < full ? e->mapgen_grid : full;
-  kern<<<grid, B, smem, st>>>(e->dc, e->dp, e->dp.parity);
+  unsigned char* const origin = (unsigned char*)4096;
+  const pgtg::SharedLayout layout = pgtg::layout_of(pgtg::carve_mapgen(origin, e->dc, B), origin);
+  kern<<<grid, B, smem, st>>>(e->dc, e->dp, e->dp.parity, layout);
   return ck(cudaGetLastError());
 }
 
