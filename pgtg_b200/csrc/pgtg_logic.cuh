@@ -357,7 +357,8 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
   r.reward = 0; r.cost = 0; r.terminated = 0; r.braking = 0; r.outcome = 0;
   double perf = 0;
   e.elapsed++;
-  int light = (misc_light(e.misc) + 1) % c.light_total;  // :1113-1115
+  int light = misc_light(e.misc) + 1;  // :1113-1115; the counter is below the period except after an arbitrary set_state
+  if (light >= c.light_total) light = light == c.light_total ? 0 : light % c.light_total;
   e.misc = misc_pack(misc_flat(e.misc), light, misc_ncars(e.misc));
   int ax = action / 3 - 1, ay = action % 3 - 1;  // constants.py:6-16
   int n_cars = misc_ncars(e.misc);
