@@ -210,6 +210,7 @@ struct Lut {
   uint8_t entry_sq[4];
   uint32_t spawner_cols;  // local columns that can hold a car_spawner (derived when staging)
   uint32_t exit_any[3];   // union of the four exit lines (derived when staging)
+  uint8_t line_sq[4][4];  // the three squares of each exit line in ascending order (derived when staging)
 };
 struct LutInit { uint32_t wall[16][3], exit_line[4][3], mask[PGTG_NUM_MASKS][3], lane_any[16][3]; uint8_t native_spawner[16], entry_sq[4]; };
 PG_DEVCONST LutInit g_lut = {PGTG_TAB_WALL, PGTG_TAB_EXIT_LINE, PGTG_TAB_MASK, PGTG_TAB_LANE_ANY, PGTG_TAB_NATIVE_SPAWNER, PGTG_TAB_ENTRY_SQ};

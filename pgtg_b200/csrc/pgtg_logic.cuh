@@ -860,16 +860,10 @@ PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
   e.flags |= EF_TILES_DIRTY | EF_RESET;
   int stile = m.start_tile(), sd = plan_sd(e.plan);
   int k = plan_start_index(e.plan);
-  int ox = (stile % c.W) * TILE, oy = (stile / c.W) * TILE;
-  e.x = e.y = 0;
-  for (int w = 0; w < 3; w++) {
-    uint32_t bits = m.L.exit_line[sd][w];
-    while (bits) {
-      int sq = w * 32 + pg_ffs(bits) - 1;
-      bits &= bits - 1;
-      if (k-- == 0) { e.x = ox + sq / TILE; e.y = oy + sq % TILE; }
-    }
-  }
+  int ox = plan_sx(e.plan) * TILE, oy = plan_sy(e.plan) * TILE;
+  (void)stile;
+  int sq = m.L.line_sq[sd][k < 3 ? k : 0];  // k-th square of the start line, x-major (map.starters order)
+  e.x = ox + sq / TILE; e.y = oy + sq % TILE;
   e.vx = e.vy = 0;
   e.misc = 0;  // flat_tire, light counter, cars (:637-650)
   e.next_car_id = 0;
@@ -1017,7 +1011,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
     }
     if ((ch = c.kind_channel[PGTG_CH_CAR_SPAWNER]) >= 0) {
       uint32_t w[3] = {0u, 0u, 0u};
-      spawner_bits(c, m.L, ex, t % c.W, t / c.W, w);
+      spawner_bits(c, m.L, ex, tx, ty, w);
       uint32_t off = base + ch * 81;
       emit_bits(bits, off, w[0]); emit_bits(bits, off + 32, w[1]); emit_bits(bits, off + 64, w[2]);
     }
