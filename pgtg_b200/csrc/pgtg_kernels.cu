@@ -75,6 +75,18 @@ struct StatsArgs {
   double* rows;  // [gridDim.x][8]
 };
 
+// -DPGTG_PHASE_CLOCKS: profiling build (never the shipped one; load it through PGTG_B200_LIB):
+// per-warp SM-clock time of each phase of the ring-fed tick, summed into g_phase_clk and printed
+// by the statistics reduction. The macros expand to nothing in the normal build.
+#ifdef PGTG_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define PG_CLK_INIT long long clk_prev = clock64();
+#define PG_CLK(i) { if ((threadIdx.x & 31) == 0) { long long t_ = clock64(); atomicAdd(&g_phase_clk[i], (unsigned long long)(t_ - clk_prev)); clk_prev = t_; } }
+#else
+#define PG_CLK_INIT
+#define PG_CLK(i)
+#endif
+
 template <int RNG, int MODE, int TMAX, bool PREGEN>
 __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
@@ -89,9 +101,12 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
   const int lane = tid & 31, warp = tid >> 5, nwarps = B >> 5;
   BlockShared sh = carve_layout(smem, layout);
 
+  PG_CLK_INIT
   phase_stage(c, p, sh, tid, B, env0, nvalid, true, !(PREGEN && MODE == MODE_STEP));
   if (tid < 8) { sh.counters[8 + tid] = 0; sh.dsum[tid] = 0.0; }
+  PG_CLK(0)
   __syncthreads();
+  PG_CLK(1)
 
   bool done = false;
   if (MODE == MODE_STEP) {
@@ -104,6 +119,7 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
       done = r.outcome != 0;
       len = done ? (int)sh.regs[tid].elapsed : 0;
     }
+    PG_CLK(2)
     // episode statistics: ballots for the counters, warp reductions for the sums, one row per CTA
     unsigned any = __ballot_sync(0xffffffffu, done);
     if (any) {
@@ -125,11 +141,14 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
       // per warp; the atomic's round trip hides behind the observation emit.
       uint32_t k = 0, qbase = 0;
       if (any && lane == 0) qbase = atomicAdd(p.regen_count + p.parity, (uint32_t)__popc(any));
+      PG_CLK(3)
       if (done) {
         k = sh.regs[tid].episode + 1u;  // the episode this env is about to start
         phase_reset<RNG, TMAX, true>(c, p, sh, tid, env);
       }
+      PG_CLK(4)
       if (valid) phase_emit(c, p, sh, tid, env, false);
+      PG_CLK(5)
       if (any) {
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
         if (done) {
@@ -137,13 +156,16 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
           p.regen_list[(size_t)p.parity * 2 * c.N + qbase + __popc(any & ((1u << lane) - 1u))] = q;
         }
       }
+      PG_CLK(6)
       __syncthreads();
+      PG_CLK(7)
       if (tid == 0 && sh.counters[12]) {
         double* row = sa.rows + (size_t)blockIdx.x * STATS_STRIDE;
         row[0] += sh.counters[12]; row[1] += sh.dsum[0]; row[2] += sh.counters[11];
         row[3] += sh.counters[8]; row[4] += sh.counters[9]; row[5] += sh.counters[10];
       }
       phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid);
+      PG_CLK(8)
       return;
     }
   } else if (MODE == MODE_RESET) {
@@ -389,6 +411,19 @@ extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
 // Sum the per-CTA statistic rows into the 8-double `stats` buffer on the device (the buffer the
 // host all-reduces with NCCL), on `stream`, without synchronising.
 static int bk_stats_reduce(pgtg_env* e, void* stream) {
+#ifdef PGTG_PHASE_CLOCKS
+  {
+    unsigned long long h[16];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, pgtg::g_phase_clk, sizeof(h));
+    const char* names[9] = {"stage", "barrier", "step", "statistics, queue atomic", "reset", "emit", "queue write", "barrier", "expand"};
+    double tot = 0;
+    for (int i = 0; i < 9; i++) tot += (double)h[i];
+    for (int i = 0; i < 9 && tot > 0; i++) fprintf(stderr, "[phase clocks] %-26s %6.2f %%\n", names[i], 100.0 * (double)h[i] / tot);
+    memset(h, 0, sizeof(h));
+    cudaMemcpyToSymbol(pgtg::g_phase_clk, h, sizeof(h));
+  }
+#endif
   pgtg::pgtg_reduce_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->stats_rows, e->nblk, e->dp.stats);
   e->launches++;
   return ck(cudaGetLastError());
