@@ -208,6 +208,8 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   d.obs_bits = d.C * d.P * d.P;
   if (c.traffic_density > 0) { d.occ_words = (d.WS * d.HS + 15) / 16;  /* 2-bit counters */ d.spawner_cap = 2 * (d.W + d.H) + d.T; }
   d.pregen = (c.rng_mode != PGTG_RNG_TAPE && !c.fixed_map) ? 1 : 0;
+  d.lean = (d.pregen && !(c.traffic_density > 0) && !d.rules_without_traffic && !c.sliding && d.obs_fast && d.kind_channel[PGTG_CH_CAR_SPAWNER] < 0 &&
+            !d.use_nsd && !d.vis_words && !c.separate_reward_cost && !c.write_final_obs) ? 1 : 0;
   d.env_id_base = c.env_id_base; d.seed = c.seed;
   if (!c.fixed_map) {
     d.n_edge_tab = 2 * (d.W * (d.H - 1) + d.H * (d.W - 1));

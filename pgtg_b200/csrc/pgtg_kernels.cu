@@ -87,7 +87,7 @@ __device__ unsigned long long g_phase_clk[16];
 #define PG_CLK(i)
 #endif
 
-template <int RNG, int MODE, int TMAX, bool PREGEN>
+template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false>
 __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
                                                         const void* __restrict__ actions, int action_bytes, StatsArgs sa,
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
     int len = 0;
     if (valid) {
       int a = action_bytes == 8 ? (int)((const long long*)actions)[env] : ((const int*)actions)[env];
-      r = phase_step<RNG>(c, p, sh, tid, env, a);
+      r = phase_step<RNG, LEAN>(c, p, sh, tid, env, a);
       done = r.outcome != 0;
       len = done ? (int)sh.regs[tid].elapsed : 0;
     }
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
         atomicAdd(&sh.dsum[0], rs);
       }
     }
-    if (PREGEN && !c.write_final_obs) {
+    if (LEAN || (PREGEN && !c.write_final_obs)) {
       // Hot configuration (next maps come from the ring, no terminal-observation output): the
       // reset is a cheap swap, so every finished env is reset by its own thread and the CTA
       // needs one barrier only, the one in front of the byte expansion. Map requests are queued
@@ -144,10 +144,10 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
       PG_CLK(3)
       if (done) {
         k = sh.regs[tid].episode + 1u;  // the episode this env is about to start
-        phase_reset<RNG, TMAX, true>(c, p, sh, tid, env);
+        phase_reset<RNG, TMAX, true, LEAN>(c, p, sh, tid, env);
       }
       PG_CLK(4)
-      if (valid) phase_emit(c, p, sh, tid, env, false);
+      if (valid) phase_emit<LEAN>(c, p, sh, tid, env, false);
       PG_CLK(5)
       if (any) {
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
   } else {
     if (valid) sh.regs[tid] = load_regs(c, p, env);
   }
+
+  if (LEAN) return;  // (the lean instantiation is step-mode only and has returned above)
 
   // compaction of the done envs: warp ballot + CTA scan -> dense list in shared memory
   unsigned ballot = __ballot_sync(0xffffffffu, done);
@@ -331,9 +333,9 @@ static int bk_pick_block(const pgtg::DevCfg& c, int* block, size_t* smem) {
   return -1;
 }
 
-template <int RNG, int MODE, int TMAX, bool PREGEN>
+template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false>
 static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
-  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN>;
+  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN, LEAN>;
   // same L1/shared carveout as the map-generation kernel: an SM cannot host CTAs of two kernels with
   // different carveouts, which would serialise the two (measured: no overlap at all without this)
   static bool carve_set = false;
@@ -377,6 +379,9 @@ template <int RNG>
 static int launch_mode(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
   switch (mode) {
     case MODE_STEP:
+      // plain configuration: the lean instantiation (the ring-fed reset does not depend on the board size)
+      if (RNG != PGTG_RNG_TAPE && e->dc.pregen && e->dc.lean && !getenv("PGTG_NO_LEAN"))
+        return launch_one<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, MODE_STEP, 16, RNG != PGTG_RNG_TAPE, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
       if (RNG != PGTG_RNG_TAPE && e->dc.pregen) return launch_sized<RNG, MODE_STEP, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
       return launch_sized<RNG, MODE_STEP, false>(e, mask, seeds, actions, action_bytes, st);
     case MODE_RESET:

@@ -351,8 +351,12 @@ PG_HD bool visited_test_set(const DevCfg& c, const DevPtrs& p, int env, int x, i
   return was;
 }
 
-template <int RNG>
+// LEAN = compile-time promise of the plain configuration (no traffic and no rule that can fire
+// without it, fixed window written kind by kind, no next_subgoal_direction / visited penalty /
+// cost split): the corresponding code is not even emitted, which is what keeps the hot kernel small.
+template <int RNG, bool LEAN = false>
 PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env, int action) {
+  const bool split_cost = LEAN ? false : (bool)c.separate_reward_cost;
   StepResult r;
   r.reward = 0; r.cost = 0; r.terminated = 0; r.braking = 0; r.outcome = 0;
   double perf = 0;
@@ -361,7 +365,7 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
   if (light >= c.light_total) light = light == c.light_total ? 0 : light % c.light_total;
   e.misc = misc_pack(misc_flat(e.misc), light, misc_ncars(e.misc));
   int ax = action / 3 - 1, ay = action % 3 - 1;  // constants.py:6-16
-  int n_cars = misc_ncars(e.misc);
+  const int n_cars = LEAN ? 0 : misc_ncars(e.misc);
   if (n_cars > 0) {  // :1121-1127
     TrafficIO io = advance_cars<RNG>(c, p, m, e, env);
     e.next_car_id = io.next_car_id; e.err |= io.err; e.cursor = io.cursor;
@@ -369,7 +373,7 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
   Rng<RNG> rng(p, e, env);  // ice / broken road / sand streams of this tick
   int cx = e.x, cy = e.y;
   e.vx += ax; e.vy += ay;  // :1139
-  if (n_cars > 0 || c.rules_without_traffic) {  // :1145 (the default rules need traffic in the agent's tile)
+  if (!LEAN && (n_cars > 0 || c.rules_without_traffic)) {  // :1145 (the default rules need traffic in the agent's tile)
     if (apply_braking(c, p, m, e, env)) { r.braking = 1; e.vx = 0; e.vy = 0; }
   }
 
@@ -405,26 +409,26 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
       if (occ == 3) crash = any_car_at<RNG>(c, p, env, (unsigned)cx | (unsigned)cy << 8, 0, n_cars);
     }
     if (crash) {
-      if (c.separate_reward_cost) r.cost += c.crash_penalty; else r.reward -= c.crash_penalty;
+      if (split_cost) r.cost += c.crash_penalty; else r.reward -= c.crash_penalty;
       r.terminated = 1; r.outcome = 1;
       break;
     }
     if (f & SF_FINAL) {  // :1174-1180
       double isr = c.sum_subgoals_reward / (double)plan_ns(e.plan);  // :631-633
-      if (c.separate_reward_cost) perf += isr + c.final_goal_bonus; else r.reward += isr + c.final_goal_bonus;
+      if (split_cost) perf += isr + c.final_goal_bonus; else r.reward += isr + c.final_goal_bonus;
       r.terminated = 1; r.outcome = 2;
       break;
     }
     if (f & SF_SUBGOAL) {  // :1183-1188
       double isr = c.sum_subgoals_reward / (double)plan_ns(e.plan);
-      if (c.separate_reward_cost) perf += isr; else r.reward += isr;
+      if (split_cost) perf += isr; else r.reward += isr;
       m.consume_subgoal(cx, cy);
       e.flags |= EF_TILES_DIRTY;
     }
     if (!has_part) continue;  // :1191-1192
     int nx = cx + sx, ny = cy + sy;  // red light on the NEXT square, before ice (:1195-1202)
     if (red && m.inside(nx, ny) && m.light_at(nx, ny)) {
-      if (c.separate_reward_cost) r.cost += c.light_penalty; else r.reward -= c.light_penalty;
+      if (split_cost) r.cost += c.light_penalty; else r.reward -= c.light_penalty;
     }
     if ((f & SF_ICE) && rng.uniform(PGTG_STREAM_ICE) < c.ice_p) {  // :1205-1213
       int ia = rng.index(PGTG_STREAM_ICE, 9);
@@ -439,18 +443,18 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
   }
   if (flat) { e.vx = 0; e.vy = 0; }  // :1240-1241
   e.misc = misc_pack(flat, light, misc_ncars(e.misc));
-  if (c.vis_words) {  // :1244-1255
+  if (!LEAN && c.vis_words) {  // :1244-1255
     bool was = visited_test_set(c, p, env, cx, cy, true);
     if (was && !(ax == 0 && ay == 0)) {
-      if (c.separate_reward_cost) r.cost += c.visited_penalty; else r.reward -= c.visited_penalty;
+      if (split_cost) r.cost += c.visited_penalty; else r.reward -= c.visited_penalty;
     }
   }
   if (c.standing_penalty != 0 && ax == 0 && ay == 0 && e.x == cx && e.y == cy) {  // :1257-1263
-    if (c.separate_reward_cost) r.cost += c.standing_penalty; else r.reward -= c.standing_penalty;
+    if (split_cost) r.cost += c.standing_penalty; else r.reward -= c.standing_penalty;
   }
   e.x = cx; e.y = cy;
   rng.flush();
-  if (c.separate_reward_cost) r.reward = perf;  // :1271-1281
+  if (split_cost) r.reward = perf;  // :1271-1281
   return r;
 }
 
@@ -855,7 +859,7 @@ PG_HD void build_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
 }
 
 // the rest of PGTGEnv.reset (environment.py:635-656) on a finished map
-template <int RNG>
+template <int RNG, bool LEAN = false>
 PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng, int env) {
   e.flags |= EF_TILES_DIRTY | EF_RESET;
   int stile = m.start_tile(), sd = plan_sd(e.plan);
@@ -867,12 +871,12 @@ PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
   e.vx = e.vy = 0;
   e.misc = 0;  // flat_tire, light counter, cars (:637-650)
   e.next_car_id = 0;
-  if (c.vis_words) {
+  if (!LEAN && c.vis_words) {
     for (int i = 0; i < c.vis_words; i++) p.visited[(size_t)i * c.N + env] = 0;
     visited_test_set(c, p, env, e.x, e.y, true);  // positions_path = [position] (:643)
   }
   if (RNG == PGTG_RNG_NUMPY) rng.np_begin_episode();  // children 5r+1..5r+4 of this reset (:593-599)
-  if (c.traffic_density > 0) {  // :652-653
+  if (!LEAN && c.traffic_density > 0) {  // :652-653
     build_spawner_list(c, p, m, env);
     int64_t cur; uint32_t err;
     uint32_t r = create_initial_traffic<RNG>(c, p, m, e, env, rng.kcount[PGTG_STREAM_CAR], &cur, &err);
@@ -892,7 +896,7 @@ PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
 }
 
 // the same with the map taken from the pre-generated "next map" of this env
-template <int RNG>
+template <int RNG, bool LEAN = false>
 PG_HD void env_reset_pregenerated(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
   e.episode++;
   e.elapsed = 0;
@@ -908,7 +912,7 @@ PG_HD void env_reset_pregenerated(const DevCfg& c, const DevPtrs& p, MapView& m,
   }
   e.plan = p.next_plan[slot * c.N + env];
   m.plan = e.plan;
-  begin_episode<RNG>(c, p, m, e, rng, env);
+  begin_episode<RNG, LEAN>(c, p, m, e, rng, env);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -960,15 +964,16 @@ PG_HD void emit_bits(uint32_t* bits, uint32_t off, uint32_t v) {
 }
 
 // writes env's C*P*P observation bits at bit offset `base` of `bits`, plus position/velocity/nsd
+template <bool LEAN = false>
 PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, uint32_t* bits,
                         uint32_t base, int32_t* pos, int32_t* vel, int32_t* nsd) {
   int pix = e.x < 0 ? 0 : (e.x > c.WS - 1 ? c.WS - 1 : e.x);  // :1352-1356
   int piy = e.y < 0 ? 0 : (e.y > c.HS - 1 ? c.HS - 1 : e.y);
   int tx = pix / TILE, ty = piy / TILE;
   int phase = light_phase(c, misc_light(e.misc));
-  int ncars = misc_ncars(e.misc);
+  const int ncars = LEAN ? 0 : misc_ncars(e.misc);
   int PP = c.P * c.P;
-  if (!c.sliding && c.obs_fast) {
+  if (LEAN || (!c.sliding && c.obs_fast)) {
     // Fixed window, kind by kind: a tile has walls, at most ONE obstacle / light plane, goal-ish
     // lines only on path tiles; everything else stays zero and costs nothing (same bits as the
     // channel loop below, which remains for feature lists that name a kind twice).
@@ -999,7 +1004,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
         emit_bits(bits, off, w[0]); emit_bits(bits, off + 32, w[1]); emit_bits(bits, off + 64, w[2]);
       }
     }
-    if (ncars && (ch = c.kind_channel[PGTG_CH_TRAFFIC]) >= 0) {  // :1397-1409
+    if (!LEAN && ncars && (ch = c.kind_channel[PGTG_CH_TRAFFIC]) >= 0) {  // :1397-1409
       uint32_t w[3] = {0u, 0u, 0u};
       for (int k = 0; k < ncars; k++) {
         unsigned xy = car_xy(car_slot(c, p, env, k));
@@ -1009,7 +1014,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
       uint32_t off = base + ch * 81;
       emit_bits(bits, off, w[0]); emit_bits(bits, off + 32, w[1]); emit_bits(bits, off + 64, w[2]);
     }
-    if ((ch = c.kind_channel[PGTG_CH_CAR_SPAWNER]) >= 0) {
+    if (!LEAN && (ch = c.kind_channel[PGTG_CH_CAR_SPAWNER]) >= 0) {
       uint32_t w[3] = {0u, 0u, 0u};
       spawner_bits(c, m.L, ex, tx, ty, w);
       uint32_t off = base + ch * 81;
@@ -1075,7 +1080,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
   }
   vel[0] = e.vx; vel[1] = e.vy;
   int d = -1;
-  if (c.use_nsd) {  // :1466-1504
+  if (!LEAN && c.use_nsd) {  // :1466-1504
     int sg = td_sg(m.tiles[ty * c.W + tx]);  // map.py:120-141
     d = sg ? sg - 1 : -1;
     if (d == -1 || c.sliding) {

@@ -40,7 +40,7 @@ static int bk_build_path_table(pgtg_env*, uint64_t*);
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
-template <int RNG, int TMAX, bool PREGEN>
+template <int RNG, int TMAX, bool PREGEN, bool LEAN = false>
 static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes,
                       int blk, unsigned char* smem) {
   const DevCfg& c = h->dc;
@@ -54,7 +54,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
     for (int t = 0; t < nvalid; t++) {
       int env = env0 + t;
       int a = action_bytes == 8 ? (int)((const int64_t*)actions)[env] : ((const int32_t*)actions)[env];
-      StepResult r = phase_step<RNG>(c, p, sh, t, env, a);
+      StepResult r = phase_step<RNG, LEAN>(c, p, sh, t, env, a);
       if (r.outcome) {
         sh.done_list[n_done++] = t;
         st[0] += 1; st[1] += r.ep_return; st[2] += sh.regs[t].elapsed;
@@ -93,10 +93,10 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
     }
   }
   for (int k = 0; k < n_done; k++) {
-    if (PREGEN && mode == MODE_STEP) phase_reset<RNG, TMAX, true>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+    if (PREGEN && mode == MODE_STEP) phase_reset<RNG, TMAX, true, LEAN>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
     else phase_reset<RNG, TMAX, false>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
   }
-  for (int t = 0; t < nvalid; t++) phase_emit(c, p, sh, t, env0 + t, false);
+  for (int t = 0; t < nvalid; t++) phase_emit<LEAN>(c, p, sh, t, env0 + t, false);
   for (int t = 0; t < B; t++) phase_expand(c, p.obs_map, sh, t, B, env0, nvalid);
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
 }
@@ -133,11 +133,15 @@ static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* 
     memset(smem, 0xA5, bytes);  // shared memory starts undefined on the device too
     bool tape = h->cfg.rng_mode == PGTG_RNG_TAPE;
 #define RUN(R, M, G) run_block<R, M, G>(h, mode, mask, seeds, actions, action_bytes, b, smem)
+// the lean instantiation is a step-mode specialisation, as in the CUDA launch code
+#define RUNL(R, M) run_block<R, M, true, true>(h, mode, mask, seeds, actions, action_bytes, b, smem)
+    const bool lean = h->dc.lean && mode == MODE_STEP;
 #define RUN3(M) do { bool np = h->cfg.rng_mode == PGTG_RNG_NUMPY; if (tape) RUN(PGTG_RNG_TAPE, M, false); \
-    else if (np) { if (h->dc.pregen) RUN(PGTG_RNG_NUMPY, M, true); else RUN(PGTG_RNG_NUMPY, M, false); } \
-    else if (h->dc.pregen) RUN(PGTG_RNG_PHILOX, M, true); else RUN(PGTG_RNG_PHILOX, M, false); } while (0)
+    else if (np) { if (h->dc.pregen && lean) RUNL(PGTG_RNG_NUMPY, M); else if (h->dc.pregen) RUN(PGTG_RNG_NUMPY, M, true); else RUN(PGTG_RNG_NUMPY, M, false); } \
+    else if (h->dc.pregen && lean) RUNL(PGTG_RNG_PHILOX, M); else if (h->dc.pregen) RUN(PGTG_RNG_PHILOX, M, true); else RUN(PGTG_RNG_PHILOX, M, false); } while (0)
     if (T <= 16) RUN3(16); else if (T <= 64) RUN3(64); else RUN3(256);
 #undef RUN3
+#undef RUNL
 #undef RUN
   }
   free(smem);
