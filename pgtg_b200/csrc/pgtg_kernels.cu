@@ -66,6 +66,9 @@ constexpr int STATS_STRIDE = 8;
 #ifndef PGTG_MIN_BLOCKS
 #define PGTG_MIN_BLOCKS 8
 #endif
+#ifndef PGTG_LEAN_MIN_BLOCKS
+#define PGTG_LEAN_MIN_BLOCKS 8
+#endif
 #ifndef PGTG_MAPGEN_MIN_BLOCKS
 #define PGTG_MAPGEN_MIN_BLOCKS 12
 #endif
@@ -88,7 +91,7 @@ __device__ unsigned long long g_phase_clk[16];
 #endif
 
 template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false>
-__global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
+__global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
                                                         const void* __restrict__ actions, int action_bytes, StatsArgs sa,
                                                         const __grid_constant__ SharedLayout layout) {
@@ -113,11 +116,13 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
     StepResult r;
     r.outcome = 0; r.ep_return = 0;
     int len = 0;
+    EnvRegs er;  // lean instantiation: the env's registers stay in registers from step to emit
     if (valid) {
       int a = action_bytes == 8 ? (int)((const long long*)actions)[env] : ((const int*)actions)[env];
-      r = phase_step<RNG, LEAN>(c, p, sh, tid, env, a);
+      if (LEAN) { r = phase_step_regs<RNG, true>(c, p, sh, tid, env, a, er); len = (int)er.elapsed; }
+      else { r = phase_step<RNG, false>(c, p, sh, tid, env, a); len = (int)sh.regs[tid].elapsed; }
       done = r.outcome != 0;
-      len = done ? (int)sh.regs[tid].elapsed : 0;
+      len = done ? len : 0;
     }
     PG_CLK(2)
     // episode statistics: ballots for the counters, warp reductions for the sums, one row per CTA
@@ -143,11 +148,11 @@ __global__ void __launch_bounds__(128, PGTG_MIN_BLOCKS) pgtg_tick_kernel(const _
       if (any && lane == 0) qbase = atomicAdd(p.regen_count + p.parity, (uint32_t)__popc(any));
       PG_CLK(3)
       if (done) {
-        k = sh.regs[tid].episode + 1u;  // the episode this env is about to start
-        phase_reset<RNG, TMAX, true, LEAN>(c, p, sh, tid, env);
+        if (LEAN) { k = er.episode + 1u; phase_reset_regs<RNG, TMAX, true, true>(c, p, sh, tid, env, er); }
+        else { k = sh.regs[tid].episode + 1u; phase_reset<RNG, TMAX, true, false>(c, p, sh, tid, env); }  // k: the episode this env is about to start
       }
       PG_CLK(4)
-      if (valid) phase_emit<LEAN>(c, p, sh, tid, env, false);
+      if (valid) { if (LEAN) phase_emit_regs<true>(c, p, sh, tid, env, false, er); else phase_emit<false>(c, p, sh, tid, env, false); }
       PG_CLK(5)
       if (any) {
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
@@ -340,13 +345,13 @@ static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, co
   // different carveouts, which would serialise the two (measured: no overlap at all without this)
   static bool carve_set = false;
   if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve_set = true; }
-  const size_t smem = e->smem;
+  const size_t smem = LEAN ? pgtg::block_shared_bytes(e->dc, e->block, true) : e->smem;
   if (smem > 48 * 1024) {
     if (ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return -1;
   }
   pgtg::StatsArgs sa = {e->stats_rows};
   unsigned char* const origin = (unsigned char*)4096;  // any 16-byte-aligned address: only differences are used
-  const pgtg::SharedLayout layout = pgtg::layout_of(pgtg::carve_shared(origin, e->dc, e->block), origin);
+  const pgtg::SharedLayout layout = pgtg::layout_of(pgtg::carve_shared(origin, e->dc, e->block, LEAN), origin);
   kern<<<e->nblk, e->block, smem, st>>>(e->dc, e->dp, mask, seeds, actions, action_bytes, sa, layout);
   return ck(cudaGetLastError());
 }
