@@ -66,6 +66,9 @@ constexpr int STATS_STRIDE = 8;
 #ifndef PGTG_MIN_BLOCKS
 #define PGTG_MIN_BLOCKS 8
 #endif
+#ifndef PGTG_MAPGEN_TABLED_MIN_BLOCKS
+#define PGTG_MAPGEN_TABLED_MIN_BLOCKS 16  /* 32 registers, no spills: the tabled generator has no flood fill / BFS state */
+#endif
 #ifndef PGTG_LEAN_MIN_BLOCKS
 #define PGTG_LEAN_MIN_BLOCKS 8
 #endif
@@ -245,8 +248,8 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
 // Map generation ahead of time: a small PERSISTENT grid (a few CTAs per SM, grid-stride over the
 // request queue) so that it only occupies a slice of each SM's registers and the tick kernel of the
 // next launch co-resides with it: this kernel is ALU-bound, the tick is HBM-bound.
-template <int RNG, int TMAX>
-__global__ void __launch_bounds__(128, PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity,
+template <int RNG, int TMAX, bool TABLED = false>
+__global__ void __launch_bounds__(128, TABLED ? PGTG_MAPGEN_TABLED_MIN_BLOCKS : PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity,
                                                                                 const __grid_constant__ SharedLayout layout) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t count = p.regen_count[parity];
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(128, PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kerne
   const uint2* list = p.regen_list + (size_t)parity * 2 * c.N;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     uint2 r = list[i];
-    phase_pregenerate<RNG, TMAX>(c, p, sh, threadIdx.x, (int)r.x, r.y);
+    phase_pregenerate<RNG, TMAX, TABLED>(c, p, sh, threadIdx.x, (int)r.x, r.y);
   }
 }
 
@@ -364,11 +367,11 @@ static int launch_sized(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, 
   return launch_one<RNG, MODE, 256, PREGEN>(e, mask, seeds, actions, action_bytes, st);
 }
 
-template <int RNG, int TMAX>
+template <int RNG, int TMAX, bool TABLED = false>
 static int launch_mapgen(pgtg_env* e, cudaStream_t st) {
   const int B = 128;
   size_t smem = pgtg::mapgen_shared_bytes(e->dc, B);
-  auto kern = pgtg::pgtg_mapgen_kernel<RNG, TMAX>;
+  auto kern = pgtg::pgtg_mapgen_kernel<RNG, TMAX, TABLED>;
   static bool carve_set = false;
   if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve_set = true; }
   if (smem > 48 * 1024 && ck(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return -1;
@@ -393,6 +396,7 @@ static int launch_mode(pgtg_env* e, int mode, const uint8_t* mask, const int64_t
       return launch_sized<RNG, MODE_RESET, false>(e, mask, seeds, actions, action_bytes, st);
     case MODE_MAPGEN:
       if (RNG == PGTG_RNG_TAPE) return -1;
+      if (e->dc.conn_bits && e->dc.path_tab && !getenv("PGTG_NO_TABLED")) return launch_mapgen<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, 16, true>(e, st);
       if (e->dc.T <= 16) return launch_mapgen<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, 16>(e, st);
       if (e->dc.T <= 64) return launch_mapgen<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, 64>(e, st);
       return launch_mapgen<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, 256>(e, st);

@@ -604,10 +604,12 @@ PG_HD void graph_to_boards(const DevCfg& c, uint32_t graph, uint32_t& E, uint32_
   E = e; S = graph >> c.conn_ne;
 }
 
-template <int RNG, int TMAX>
+// TABLED = compile-time promise that both per-handle tables exist (fixed start/goal, <= 16 tiles,
+// <= 24 inner edges): the flood fill, the BFS and the start/goal draws are not emitted.
+template <int RNG, int TMAX, bool TABLED = false>
 PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng) {
   int sx = c.start_x, sy = c.start_y, sd = c.start_dir, gx = c.goal_x, gy = c.goal_y, gd = c.goal_dir;
-  if (c.start_mode != 0 || c.goal_mode != 0) choose_start_goal<RNG>(c, rng, sx, sy, sd, gx, gy, gd);
+  if (!TABLED && (c.start_mode != 0 || c.goal_mode != 0)) choose_start_goal<RNG>(c, rng, sx, sy, sd, gx, gy, gd);
   int W = c.W, T = c.T;
   int st = sy * W + sx, gt = gy * W + gx;
 
@@ -624,7 +626,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
 #pragma unroll
   for (int i = 0; i < AW; i++) alive[i] = (i * 32 + 32 <= n_tab) ? 0xFFFFFFFFu : (i * 32 < n_tab ? ((1u << (n_tab & 31)) - 1u) : 0u);
   // with the connectivity table the graph is kept as the table index itself (one bit per grid edge)
-  const bool tabled = TMAX <= 32 && c.conn_bits != 0;
+  const bool tabled = TABLED || (TMAX <= 32 && c.conn_bits != 0);
   uint32_t graph = tabled ? ((c.conn_bits >= 32 ? 0u : (1u << c.conn_bits)) - 1u) : 0u;
   while (cur > c.edges_to_keep && n_alive > 0) {  // :245
     int idx = rng.index(PGTG_STREAM_MAP, n_alive);  // :249
@@ -797,16 +799,16 @@ PG_HD void assign_subgoals_bfs(const DevCfg& c, MapView& m, EnvRegs& e) {
 // The path is a pure function of the inner edge set when start and goal are fixed: with the
 // connectivity table on and T <= 16 it is read from a table built once per handle by running
 // assign_subgoals_bfs on every edge set (path_table_entry), 8 bytes per map instead of a BFS.
-template <int TMAX>
+template <int TMAX, bool TABLED = false>
 PG_HD void assign_subgoals(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e) {
-  if (TMAX <= 16 && c.path_tab && m.graph_valid) {
+  if (TABLED || (TMAX <= 16 && c.path_tab && m.graph_valid)) {
     uint64_t v = pg_ldg(&p.path_table[m.graph]);
     for (int t = 0; t < c.T; t++) m.tiles[t] = (uint16_t)((m.tiles[t] & 0x07FF) | (unsigned)((v >> (3 * t)) & 7u) << 11);
     if (v >> 63) e.err |= 8;
     e.plan = (e.plan & 0xFFFFFu) | (unsigned)((v >> 48) & 0x1FFu) << 20;
     return;
   }
-  assign_subgoals_bfs<TMAX>(c, m, e);
+  if (!TABLED) assign_subgoals_bfs<TMAX>(c, m, e);
 }
 
 // one entry of the path table: edge set `graph` -> packed subgoal directions (scratch: T descriptors)
@@ -840,15 +842,15 @@ PG_HOSTDEV int plan_start_index(unsigned pl) { return (pl >> 29) & 3; }
 // goal / number of subgoals) and the start-square draw -- everything PGTGEnv.reset takes from
 // map_rng (environment.py:601-635). It depends only on (seed, episode), never on the actions, so
 // it can be built ahead of time by the map-generation kernel.
-template <int RNG, int TMAX>
+template <int RNG, int TMAX, bool TABLED = false>
 PG_HD void build_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng) {
-  if (c.fixed_map) {
+  if (!TABLED && c.fixed_map) {
     for (int t = 0; t < c.T; t++) m.tiles[t] = pg_ldg(&p.fixed_tiles[t]);
     e.plan = p.fixed_plan;
   } else {
-    generate_map<RNG, TMAX>(c, p, m, e, rng);
+    generate_map<RNG, TMAX, TABLED>(c, p, m, e, rng);
   }
-  assign_subgoals<TMAX>(c, p, m, e);
+  assign_subgoals<TMAX, TABLED>(c, p, m, e);
   m.plan = e.plan;
   // self.position = map_rng.choice(self.map.starters) (:635): 3 squares of the start line, x-major
   int stile = m.start_tile(), sd = plan_sd(e.plan);

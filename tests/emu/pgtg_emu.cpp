@@ -101,7 +101,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
 }
 
-template <int RNG, int TMAX>
+template <int RNG, int TMAX, bool TABLED = false>
 static void run_mapgen(pgtg_env* h) {
   const DevCfg& c = h->dc;
   const DevPtrs& p = h->dp;
@@ -114,7 +114,7 @@ static void run_mapgen(pgtg_env* h) {
     memset(smem, 0xA5, bytes);
     BlockShared sh = carve_mapgen(smem, c, B);
     for (int t = 0; t < B; t++) stage_tables(c, p, sh, t, B);
-    for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<RNG, TMAX>(c, p, sh, t, (int)list[i0 + t].x, list[i0 + t].y);
+    for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<RNG, TMAX, TABLED>(c, p, sh, t, (int)list[i0 + t].x, list[i0 + t].y);
   }
   free(smem);
 }
@@ -122,8 +122,9 @@ static void run_mapgen(pgtg_env* h) {
 static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void*) {
   int T = h->dc.T;  // same TMAX dispatch as the CUDA backend
   if (mode == MODE_MAPGEN) {
-    if (h->cfg.rng_mode == PGTG_RNG_NUMPY) { if (T <= 16) run_mapgen<PGTG_RNG_NUMPY, 16>(h); else if (T <= 64) run_mapgen<PGTG_RNG_NUMPY, 64>(h); else run_mapgen<PGTG_RNG_NUMPY, 256>(h); }
-    else { if (T <= 16) run_mapgen<PGTG_RNG_PHILOX, 16>(h); else if (T <= 64) run_mapgen<PGTG_RNG_PHILOX, 64>(h); else run_mapgen<PGTG_RNG_PHILOX, 256>(h); }
+    const bool tabled = h->dc.conn_bits && h->dc.path_tab;  // same dispatch as the CUDA launch code
+    if (h->cfg.rng_mode == PGTG_RNG_NUMPY) { if (tabled) run_mapgen<PGTG_RNG_NUMPY, 16, true>(h); else if (T <= 16) run_mapgen<PGTG_RNG_NUMPY, 16>(h); else if (T <= 64) run_mapgen<PGTG_RNG_NUMPY, 64>(h); else run_mapgen<PGTG_RNG_NUMPY, 256>(h); }
+    else { if (tabled) run_mapgen<PGTG_RNG_PHILOX, 16, true>(h); else if (T <= 16) run_mapgen<PGTG_RNG_PHILOX, 16>(h); else if (T <= 64) run_mapgen<PGTG_RNG_PHILOX, 64>(h); else run_mapgen<PGTG_RNG_PHILOX, 256>(h); }
     return 0;
   }
   size_t bytes = block_shared_bytes(h->dc, h->block);
