@@ -95,3 +95,39 @@ def test_results_do_not_depend_on_sharding():
     assert np.allclose(s, full.raw.stats())
     for e in (full, lo, hi):
         e.close()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(random_map_obstacle_probability=0.4), dict(random_map_width=3, random_map_height=3)],
+                         ids=["default", "obstacles", "3x3"])
+def test_specialised_kernels_match_general(kw, monkeypatch):
+    """The lean tick and the tabled map generation are compile-time specialisations of the general
+    kernels (same source, cold code not emitted): switching them off must not change one bit."""
+    import torch
+
+    from pgtg_b200 import PGTGVectorEnv
+
+    n, ticks = 20000, 40  # ragged last CTA; enough ticks for several generations of maps per env
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(11)
+    actions = [torch.randint(0, 9, (n,), device="cuda:0", dtype=torch.int32, generator=g) for _ in range(ticks)]
+
+    def run():
+        env = PGTGVectorEnv(n, device="cuda:0", seed=5, **kw)
+        env.reset()
+        out = []
+        for a in actions:
+            obs, rew, term, trunc, info = env.step(a)
+            out.append((env._t["obs_map"].clone(), obs["position"].clone(), obs["velocity"].clone(), rew.clone(), term.clone(), trunc.clone()))
+        return out, env.episode_stats()
+
+    fast, fast_stats = run()
+    monkeypatch.setenv("PGTG_NO_LEAN", "1")
+    monkeypatch.setenv("PGTG_NO_TABLED", "1")
+    slow, slow_stats = run()
+    for t, (a, b) in enumerate(zip(fast, slow)):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), f"tick {t}"
+    # (sums of returns are accumulated with atomics: the order, hence the last bits, may differ)
+    assert fast_stats.keys() == slow_stats.keys()
+    for k in fast_stats:
+        assert fast_stats[k] == pytest.approx(slow_stats[k], rel=1e-12), k
