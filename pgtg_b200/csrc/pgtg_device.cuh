@@ -34,6 +34,7 @@
 #define pg_ddiv(a, b) __ddiv_rn((a), (b))
 #define pg_atomic_or(p, v) atomicOr((p), (v))
 #define pg_store_streaming(ptr, v) __stcs((ptr), (v))  /* written once, never re-read by the kernel: evict-first */
+#define pg_prefetch_l2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))  /* fire-and-forget */
 #else
 #include <math.h>
 #include <string.h>
@@ -53,6 +54,7 @@ static inline uint32_t pg_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((u
 #define pg_ddiv(a, b) ((a) / (b))
 #define pg_atomic_or(p, v) (*(p) |= (v))
 #define pg_store_streaming(ptr, v) (*(ptr) = (v))
+#define pg_prefetch_l2(ptr) ((void)(ptr))
 struct short4 { short x, y, z, w; };
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
