@@ -678,6 +678,7 @@ extern "C" int pgtg_set_state(pgtg_env* e, const pgtg_state* s) {
         if (k == n - 1) next_id[i] = (unsigned)o[0] + 1;  // :1340
       }
       misc[i] = (misc[i] & 0xFFFFu) | (uint32_t)n << 16;
+      if (n > 0) e->dc.lean = 0;  // cars injected into a no-traffic handle: from now on the general tick
     }
     bk_h2d(p.cars, cars.data(), MC * N * 8, nullptr);
     bk_h2d(p.next_car_id, next_id.data(), N * 4, nullptr);
