@@ -244,10 +244,9 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
 }
 
 // Map generation ahead of time: dense over the envs queued by the tick that just ran (every lane
-// busy, no CTA barrier after the staging, tiny shared-memory footprint -> high occupancy).
-// Map generation ahead of time: a small PERSISTENT grid (a few CTAs per SM, grid-stride over the
-// request queue) so that it only occupies a slice of each SM's registers and the tick kernel of the
-// next launch co-resides with it: this kernel is ALU-bound, the tick is HBM-bound.
+// busy, no CTA barrier after the staging, tiny shared-memory footprint -> high occupancy). The
+// loop is grid-stride so that the launch code may also run it as a small persistent grid
+// (PGTG_MAPGEN_CTAS_PER_SM); the default is one request per thread. TABLED: see generate_map.
 template <int RNG, int TMAX, bool TABLED = false>
 __global__ void __launch_bounds__(128, TABLED ? PGTG_MAPGEN_TABLED_MIN_BLOCKS : PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity,
                                                                                 const __grid_constant__ SharedLayout layout) {

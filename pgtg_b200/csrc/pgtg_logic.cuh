@@ -510,14 +510,6 @@ PG_HD bool flood_connected32(int W, uint32_t e, uint32_t so, int s, int g) {
   }
 }
 
-// index of the subgraph (E, S) in the connectivity table: the E board has a hole after every row
-// (no edge from the last column), the S board is contiguous
-PG_HD uint32_t conn_index(const DevCfg& c, uint32_t e, uint32_t so) {
-  uint32_t idx = 0, rowmask = (1u << (c.W - 1)) - 1u;
-  for (int r = 0; r < c.H; r++) idx |= ((e >> (r * c.W)) & rowmask) << (r * (c.W - 1));
-  return idx | so << c.conn_ne;
-}
-
 template <int TMAX>
 PG_HD bool still_connected(const DevCfg& c, const DevPtrs& p, const Board<TMAX>& E, const Board<TMAX>& S, int a, int b, int s, int g) {
   if (TMAX <= 32) {  // whole board in one register: flood fill by shifts
