@@ -698,16 +698,14 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
       int mask;
       if (type != 4) mask = rng.index(PGTG_STREAM_MAP, 8);  // :430
       else {
-        int opts[6], n = 0, cnt = pg_popc(ex);
-        if (ex & 1) opts[n++] = 8;
-        if (ex & 2) opts[n++] = 9;
-        if (ex & 4) opts[n++] = 10;
-        if (ex & 8) opts[n++] = 11;
-        if ((ex & 1) && (ex & 4) && cnt >= 3) opts[n++] = 12;
-        if ((ex & 2) && (ex & 8) && cnt >= 3) opts[n++] = 13;
-        int k = rng.index(PGTG_STREAM_MAP, n);  // :470
-        mask = opts[0];
-        for (int q = 1; q < 6; q++) if (q == k) mask = opts[q];
+        // candidate masks 8..13 as a bit set (no indexed local array: that would live in local memory)
+        int cnt = pg_popc(ex);
+        unsigned cand = (unsigned)(ex & 15);                          // 8..11: one light per exit
+        if ((ex & 1) && (ex & 4) && cnt >= 3) cand |= 16u;            // 12: north-south pair
+        if ((ex & 2) && (ex & 8) && cnt >= 3) cand |= 32u;            // 13: east-west pair
+        int k = rng.index(PGTG_STREAM_MAP, pg_popc(cand));  // :470
+        while (k-- > 0) cand &= cand - 1;                             // drop the k lowest candidates
+        mask = 8 + pg_ffs(cand) - 1;
       }
       m.tiles[t] = (uint16_t)(ex | type << 4 | mask << 7);
     }
