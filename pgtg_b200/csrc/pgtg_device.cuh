@@ -35,6 +35,10 @@
 #define pg_atomic_or(p, v) atomicOr((p), (v))
 #define pg_store_streaming(ptr, v) __stcs((ptr), (v))  /* written once, never re-read by the kernel: evict-first */
 #define pg_prefetch_l2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))  /* fire-and-forget */
+/* 32 bytes with one 256-bit streaming store (sm_100: STG.256); ptr 32-byte aligned */
+__device__ __forceinline__ void pg_store_streaming32(void* ptr, uint2 a, uint2 b, uint2 c2, uint2 d) {
+  asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(b.x), "r"(b.y), "r"(c2.x), "r"(c2.y), "r"(d.x), "r"(d.y) : "memory");
+}
 #else
 #include <math.h>
 #include <string.h>
@@ -60,6 +64,9 @@ struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 struct uint2 { unsigned x, y; };
+static inline void pg_store_streaming32(void* ptr, uint2 a, uint2 b, uint2 c2, uint2 d) {
+  uint2* q = (uint2*)ptr; q[0] = a; q[1] = b; q[2] = c2; q[3] = d;
+}
 #endif
 
 #include "../../include/pgtg_b200.h"
