@@ -236,3 +236,63 @@ def record_trace(kwargs: dict, num_envs: int, ticks: int, seed: int, action_seed
                 observation_keys=keys, numpy=np.__version__)
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     return out
+
+
+# ---- digests of a full-size reference run (see oracle/digest.py) -----------------------------------
+def _digest_chunk(args):
+    kwargs, start, n, ticks, seed, actions, max_episode_steps, keep_tape = args
+    import warnings
+
+    from oracle import digest
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tr = record_trace(kwargs, num_envs=n, ticks=ticks, seed=seed + start, max_episode_steps=max_episode_steps, actions=actions)
+    Cn, P = tr["obs_map"].shape[2], tr["obs_map"].shape[3]
+    T, MC = tr["tiles"].shape[2], tr["cars"].shape[2]
+    h = np.zeros((n, ticks + 1, 16), np.uint8)
+
+    def obs(t):
+        return dict(map=tr["obs_map"][t], position=tr["obs_position"][t], velocity=tr["obs_velocity"][t], nsd=tr["obs_nsd"][t])
+
+    def state(t):
+        return dict(agent=tr["agent"][t], num_cars=tr["num_cars"][t], cars=tr["cars"][t], tiles=tr["tiles"][t], plan=tr["plan"][t],
+                    agent_direction=tr["agent_direction"][t])
+
+    h[:, 0] = digest.row_hashes(digest.rows(n, Cn, P, T, MC, obs=obs(0), state=state(0)))
+    for t in range(ticks):
+        step = {k: tr[k][t] for k in ("reward", "cost", "terminated", "truncated", "step_state", "step_flags")}
+        final = dict(map=tr["final_obs_map"][t], position=tr["final_obs_position"][t], velocity=tr["final_obs_velocity"][t], nsd=tr["final_obs_nsd"][t])
+        h[:, t + 1] = digest.row_hashes(digest.rows(n, Cn, P, T, MC, step=step, final=final, obs=obs(t + 1), state=state(t + 1)))
+    tape = (tr["tape_values"], tr["tape_tags"], np.diff(tr["tape_offsets"])) if keep_tape else None
+    counts = dict(done=int(tr["terminated"].sum() + tr["truncated"].sum()), reward_pos=int((tr["reward"] > 0).sum()),
+                  brake=int(((tr["step_flags"] & 2) > 0).sum()), draws=int(tr["tape_offsets"][-1]), cars_max=int(tr["num_cars"].max()))
+    return start, h, tape, counts
+
+
+def record_digests(kwargs: dict, num_envs: int, ticks: int, seed: int, actions: np.ndarray, max_episode_steps: int | None = None,
+                   workers: int = 8, chunk: int = 16, keep_tape: bool = True) -> dict:
+    """Run `num_envs` reference envs (seed + i) for `ticks` ticks of `actions` [ticks, num_envs] with same-step
+    auto-reset, in `workers` forked processes, and keep only the digests (+ optionally the draw tape)."""
+    import multiprocessing as mp
+
+    jobs = [(kwargs, s, min(chunk, num_envs - s), ticks, seed, np.ascontiguousarray(actions[:, s:s + chunk]), max_episode_steps, keep_tape)
+            for s in range(0, num_envs, chunk)]
+    h = np.zeros((num_envs, ticks + 1, 16), np.uint8)
+    tapes, totals = {}, {}
+    with mp.get_context("fork").Pool(workers) as pool:
+        for start, hc, tape, counts in pool.imap_unordered(_digest_chunk, jobs):
+            h[start:start + hc.shape[0]] = hc
+            tapes[start] = tape
+            for k, v in counts.items():
+                totals[k] = max(totals.get(k, 0), v) if k == "cars_max" else totals.get(k, 0) + v
+    from oracle import digest
+
+    tick_digest, env_digest = digest.fold(h)
+    out = dict(tick_digest=tick_digest, env_digest=env_digest, totals=totals)
+    if keep_tape:
+        order = sorted(tapes)
+        out["tape_values"] = np.concatenate([tapes[s][0] for s in order])
+        out["tape_tags"] = np.concatenate([tapes[s][1] for s in order])
+        out["tape_offsets"] = np.concatenate([[0], np.cumsum(np.concatenate([tapes[s][2] for s in order]))]).astype(np.int64)
+    return out

@@ -31,36 +31,7 @@
 
 using namespace pgtg;
 
-enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2, MODE_MAPGEN = 3 };
-
-struct pgtg_env {
-  pgtg_config cfg;
-  DevCfg dc;
-  DevPtrs dp;
-  int device;
-  int block;
-  size_t smem;
-  int64_t launches;
-  std::vector<void*> allocs;
-  bool have_fixed, have_tape, did_reset;
-  int nblk;             // CTAs per launch
-  // pregen pipeline: the persistent map-generation kernel runs on a side stream and overlaps the next tick
-  void* side_stream; void* ev_tick; void* ev_map[2];
-  uint64_t launch_index;
-  int mapgen_grid;      // CTAs of the persistent map-generation kernel (0 = one per 128 requests)
-  int mapgen_grid_overlap; bool overlap;  // overlap on: side stream + small grid; off: same stream, full grid
-  // optional per-kernel timing (CUDA events on the launching stream around each kernel of a tick)
-  bool timing; std::vector<void*> tev; int tev_used;
-  // flattened observation (FlattenObservation view for SB3-style consumers), allocated on first use
-  float* flat; int flat_dim; int flat_order[PGTG_MAX_CHANNELS];
-  double* stats_rows;   // [nblk][8] per-CTA episode statistics (CUDA backend)
-  // device scratch for reset arguments and host-buffer steps
-  uint8_t* mask_dev;
-  int64_t* seeds_dev;
-  int32_t* actions_dev;
-  // host tables kept for get_state / introspection
-  std::vector<uint16_t> edge_tab, edge_rev, border_slots;
-};
+#include "pgtg_env.hpp"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -150,6 +121,13 @@ static void build_direction_lut(int R, std::vector<uint8_t>& lut) {
     }
 }
 
+// The plain configuration the LEAN tick instantiation promises (pgtg_logic.cuh, env_step): decided at
+// pgtg_create and again whenever something it depends on changes (pgtg_update_rules, pgtg_set_state).
+static int lean_predicate(const pgtg_config& c, const DevCfg& d) {
+  return (d.pregen && !(c.traffic_density > 0) && !d.rules_without_traffic && !c.sliding && d.obs_fast && d.kind_channel[PGTG_CH_CAR_SPAWNER] < 0 &&
+          !d.use_nsd && !d.vis_words && !c.separate_reward_cost && !c.write_final_obs) ? 1 : 0;
+}
+
 static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   memset(&d, 0, sizeof d);
   if (c.abi_version != PGTG_ABI_VERSION) { why = "pgtg_config.abi_version mismatch"; return -1; }
@@ -208,8 +186,7 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   d.obs_bits = d.C * d.P * d.P;
   if (c.traffic_density > 0) { d.occ_words = (d.WS * d.HS + 15) / 16;  /* 2-bit counters */ d.spawner_cap = 2 * (d.W + d.H) + d.T; }
   d.pregen = (c.rng_mode != PGTG_RNG_TAPE && !c.fixed_map) ? 1 : 0;
-  d.lean = (d.pregen && !(c.traffic_density > 0) && !d.rules_without_traffic && !c.sliding && d.obs_fast && d.kind_channel[PGTG_CH_CAR_SPAWNER] < 0 &&
-            !d.use_nsd && !d.vis_words && !c.separate_reward_cost && !c.write_final_obs) ? 1 : 0;
+  d.lean = lean_predicate(c, d);
   d.env_id_base = c.env_id_base; d.seed = c.seed;
   if (!c.fixed_map) {
     d.n_edge_tab = 2 * (d.W * (d.H - 1) + d.H * (d.W - 1));
@@ -239,6 +216,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   pgtg_env* e = new pgtg_env();
   e->cfg = *cfg; e->dc = dc; e->device = device; e->launches = 0;
   e->have_fixed = e->have_tape = e->did_reset = false;
+  e->cars_injected = false;
   e->timing = false; e->tev_used = 0;
   e->side_stream = e->ev_tick = e->ev_map[0] = e->ev_map[1] = nullptr;
   e->launch_index = 0; e->mapgen_grid = 0;
@@ -399,6 +377,9 @@ extern "C" int pgtg_update_rules(pgtg_env* e, const pgtg_rule* rules, int num_ru
   e->dc.rules_without_traffic = 0;
   for (int i = 0; i < num_rules; i++) if (rules[i].min_traffic <= 0 && rules[i].min_matching_traffic <= 0) e->dc.rules_without_traffic = 1;
   e->cfg.num_rules = num_rules;
+  for (int i = 0; i < num_rules; i++) e->cfg.rules[i] = rules[i];
+  // a rule that can fire without traffic needs apply_braking, which the lean tick does not contain
+  e->dc.lean = lean_predicate(e->cfg, e->dc) && !e->cars_injected;
   return PGTG_OK;
 }
 
@@ -678,7 +659,7 @@ extern "C" int pgtg_set_state(pgtg_env* e, const pgtg_state* s) {
         if (k == n - 1) next_id[i] = (unsigned)o[0] + 1;  // :1340
       }
       misc[i] = (misc[i] & 0xFFFFu) | (uint32_t)n << 16;
-      if (n > 0) e->dc.lean = 0;  // cars injected into a no-traffic handle: from now on the general tick
+      if (n > 0) { e->cars_injected = true; e->dc.lean = 0; }  // cars injected into a no-traffic handle: from now on the general tick
     }
     bk_h2d(p.cars, cars.data(), MC * N * 8, nullptr);
     bk_h2d(p.next_car_id, next_id.data(), N * 4, nullptr);
@@ -706,6 +687,8 @@ extern "C" int pgtg_reset_stats(pgtg_env* e, void* stream) {
 extern "C" int pgtg_stats(pgtg_env* e, double* out8, int reset_after) {
   if (!e || !out8) return fail(PGTG_ERR_INVALID, "null argument");
   bk_set_device(e->device);
+  // ticks may be in flight on non-blocking streams: the reduction below runs on the legacy stream
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
   if (bk_stats_reduce(e, nullptr)) return fail(PGTG_ERR_CUDA, std::string("stats reduction failed: ") + bk_error());
   bk_d2h(out8, e->dp.stats, 64, nullptr);
   if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());

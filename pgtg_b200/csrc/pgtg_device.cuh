@@ -20,7 +20,7 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define PG_HD __device__ __forceinline__
-#define PG_HDN __device__ __noinline__
+#define PG_HDN static __device__ __noinline__
 #define PG_HOSTDEV __host__ __device__ inline
 #define PG_MEMBER __device__
 #define PG_DEVCONST __device__ const

@@ -1,0 +1,7 @@
+// pgtg_inst_tape.cu -- the PGTG_RNG_TAPE instantiations of the tick and map-generation kernels
+// (pgtg_tick_kernels.cuh); one translation unit per random-number source so that they build in parallel.
+#include "pgtg_tick_kernels.cuh"
+
+int pgtg_launch_mode_tape(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream) {
+  return launch_mode<PGTG_RNG_TAPE>(e, mode, mask, seeds, actions, action_bytes, (cudaStream_t)stream);
+}

@@ -17,6 +17,7 @@ by the native handle -- valid until the next `step`/`reset`; clone what must out
 """
 from __future__ import annotations
 
+from collections.abc import MutableMapping
 from typing import Any
 
 import numpy as np
@@ -28,31 +29,41 @@ from ._names import ROUTE_NAMES
 from .raw import RawEnv
 
 
-class LazyInfo(dict):
+class LazyInfo(MutableMapping):
     """`info` of a step: entries that cost a kernel launch (bit tests on `step_flags`) are computed on
-    first access, so a rollout loop that ignores them pays nothing."""
+    first access, so a rollout loop that ignores them pays nothing. A Mapping rather than a dict
+    subclass, so that `dict(info)`, `{**info}` and wrappers that copy infos go through `__getitem__`
+    and see the materialised values."""
 
     def __init__(self, *a, **k):
-        super().__init__(*a, **k)
+        self._d = dict(*a, **k)
         self._lazy = {}
 
     def lazy(self, key, fn):
         self._lazy[key] = fn
-        dict.__setitem__(self, key, None)
+        self._d[key] = None
 
     def __getitem__(self, key):
         if key in self._lazy:
-            dict.__setitem__(self, key, self._lazy.pop(key)())
-        return dict.__getitem__(self, key)
+            self._d[key] = self._lazy.pop(key)()
+        return self._d[key]
 
-    def get(self, key, default=None):
-        return self[key] if key in self else default
+    def __setitem__(self, key, value):
+        self._lazy.pop(key, None)
+        self._d[key] = value
 
-    def items(self):
-        return [(k, self[k]) for k in self]
+    def __delitem__(self, key):
+        self._lazy.pop(key, None)
+        del self._d[key]
 
-    def values(self):
-        return [self[k] for k in self]
+    def __iter__(self):
+        return iter(self._d)
+
+    def __len__(self):
+        return len(self._d)
+
+    def __repr__(self):
+        return f"LazyInfo({dict(self)!r})"
 
 
 def _device_index(device) -> int:
@@ -127,8 +138,8 @@ class PGTGVectorEnv:
         seeds = None
         if seed is not None:
             seeds = np.asarray(seed, dtype=np.int64)
-            if seeds.ndim == 0:
-                seeds = int(seeds) + np.arange(self.num_envs, dtype=np.int64)
+            if seeds.ndim == 0:  # env i of the whole (possibly sharded) job is seeded seed + global index
+                seeds = int(seeds) + int(self.hc.pod.env_id_base) + np.arange(self.num_envs, dtype=np.int64)
             if seeds.shape != (self.num_envs,):
                 raise ValueError("seed must be an int or one seed per env")
         with torch.cuda.device(self.device):
