@@ -74,6 +74,8 @@ typedef struct {
   uint32_t draw_k[5];       /* words consumed per stream this tick */
   uint32_t blk[4], blk_index; /* cached Philox block of blk_stream */
   int blk_stream;
+  uint32_t cblk[4], cblk_index; /* cached car-stream block of car slot cblk_slot */
+  int cblk_slot;
   /* numpy mode: the five PCG64 children of this reset (environment.py:593-599) */
   struct { unsigned __int128 state, inc; uint32_t buf; int has; } pcg[5];
   int64_t cursor, tape_end;
@@ -134,6 +136,41 @@ static uint32_t philox_word(rctx* r, int stream) {
     e->blk_stream = stream; e->blk_index = b;
   }
   return e->blk[pos & 3u];
+}
+
+/* Philox CAR stream (product specification, pgtg_b200/csrc/pgtg_device.cuh CW_*): every car owns one block
+ * sequence per tick, block b of car slot s = philox(counter = (b, tick, episode, STREAM_CAR | (s + 1) << 8), key),
+ * s = the car's list index when the tick starts, with fixed word meanings; a car-stream uniform is one word
+ * * 2^-32. Initial traffic: car slot j takes lane square perm(j) (4-round Feistel over [0, 4^h), keys = the
+ * block of slot -1, cycle-walked into [0, n)); profile and route from words 0 and 1 of its own tick-0 block. */
+enum { CW_DELAY = 0, CW_SPEED = 1, CW_IDX = 2, CW_PUSH = 3, CW_LIGHT = 4, CW_SPAWNER = 5, CW_SPAWN_ROUTE = 6, CW_PROFILE = 7,
+       CW0_PROFILE = 0, CW0_ROUTE = 1 };
+static uint32_t philox_car_word(rctx* r, int slot, int pos) {
+  ora_env* e = r->e;
+  uint32_t b = (uint32_t)pos >> 2;
+  if (e->cblk_slot != slot || e->cblk_index != b) {
+    e->cblk[0] = b; e->cblk[1] = (uint32_t)e->elapsed; e->cblk[2] = e->episode;
+    e->cblk[3] = (uint32_t)PGTG_STREAM_CAR | (uint32_t)(slot + 1) << 8;
+    philox4x32_10(e->cblk, (uint32_t)e->seed, (uint32_t)(e->seed >> 32));
+    e->cblk_slot = slot; e->cblk_index = b;
+  }
+  return e->cblk[pos & 3];
+}
+static uint32_t feistel_round(uint32_t x, uint32_t k, int h) {
+  uint32_t t = (x + k) * 0x9E3779B1u;
+  t ^= t >> 15; t *= 0x85EBCA6Bu; t ^= t >> 13; t *= 0xC2B2AE35u; t ^= t >> 16;
+  return t >> (32 - h);
+}
+static int initial_car_position(const uint32_t keys[4], int n, int slot) {
+  int h = 1;
+  while ((1 << (2 * h)) < n) h++;
+  uint32_t v = (uint32_t)slot, mask = (1u << h) - 1u;
+  do {
+    uint32_t L = v >> h, R = v & mask;
+    for (int i = 0; i < 4; i++) { uint32_t t = L ^ feistel_round(R, keys[i], h); L = R; R = t; }
+    v = L << h | R;
+  } while (v >= (uint32_t)n);
+  return (int)v;
 }
 
 /* ---- numpy mode (PGTG_RNG_NUMPY): SeedSequence + PCG64 + Generator methods, restated from numpy's
@@ -223,9 +260,33 @@ static int rng_choice_cdf(rctx* r, int stream, const double* cdf, int n) {
   return i;
 }
 
+/* car-stream draws: the reference's sequential car_rng order in tape / numpy mode, the per-car blocks in Philox mode */
+static double rng_car_double(rctx* r, int slot, int pos) {
+  if (r->b->cfg.rng_mode != PGTG_RNG_PHILOX) return rng_double(r, PGTG_STREAM_CAR);
+  return (double)philox_car_word(r, slot, pos) * (1.0 / 4294967296.0);
+}
+static int rng_car_index(rctx* r, int slot, int pos, int n) {
+  if (n <= 1) return 0;
+  if (r->b->cfg.rng_mode != PGTG_RNG_PHILOX) return rng_index(r, PGTG_STREAM_CAR, n);
+  return (int)(((uint64_t)philox_car_word(r, slot, pos) * (uint64_t)n) >> 32);
+}
+static int rng_car_choice_cdf(rctx* r, int slot, int pos, const double* cdf, int n) {
+  if (r->b->cfg.rng_mode != PGTG_RNG_PHILOX) return rng_choice_cdf(r, PGTG_STREAM_CAR, cdf, n);
+  double u = rng_car_double(r, slot, pos);
+  int i = 0;
+  while (i < n - 1 && cdf[i] <= u) i++;
+  return i;
+}
+
 /* Generator.choice(n, size=k, replace=False): k distinct indices in returned order.
- * Philox mode: sequential rejection sampling (spec shared with the product). */
+ * Philox mode: the keyed Feistel permutation of the car-stream specification above. */
 static void rng_distinct(rctx* r, int stream, int n, int k, int* out) {
+  if (r->b->cfg.rng_mode == PGTG_RNG_PHILOX) {
+    uint32_t keys[4];
+    for (int i = 0; i < 4; i++) keys[i] = philox_car_word(r, -1, i);
+    for (int j = 0; j < k; j++) out[j] = initial_car_position(keys, n, j);
+    return;
+  }
   if (r->b->cfg.rng_mode == PGTG_RNG_NUMPY) { /* Floyd's sampling + shuffle (_generator.pyx choice) */
     for (int t = 0; t < k; t++) {
       uint32_t j = (uint32_t)(n - k + t), v = np_bounded(r->e, stream, j);
@@ -237,18 +298,9 @@ static void rng_distinct(rctx* r, int stream, int n, int k, int* out) {
     return;
   }
   for (int j = 0; j < k; j++) {
-    if (r->b->cfg.rng_mode == PGTG_RNG_TAPE) {
-      int v = (int)tape_next(r, stream, PGTG_DRAW_INDEX);
-      if (v < 0 || v >= n) { r->e->error |= 4; v = 0; }
-      out[j] = v;
-      continue;
-    }
-    for (;;) {
-      int v = (int)(((uint64_t)philox_word(r, stream) * (uint64_t)n) >> 32);
-      int dup = 0;
-      for (int q = 0; q < j; q++) if (out[q] == v) { dup = 1; break; }
-      if (!dup) { out[j] = v; break; }
-    }
+    int v = (int)tape_next(r, stream, PGTG_DRAW_INDEX);
+    if (v < 0 || v >= n) { r->e->error |= 4; v = 0; }
+    out[j] = v;
   }
 }
 
@@ -596,15 +648,15 @@ static int light_phase(const pgtg_config* c, int counter) {
   return 2;
 }
 
-static int select_profile(rctx* r) { /* _select_driver_profile (:658-662) */
-  return rng_choice_cdf(r, PGTG_STREAM_CAR, r->b->cfg.profile_cdf, PGTG_NUM_PROFILES);
+static int select_profile(rctx* r, int slot, int pos) { /* _select_driver_profile (:658-662) */
+  return rng_car_choice_cdf(r, slot, pos, r->b->cfg.profile_cdf, PGTG_NUM_PROFILES);
 }
 
-static int random_route_at(rctx* r, int x, int y) {
+static int random_route_at(rctx* r, int x, int y, int slot, int pos) {
   /* sorted route names of the square's non-"all" lanes, then car_rng.choice (:854-874, 982-997) */
   const ora_lane_sq* l = lanes_at(r->e, x, y);
   if (l->n == 0) { r->e->error |= 16; return 0; }
-  return l->route[rng_index(r, PGTG_STREAM_CAR, l->n)];
+  return l->route[rng_car_index(r, slot, pos, l->n)];
 }
 
 static void create_initial_traffic(rctx* r) {
@@ -620,47 +672,47 @@ static void create_initial_traffic(rctx* r) {
   for (int i = 0; i < num_cars; i++) {
     int x = e->spawnable[idx[i]][0], y = e->spawnable[idx[i]][1];
     ora_car* c = &e->cars[e->n_cars++];
-    c->profile = select_profile(r);
-    c->route = random_route_at(r, x, y);
+    c->profile = select_profile(r, i, CW0_PROFILE);
+    c->route = random_route_at(r, x, y, i, CW0_ROUTE);
     c->id = e->next_car_id++;
     c->x = x; c->y = y; c->patience = 0; c->delay = 0;
   }
   free(idx);
 }
 
-static void spawn_new_car(rctx* r, ora_car* out) {
+static void spawn_new_car(rctx* r, ora_car* out, int slot) {
   /* _spawn_new_car (environment.py:970-1002) */
   ora_env* e = r->e;
   int x = 0, y = 0;
   if (e->n_spawners > 0) {
-    int i = rng_index(r, PGTG_STREAM_CAR, e->n_spawners);
+    int i = rng_car_index(r, slot, CW_SPAWNER, e->n_spawners);
     x = e->spawners[i][0]; y = e->spawners[i][1];
   }
   /* argument order in the reference: routes are listed first, the profile is drawn (:992),
    * then the route (:997) */
-  out->profile = select_profile(r);
-  out->route = random_route_at(r, x, y);
+  out->profile = select_profile(r, slot, CW_PROFILE);
+  out->route = random_route_at(r, x, y, slot, CW_SPAWN_ROUTE);
   out->id = e->next_car_id++;
   out->x = x; out->y = y; out->patience = 0; out->delay = 0;
 }
 
-static int should_car_move(rctx* r, ora_car* c) {
+static int should_car_move(rctx* r, ora_car* c, int slot) {
   /* _should_car_move (environment.py:678-691) */
   const pgtg_config* cfg = &r->b->cfg;
   if (c->delay > 0) { c->delay--; return 0; }
-  if (rng_double(r, PGTG_STREAM_CAR) < cfg->drv_reaction_delay[c->profile]) {
-    c->delay = 1 + rng_index(r, PGTG_STREAM_CAR, 3); /* integers(1, 4) */
+  if (rng_car_double(r, slot, CW_DELAY) < cfg->drv_reaction_delay[c->profile]) {
+    c->delay = 1 + rng_car_index(r, slot, CW_IDX, 3); /* integers(1, 4) */
     return 0;
   }
-  return rng_double(r, PGTG_STREAM_CAR) < cfg->drv_speed_multiplier[c->profile];
+  return rng_car_double(r, slot, CW_SPEED) < cfg->drv_speed_multiplier[c->profile];
 }
 
 /* returns 0 = despawn (None), 1 = (position, route) written back into the car */
-static int next_car_position_and_route(rctx* r, ora_car* c) {
+static int next_car_position_and_route(rctx* r, ora_car* c, int slot) {
   /* _get_next_car_position_and_route (environment.py:881-968) */
   ora_env* e = r->e;
   const pgtg_config* cfg = &r->b->cfg;
-  if (!should_car_move(r, c)) { c->patience++; return 1; }
+  if (!should_car_move(r, c, slot)) { c->patience++; return 1; }
   static const int DX[4] = {0, 0, -1, 1}, DY[4] = {-1, 1, 0, 0}; /* up, down, left, right */
   for (int d = 0; d < 4; d++) {
     int px = c->x + DX[d], py = c->y + DY[d];
@@ -669,7 +721,7 @@ static int next_car_position_and_route(rctx* r, ora_car* c) {
     if (!(feat_at(e, px, py) & F_LANE)) continue;
     if (l->all && l->all - 1 == d) { /* :915-928 */
       c->patience = 0;
-      int route = l->route[rng_index(r, PGTG_STREAM_CAR, l->n)];
+      int route = l->route[rng_car_index(r, slot, CW_IDX, l->n)];
       c->x = px; c->y = py; c->route = route;
       return 1;
     }
@@ -679,15 +731,15 @@ static int next_car_position_and_route(rctx* r, ora_car* c) {
         int phase = light_phase(cfg, e->light_counter);
         int stop;
         if (phase == 0) stop = 0;
-        else if (phase == 1) stop = rng_double(r, PGTG_STREAM_CAR) < cfg->drv_yellow_stop[c->profile];
-        else stop = rng_double(r, PGTG_STREAM_CAR) >= cfg->drv_red_violation[c->profile];
+        else if (phase == 1) stop = rng_car_double(r, slot, CW_LIGHT) < cfg->drv_yellow_stop[c->profile];
+        else stop = rng_car_double(r, slot, CW_LIGHT) >= cfg->drv_red_violation[c->profile];
         if (stop) { c->patience++; return 1; }
       }
       int blocked = 0; /* :944-948 */
       for (int k = 0; k < e->n_cars; k++) if (e->cars[k].x == px && e->cars[k].y == py) { blocked = 1; break; }
       if (blocked) { /* :950-962 */
         if (cfg->drv_min_following[c->profile] == 0 || (double)c->patience > cfg->drv_patience_threshold[c->profile]) {
-          if (rng_double(r, PGTG_STREAM_CAR) < cfg->drv_push_probability[c->profile]) {
+          if (rng_car_double(r, slot, CW_PUSH) < cfg->drv_push_probability[c->profile]) {
             c->patience = 0; c->x = px; c->y = py; return 1;
           }
         }
@@ -712,11 +764,11 @@ static void advance_cars(rctx* r) {
     int k = -1;
     for (int j = 0; j < e->n_cars; j++) if (e->cars[j].id == ids[i]) { k = j; break; }
     if (k < 0) continue;
-    if (!next_car_position_and_route(r, &e->cars[k])) {
+    if (!next_car_position_and_route(r, &e->cars[k], i)) {
       for (int j = k; j + 1 < e->n_cars; j++) e->cars[j] = e->cars[j + 1];
       e->n_cars--;
       ora_car nc;
-      spawn_new_car(r, &nc);
+      spawn_new_car(r, &nc, i);
       e->cars[e->n_cars++] = nc;
     }
   }
@@ -863,7 +915,7 @@ static void env_reset(ora_batch* b, ora_env* e) {
   rctx r = {b, e};
   e->episode++;
   e->elapsed = 0;
-  memset(e->draw_k, 0, sizeof e->draw_k); e->blk_stream = -1;
+  memset(e->draw_k, 0, sizeof e->draw_k); e->blk_stream = -1; e->cblk_slot = -2;
   if (b->cfg.rng_mode == PGTG_RNG_NUMPY) for (int s = 0; s < 5; s++) np_seed_child(e, s, 5u * (e->episode - 1u) + (uint32_t)s);
   if (b->cfg.fixed_map) {
     e->W = b->fw; e->H = b->fh;
@@ -896,7 +948,7 @@ static double env_step(ora_batch* b, ora_env* e, int action, double* cost_out) {
   const pgtg_config* c = &b->cfg;
   rctx r = {b, e};
   e->elapsed++;
-  memset(e->draw_k, 0, sizeof e->draw_k); e->blk_stream = -1;
+  memset(e->draw_k, 0, sizeof e->draw_k); e->blk_stream = -1; e->cblk_slot = -2;
   int light_total = c->light_green + c->light_yellow + c->light_red;
   e->light_counter = (e->light_counter + 1) % light_total; /* :1113-1115 */
   int ax = action / 3 - 1, ay = action % 3 - 1;            /* constants.py:6-16 */

@@ -136,7 +136,7 @@ static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   if (c.num_channels < 0 || c.num_channels > PGTG_MAX_CHANNELS) { why = "too many observation planes"; return -1; }
   if (c.sliding && (c.window_k < 0 || c.window_k > 15)) { why = "sliding_observation_window_size must be in 0..15"; return -1; }
   if (c.num_rules < 0 || c.num_rules > PGTG_MAX_RULES) { why = "too many traffic rules"; return -1; }
-  if (c.light_green + c.light_yellow + c.light_red <= 0 || c.light_green + c.light_yellow + c.light_red > 0x7FFF) { why = "traffic light durations out of range"; return -1; }
+  if (c.light_green + c.light_yellow + c.light_red <= 0 || c.light_green + c.light_yellow + c.light_red > 0x3FFF) { why = "traffic light durations out of range"; return -1; }
   if (c.rng_mode != PGTG_RNG_PHILOX && c.rng_mode != PGTG_RNG_TAPE && c.rng_mode != PGTG_RNG_NUMPY) { why = "unknown rng_mode"; return -1; }
   if (c.max_cars > 0xFFFF) { why = "max_cars too large"; return -1; }
   d.N = c.num_envs; d.W = c.map_w; d.H = c.map_h; d.T = c.map_w * c.map_h; d.WS = c.map_w * TILE; d.HS = c.map_h * TILE;
@@ -581,20 +581,21 @@ extern "C" int pgtg_get_state(pgtg_env* e, pgtg_state* s) {
   for (size_t i = 0; i < N; i++) {
     if (s->agent) { s->agent[4 * i] = agent[i].x; s->agent[4 * i + 1] = agent[i].y; s->agent[4 * i + 2] = agent[i].z; s->agent[4 * i + 3] = agent[i].w; }
     if (s->flat_tire) s->flat_tire[i] = (uint8_t)(misc[i] & 1);
-    if (s->light_counter) s->light_counter[i] = (int32_t)((misc[i] >> 1) & 0x7FFF);
+    if (s->light_counter) s->light_counter[i] = (int32_t)misc_light(misc[i]);
     if (s->num_cars) s->num_cars[i] = (int32_t)(misc[i] >> 16);
   }
   if (s->elapsed) { bk_d2h(tmp.data(), p.elapsed, N * 4, nullptr); bk_sync(nullptr); for (size_t i = 0; i < N; i++) s->elapsed[i] = (int32_t)tmp[i]; }
   if (s->cars) {
     size_t MC = (size_t)c.max_cars;
-    std::vector<uint64_t> cars(MC * N);
-    bk_d2h(cars.data(), p.cars, MC * N * 8, nullptr);
+    std::vector<uint64_t> cars(2 * MC * N);
+    bk_d2h(cars.data(), p.cars, 2 * MC * N * 8, nullptr);
     bk_sync(nullptr);
     memset(s->cars, 0, sizeof(int32_t) * N * MC * 7);
     for (size_t i = 0; i < N; i++) {
       size_t n = misc[i] >> 16;
+      const uint64_t* live = cars.data() + (2 * i + misc_half(misc[i])) * MC;
       for (size_t k = 0; k < n && k < MC; k++) {
-        Car car = car_unpack(cars[k * N + i]);
+        Car car = car_unpack(live[k]);
         int32_t* o = s->cars + (i * MC + k) * 7;
         o[0] = (int32_t)car.id; o[1] = car.x; o[2] = car.y; o[3] = car.route; o[4] = car.profile; o[5] = car.patience; o[6] = car.delay;
       }
@@ -645,7 +646,7 @@ extern "C" int pgtg_set_state(pgtg_env* e, const pgtg_state* s) {
   bk_sync(nullptr);
   if (s->flat_tire) for (size_t i = 0; i < N; i++) misc[i] = (misc[i] & ~1u) | (s->flat_tire[i] ? 1u : 0u);
   if (s->cars && s->num_cars) {
-    std::vector<uint64_t> cars(MC * N, 0);
+    std::vector<uint64_t> cars(2 * MC * N, 0);
     std::vector<uint32_t> next_id(N);
     bk_d2h(next_id.data(), p.next_car_id, N * 4, nullptr);
     bk_sync(nullptr);
@@ -655,13 +656,13 @@ extern "C" int pgtg_set_state(pgtg_env* e, const pgtg_state* s) {
       for (size_t k = 0; k < n; k++) {
         const int32_t* o = s->cars + (i * MC + k) * 7;
         Car car; car.id = (unsigned)o[0]; car.x = o[1]; car.y = o[2]; car.route = o[3]; car.profile = o[4]; car.patience = 0; car.delay = 0;
-        cars[k * N + i] = car_pack(car);
+        cars[(2 * i + misc_half(misc[i])) * MC + k] = car_pack(car);
         if (k == n - 1) next_id[i] = (unsigned)o[0] + 1;  // :1340
       }
       misc[i] = (misc[i] & 0xFFFFu) | (uint32_t)n << 16;
       if (n > 0) { e->cars_injected = true; e->dc.lean = 0; }  // cars injected into a no-traffic handle: from now on the general tick
     }
-    bk_h2d(p.cars, cars.data(), MC * N * 8, nullptr);
+    bk_h2d(p.cars, cars.data(), 2 * MC * N * 8, nullptr);
     bk_h2d(p.next_car_id, next_id.data(), N * 4, nullptr);
   }
   bk_h2d(p.misc, misc.data(), N * 4, nullptr);

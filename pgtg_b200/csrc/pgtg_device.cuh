@@ -33,6 +33,8 @@
 #define pg_dadd(a, b) __dadd_rn((a), (b))
 #define pg_ddiv(a, b) __ddiv_rn((a), (b))
 #define pg_atomic_or(p, v) atomicOr((p), (v))
+#define pg_atomic_add(p, v) atomicAdd((p), (v))
+#define pg_atomic_cas(p, o, n) atomicCAS((p), (o), (n))
 #define pg_store_streaming(ptr, v) __stcs((ptr), (v))  /* written once, never re-read by the kernel: evict-first */
 #define pg_prefetch_l2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))  /* fire-and-forget */
 /* 32 bytes with one 256-bit streaming store (sm_100: STG.256); ptr 32-byte aligned */
@@ -57,6 +59,9 @@ static inline uint32_t pg_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((u
 #define pg_dadd(a, b) ((a) + (b))
 #define pg_ddiv(a, b) ((a) / (b))
 #define pg_atomic_or(p, v) (*(p) |= (v))
+static inline uint32_t pg_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline int pg_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline uint32_t pg_atomic_cas(uint32_t* p, uint32_t o, uint32_t n) { uint32_t c = *p; if (c == o) *p = n; return c; }
 #define pg_store_streaming(ptr, v) (*(ptr) = (v))
 #define pg_prefetch_l2(ptr) ((void)(ptr))
 struct short4 { short x, y, z, w; };
@@ -163,7 +168,7 @@ struct PcgState {
 struct DevPtrs {
   // state, SoA
   short4* agent;        // [N] x, y, vx, vy
-  uint32_t* misc;       // [N] flat_tire | light_counter << 1 | n_cars << 16
+  uint32_t* misc;       // [N] flat_tire | light_counter << 1 | live car-list half << 15 | n_cars << 16
   uint32_t* elapsed;    // [N]
   uint32_t* episode;    // [N]
   uint32_t* next_car_id;  // [N]
@@ -176,11 +181,12 @@ struct DevPtrs {
   uint2* regen_list;    // [2][2N]
   uint32_t* regen_count; // [2]
   int parity;           // launch index & 1: this launch appends to queue `parity`
-  uint64_t* cars;       // [2 * max_cars][N], second half = same-tick respawn scratch
+  uint64_t* cars;       // [N][2][max_cars]: two halves per env, misc bit 15 says which one is live (the other is the
+                        // warp-parallel tick's write target / the sequential tick's respawn scratch)
   uint32_t* visited;    // [vis_words][N] or null
   // traffic helpers (allocated when traffic_density > 0)
   uint32_t* occ;        // [occ_words][N] per-tick 2-bit car counters per square (cell x*HS+y), 3 = saturated
-  uint16_t* spawners;   // [spawner_cap][N] car_spawner squares in x-major order (x | y << 8), built at reset
+  uint16_t* spawners;   // [N][spawner_cap] car_spawner squares in x-major order (x | y << 8), built at reset
   uint16_t* spawner_count;  // [N]
   uint64_t* key;        // [N] philox key / numpy entropy (the env's seed)
   PcgState* pcg;        // [4][pcg_stride] numpy mode: car, ice, broken road, sand PCG64 streams
@@ -242,7 +248,7 @@ enum : unsigned { SF_WALL = 1, SF_SUBGOAL = 2, SF_USED = 4, SF_START = 8, SF_FIN
 // CTA may run the reset of a done env after compaction).
 struct EnvRegs {
   int x, y, vx, vy;
-  uint32_t misc;  // flat | light << 1 | ncars << 16
+  uint32_t misc;  // flat | light << 1 | half << 15 | ncars << 16
   uint32_t elapsed, episode, next_car_id, plan;
   uint32_t err;
   int64_t cursor;
@@ -250,10 +256,12 @@ struct EnvRegs {
 };
 constexpr uint32_t EF_TILES_DIRTY = 1, EF_DONE = 2, EF_RESET = 4;
 
-PG_HD int misc_flat(uint32_t m) { return m & 1; }
-PG_HD int misc_light(uint32_t m) { return (m >> 1) & 0x7FFF; }
-PG_HD int misc_ncars(uint32_t m) { return m >> 16; }
-PG_HD uint32_t misc_pack(int flat, int light, int ncars) { return (uint32_t)flat | (uint32_t)light << 1 | (uint32_t)ncars << 16; }
+// misc word: flat tire 0 | traffic-light counter 1-14 | live half of the env's car list 15 | number of cars 16-31
+PG_HOSTDEV int misc_flat(uint32_t m) { return m & 1; }
+PG_HOSTDEV int misc_light(uint32_t m) { return (m >> 1) & 0x3FFF; }
+PG_HOSTDEV int misc_half(uint32_t m) { return (m >> 15) & 1; }
+PG_HOSTDEV int misc_ncars(uint32_t m) { return m >> 16; }
+PG_HOSTDEV uint32_t misc_pack(int flat, int light, int ncars, int half = 0) { return (uint32_t)flat | (uint32_t)light << 1 | (uint32_t)half << 15 | (uint32_t)ncars << 16; }
 
 // ---------------------------------------------------------------------------------------------
 // Random draws (semantic API shared with the oracle, include/pgtg_b200.h):
@@ -338,6 +346,40 @@ PG_HD uint32_t pcg_bounded(PcgState& s, uint32_t rng) {
   return (uint32_t)(m >> 32);
 }
 
+// Philox CAR stream (specification shared with the oracle; the reference's car_rng order is only
+// reproduced in the tape / numpy modes). Every car owns one block sequence per tick, so that its draws do
+// not depend on how many words the cars before it consumed and 32 cars can draw at once:
+//   block b of car slot s at (tick, episode) = philox(counter = (b, tick, episode, STREAM_CAR | (s + 1) << 8), key)
+// with s = the car's index in the list when the tick starts, and FIXED word meanings (CW_*). A car-stream
+// uniform is one word scaled by 2^-32; an index draw is (word * n) >> 32; one-element choices draw nothing.
+// Initial traffic (tick 0 of the episode): car slot j takes lane square perm(j) of the x-major list, perm = a
+// 4-round Feistel permutation of [0, 4^h) keyed by the block of slot -1 (field 0), cycle-walked into [0, n);
+// its profile and route come from words CW0_* of its own block.
+enum { CW_DELAY = 0, CW_SPEED = 1, CW_IDX = 2 /* reaction delay length, or the route drawn on tile entry */, CW_PUSH = 3,
+       CW_LIGHT = 4, CW_SPAWNER = 5, CW_SPAWN_ROUTE = 6, CW_PROFILE = 7, CW0_PROFILE = 0, CW0_ROUTE = 1 };
+PG_HD void philox_car_block(uint64_t key, uint32_t tick, uint32_t episode, int slot, uint32_t blk, uint32_t w[4]) {
+  w[0] = blk; w[1] = tick; w[2] = episode; w[3] = (uint32_t)PGTG_STREAM_CAR | (uint32_t)(slot + 1) << 8;
+  philox4x32_10(w[0], w[1], w[2], w[3], (uint32_t)key, (uint32_t)(key >> 32));
+}
+PG_HD double car_u32_to_uniform(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+PG_HD int feistel_half_bits(int n) { int h = 1; while ((1 << (2 * h)) < n) h++; return h; }
+PG_HD uint32_t feistel_round(uint32_t x, uint32_t k, int h) {
+  uint32_t t = (x + k) * 0x9E3779B1u;
+  t ^= t >> 15; t *= 0x85EBCA6Bu; t ^= t >> 13; t *= 0xC2B2AE35u; t ^= t >> 16;
+  return t >> (32 - h);
+}
+// position of initial car `slot` among n lane squares (n >= 1, slot < n)
+PG_HD int initial_car_position(const uint32_t keys[4], int h, int n, int slot) {
+  uint32_t v = (uint32_t)slot, mask = (1u << h) - 1u;
+  do {
+    uint32_t L = v >> h, R = v & mask;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { uint32_t t = L ^ feistel_round(R, keys[i], h); L = R; R = t; }
+    v = L << h | R;
+  } while (v >= (uint32_t)n);
+  return (int)v;
+}
+
 // Philox word stream (specification shared with the oracle): for a given (stream, tick, episode)
 // the 32-bit words come from consecutive Philox4x32-10 blocks, block b = philox(counter =
 // (b, tick, episode, stream), key = env seed), 4 words per block. An index draw takes ONE word
@@ -397,6 +439,35 @@ struct Rng {
     }
     uint32_t j = pos & 3u;
     return j == 0 ? b0 : j == 1 ? b1 : j == 2 ? b2 : b3;
+  }
+  // ---- car stream (see the CW_* specification above); tape / numpy modes keep the reference's sequential order
+  PG_MEMBER uint32_t car_word(int slot, int pos) {
+    const int tag = 0x100 + slot;
+    const uint32_t b = (uint32_t)pos >> 2;
+    if (cur_stream != tag || cur_block != b) {
+      uint32_t w[4];
+      philox_car_block(p.key[env], e.elapsed, e.episode, slot, b, w);
+      b0 = w[0]; b1 = w[1]; b2 = w[2]; b3 = w[3];
+      cur_stream = tag; cur_block = b;
+    }
+    const int j = pos & 3;
+    return j == 0 ? b0 : j == 1 ? b1 : j == 2 ? b2 : b3;
+  }
+  PG_MEMBER double car_uniform(int slot, int pos) {
+    if (RNG != PGTG_RNG_PHILOX) return uniform(PGTG_STREAM_CAR);
+    return car_u32_to_uniform(car_word(slot, pos));
+  }
+  PG_MEMBER int car_index(int slot, int pos, int n) {
+    if (n <= 1) return 0;
+    if (RNG != PGTG_RNG_PHILOX) return index(PGTG_STREAM_CAR, n);
+    return (int)pg_umulhi(car_word(slot, pos), (uint32_t)n);
+  }
+  PG_MEMBER int car_choice_cdf(int slot, int pos, const double* cdf, int n) {
+    if (RNG != PGTG_RNG_PHILOX) return choice_cdf(PGTG_STREAM_CAR, cdf, n);
+    double u = car_uniform(slot, pos);
+    int i = 0;
+    while (i < n - 1 && cdf[i] <= u) i++;
+    return i;
   }
   PG_MEMBER double tape_next(int stream, int kind) {
     if (e.cursor >= p.tape_end[env]) { e.err |= 1; return 0.0; }

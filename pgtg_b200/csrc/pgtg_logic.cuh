@@ -7,7 +7,8 @@
 
 namespace pgtg {
 
-PG_HD uint64_t& car_slot(const DevCfg& c, const DevPtrs& p, int env, int slot) { return p.cars[(size_t)slot * c.N + env]; }
+// car lists: [env][half][slot]; `half` = misc bit 15 (the live list), the other half is scratch / write target
+PG_HD uint64_t* car_list(const DevCfg& c, const DevPtrs& p, int env, int half) { return p.cars + ((size_t)env * 2 + half) * c.max_cars; }
 
 PG_HD int light_phase(const DevCfg& c, int counter) {  // environment.py:1004-1015: 0 green 1 yellow 2 red
   return counter < c.light_green ? 0 : (counter < c.light_green + c.light_yellow ? 1 : 2);
@@ -56,7 +57,7 @@ PG_HDN void build_spawner_list(const DevCfg& c, const DevPtrs& p, const MapView 
         while (col) {
           int ly = pg_ffs(col) - 1;
           col &= col - 1;
-          if (n < c.spawner_cap) p.spawners[(size_t)n * c.N + env] = (uint16_t)((tx * TILE + lx) | (ty * TILE + ly) << 8);
+          if (n < c.spawner_cap) p.spawners[(size_t)env * c.spawner_cap + n] = (uint16_t)((tx * TILE + lx) | (ty * TILE + ly) << 8);
           n++;
         }
       }
@@ -87,29 +88,28 @@ PG_HD void occ_sub(const DevCfg& c, const DevPtrs& p, int env, int x, int y) {
 // ---------------------------------------------------------------------------------------------
 // traffic (environment.py:658-691, 830-1002, 1121-1127)
 template <int RNG>
-PG_HD int random_route_at(const MapView& m, Rng<RNG>& rng, EnvRegs& e, int x, int y) {
+PG_HD int random_route_at(const MapView& m, Rng<RNG>& rng, EnvRegs& e, int x, int y, int slot, int pos) {
   uint64_t d = lane_desc(m.tile_type_at(x, y), m.local_sq(x, y));
   int n = ld_n(d);
   if (n == 0) { e.err |= 16; return 0; }
-  return ld_route(d, rng.index(PGTG_STREAM_CAR, n));  // sorted route names, car_rng.choice (:861-874)
+  return ld_route(d, rng.car_index(slot, pos, n));  // sorted route names, car_rng.choice (:861-874)
 }
 
-template <int RNG>
-PG_HD bool any_car_at(const DevCfg& c, const DevPtrs& p, int env, unsigned xy, int lo, int hi) {
+PG_HD bool any_car_at(const uint64_t* list, unsigned xy, int lo, int hi) {
   for (int k = lo; k < hi; k++)
-    if (car_xy(car_slot(c, p, env, k)) == xy) return true;
+    if (car_xy(list[k]) == xy) return true;
   return false;
 }
 
 // one car tick; returns false when the car leaves the map (None at environment.py:968)
 template <int RNG>
 PG_HD bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs& e, Rng<RNG>& rng, int env, Car& car,
-                     int r, int w, int n, int s, bool use_occ) {
+                     int r, int w, int n, int s, bool use_occ, const uint64_t* live, const uint64_t* scratch) {
   // _should_car_move (:678-691)
   bool move;
   if (car.delay > 0) { car.delay--; move = false; }
-  else if (rng.uniform(PGTG_STREAM_CAR) < c.drv_reaction_delay[car.profile]) { car.delay = 1 + rng.index(PGTG_STREAM_CAR, 3); move = false; }
-  else move = rng.uniform(PGTG_STREAM_CAR) < c.drv_speed_multiplier[car.profile];
+  else if (rng.car_uniform(r, CW_DELAY) < c.drv_reaction_delay[car.profile]) { car.delay = 1 + rng.car_index(r, CW_IDX, 3); move = false; }
+  else move = rng.car_uniform(r, CW_SPEED) < c.drv_speed_multiplier[car.profile];
   if (!move) { car.patience++; return true; }
 #pragma unroll 1
   for (int d = 0; d < 4; d++) {  // up, down, left, right (:891-902)
@@ -119,7 +119,7 @@ PG_HD bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs
     if (ld == 0) continue;
     if (ld_all(ld) == d + 1) {  // entering a new tile: uniform new route (:915-928)
       car.patience = 0;
-      car.route = ld_route(ld, rng.index(PGTG_STREAM_CAR, ld_n(ld)));
+      car.route = ld_route(ld, rng.car_index(r, CW_IDX, ld_n(ld)));
       car.x = px; car.y = py;
       return true;
     }
@@ -129,8 +129,8 @@ PG_HD bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs
       if (m.light_at(px, py)) {  // :934-942
         int phase = light_phase(c, misc_light(e.misc));
         bool stop = false;
-        if (phase == 1) stop = rng.uniform(PGTG_STREAM_CAR) < c.drv_yellow_stop[car.profile];
-        else if (phase == 2) stop = rng.uniform(PGTG_STREAM_CAR) >= c.drv_red_violation[car.profile];
+        if (phase == 1) stop = rng.car_uniform(r, CW_LIGHT) < c.drv_yellow_stop[car.profile];
+        else if (phase == 2) stop = rng.car_uniform(r, CW_LIGHT) >= c.drv_red_violation[car.profile];
         if (stop) { car.patience++; return true; }
       }
       // cars_on_next_position over the live list: survivors [0,w), not-yet-moved (r,n), and the
@@ -139,11 +139,10 @@ PG_HD bool car_next(const DevCfg& c, const DevPtrs& p, const MapView& m, EnvRegs
       int occ = use_occ ? occ_get(c, p, env, px, py) : 3;
       bool blocked = occ == 1 || occ == 2;
       if (occ == 3)
-        blocked = any_car_at<RNG>(c, p, env, xy, 0, w) || any_car_at<RNG>(c, p, env, xy, r + 1, n) ||
-                  any_car_at<RNG>(c, p, env, xy, c.max_cars, c.max_cars + s);
+        blocked = any_car_at(live, xy, 0, w) || any_car_at(live, xy, r + 1, n) || any_car_at(scratch, xy, 0, s);
       if (blocked) {  // :950-962
         if (c.drv_min_following[car.profile] == 0 || (double)car.patience > c.drv_patience_threshold[car.profile]) {
-          if (rng.uniform(PGTG_STREAM_CAR) < c.drv_push_probability[car.profile]) { car.patience = 0; car.x = px; car.y = py; return true; }
+          if (rng.car_uniform(r, CW_PUSH) < c.drv_push_probability[car.profile]) { car.patience = 0; car.x = px; car.y = py; return true; }
         }
         car.patience++;
         return true;
@@ -170,39 +169,71 @@ PG_HDN TrafficIO advance_cars(const DevCfg& c, const DevPtrs& p, const MapView m
   EnvRegs e = e_in;
   Rng<RNG> rng(p, e, env);
   int n = misc_ncars(e.misc), w = 0, s = 0;
+  uint64_t* live = car_list(c, p, env, misc_half(e.misc));
+  uint64_t* scratch = car_list(c, p, env, misc_half(e.misc) ^ 1);
   const bool use_occ = n >= OCC_MIN_CARS;
   if (use_occ) {  // rebuild the occupancy counters for this tick
     for (int i = 0; i < c.occ_words; i++) p.occ[(size_t)i * c.N + env] = 0;
-    for (int r = 0; r < n; r++) { unsigned xy = car_xy(car_slot(c, p, env, r)); occ_add(c, p, env, (int)(xy & 255), (int)(xy >> 8)); }
+    for (int r = 0; r < n; r++) { unsigned xy = car_xy(live[r]); occ_add(c, p, env, (int)(xy & 255), (int)(xy >> 8)); }
   }
   for (int r = 0; r < n; r++) {
-    Car car = car_unpack(car_slot(c, p, env, r));
+    Car car = car_unpack(live[r]);
     int ox = car.x, oy = car.y;
-    if (car_next<RNG>(c, p, m, e, rng, env, car, r, w, n, s, use_occ)) {
+    if (car_next<RNG>(c, p, m, e, rng, env, car, r, w, n, s, use_occ, live, scratch)) {
       if (use_occ && (car.x != ox || car.y != oy)) { occ_sub(c, p, env, ox, oy); occ_add(c, p, env, car.x, car.y); }
-      car_slot(c, p, env, w++) = car_pack(car);
+      live[w++] = car_pack(car);
     } else {  // _spawn_new_car (:970-1002)
       if (use_occ) occ_sub(c, p, env, ox, oy);
       int sx = 0, sy = 0;
       int ns = p.spawner_count[env];
       if (ns > 0) {
-        unsigned v = p.spawners[(size_t)rng.index(PGTG_STREAM_CAR, ns) * c.N + env];
+        unsigned v = p.spawners[(size_t)env * c.spawner_cap + rng.car_index(r, CW_SPAWNER, ns)];
         sx = (int)(v & 255); sy = (int)(v >> 8);
       }
       if (use_occ) occ_add(c, p, env, sx, sy);
       Car nc;
-      nc.profile = rng.choice_cdf(PGTG_STREAM_CAR, c.profile_cdf, PGTG_NUM_PROFILES);
-      nc.route = random_route_at<RNG>(m, rng, e, sx, sy);
+      nc.profile = rng.car_choice_cdf(r, CW_PROFILE, c.profile_cdf, PGTG_NUM_PROFILES);
+      nc.route = random_route_at<RNG>(m, rng, e, sx, sy, r, CW_SPAWN_ROUTE);
       nc.id = e.next_car_id++;
       nc.x = sx; nc.y = sy; nc.patience = 0; nc.delay = 0;
-      car_slot(c, p, env, c.max_cars + s++) = car_pack(nc);
+      scratch[s++] = car_pack(nc);
     }
   }
-  for (int i = 0; i < s; i++) car_slot(c, p, env, w + i) = car_slot(c, p, env, c.max_cars + i);
+  for (int i = 0; i < s; i++) live[w + i] = scratch[i];
   rng.flush();
   TrafficIO io;
   io.next_car_id = e.next_car_id; io.err = e.err; io.cursor = e.cursor;
   return io;
+}
+
+// lane squares per global column, x-major (traffic_spawnable_positions, map.py:35-38): colpre[X] = number of
+// lane squares in the columns before X; returns their total. colpre has 9 W + 1 entries.
+PG_HD int lane_column_prefix(const DevCfg& c, const MapView& m, uint16_t* colpre) {
+  int ncol = c.W * TILE, num_positions = 0;
+  for (int X = 0; X < ncol; X++) {
+    colpre[X] = (uint16_t)num_positions;
+    int tx = X / TILE, lx = X - tx * TILE;
+    for (int ty = 0; ty < c.H; ty++) num_positions += pg_popc(col9(m.L.lane_any[td_exits(m.tiles[ty * c.W + tx])], lx));
+  }
+  colpre[ncol] = (uint16_t)num_positions;
+  return num_positions;
+}
+// the idx-th lane square of that list
+PG_HD void lane_square_at(const DevCfg& c, const MapView& m, const uint16_t* colpre, int idx, int& x, int& y) {
+  int lo = 0, hi = c.W * TILE;  // last column with colpre[X] <= idx
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)colpre[mid] <= idx) lo = mid; else hi = mid; }
+  int X = lo, tx = X / TILE, lx = X - tx * TILE, rest = idx - colpre[X];
+  x = X; y = 0;
+  for (int ty = 0; ty < c.H; ty++) {
+    uint32_t col = col9(m.L.lane_any[td_exits(m.tiles[ty * c.W + tx])], lx);
+    int cnt = pg_popc(col);
+    if (rest < cnt) { while (rest--) col &= col - 1; y = ty * TILE + pg_ffs(col) - 1; break; }
+    rest -= cnt;
+  }
+}
+PG_HD int initial_car_count(const DevCfg& c, int num_positions) {  // int(len(spawnable) * density) (:833-834)
+  int num_cars = (int)((double)num_positions * c.traffic_density);
+  return num_cars > num_positions ? num_positions : num_cars;
 }
 
 template <int RNG>
@@ -211,73 +242,53 @@ PG_HDN uint32_t create_initial_traffic(const DevCfg& c, const DevPtrs& p, const 
   // _create_initial_traffic (environment.py:830-879). Cold, self-contained unit (registers by value).
   EnvRegs e = e_in;
   Rng<RNG> rng(p, e, env);
-  if (RNG == PGTG_RNG_PHILOX) rng.kcount[PGTG_STREAM_CAR] = car_words;
-  // lane squares per global column, x-major (traffic_spawnable_positions, map.py:35-38)
+  (void)car_words;
   uint16_t colpre[TILE * 16 + 1];
-  int ncol = c.W * TILE, num_positions = 0;
-  for (int X = 0; X < ncol; X++) {
-    colpre[X] = (uint16_t)num_positions;
-    int tx = X / TILE, lx = X - tx * TILE;
-    for (int ty = 0; ty < c.H; ty++) num_positions += pg_popc(col9(m.L.lane_any[td_exits(m.tiles[ty * c.W + tx])], lx));
-  }
-  colpre[ncol] = (uint16_t)num_positions;
-  int num_cars = (int)((double)num_positions * c.traffic_density);
-  if (num_cars > num_positions) num_cars = num_positions;
+  int num_positions = lane_column_prefix(c, m, colpre);
+  int num_cars = initial_car_count(c, num_positions);
   if (num_cars > c.max_cars) { e.err |= 32; num_cars = c.max_cars; }
+  uint64_t* live = car_list(c, p, env, misc_half(e.misc));
   if (num_cars > 0) {
-    // car_rng.choice(n, size=k, replace=False): k distinct indices, kept raw in the car slots first;
-    // Philox mode draws with rejection against a bitmap of the indices already taken (the
-    // occupancy words double as that scratch)
-    if (RNG != PGTG_RNG_TAPE) for (int i = 0; i < (num_positions + 31) / 32; i++) p.occ[(size_t)i * c.N + env] = 0;
+    // car_rng.choice(n, size=k, replace=False): k distinct indices, kept raw in the car slots first
     if (RNG == PGTG_RNG_NUMPY) {
-      // Generator.choice(n, size=k, replace=False): Floyd's sampling (membership via the bitmap,
-      // numpy uses a hash set) followed by the in-place shuffle of the k values
+      // Generator.choice(n, size=k, replace=False): Floyd's sampling (membership via a bitmap in the occupancy
+      // words, numpy uses a hash set) followed by the in-place shuffle of the k values
+      for (int i = 0; i < (num_positions + 31) / 32; i++) p.occ[(size_t)i * c.N + env] = 0;
       for (int t = 0; t < num_cars; t++) {
         uint32_t j = (uint32_t)(num_positions - num_cars + t);
         uint32_t v = rng.np_bounded(PGTG_STREAM_CAR, j);
         uint32_t& wv = p.occ[(size_t)(v >> 5) * c.N + env];
         if ((wv >> (v & 31)) & 1u) { v = j; p.occ[(size_t)(j >> 5) * c.N + env] |= 1u << (j & 31); }
         else wv |= 1u << (v & 31);
-        car_slot(c, p, env, t) = (uint64_t)v;
+        live[t] = (uint64_t)v;
       }
       for (int i = num_cars - 1; i >= 1; i--) {
         int jj = (int)rng.np_bounded(PGTG_STREAM_CAR, (uint32_t)i);
-        uint64_t a = car_slot(c, p, env, i);
-        car_slot(c, p, env, i) = car_slot(c, p, env, jj);
-        car_slot(c, p, env, jj) = a;
+        uint64_t a = live[i];
+        live[i] = live[jj];
+        live[jj] = a;
       }
-    } else
-    for (int j = 0; j < num_cars; j++) {
-      int v;
-      if (RNG == PGTG_RNG_TAPE) {
-        v = (int)rng.tape_next(PGTG_STREAM_CAR, PGTG_DRAW_INDEX);
+    } else if (RNG == PGTG_RNG_TAPE) {
+      for (int j = 0; j < num_cars; j++) {
+        int v = (int)rng.tape_next(PGTG_STREAM_CAR, PGTG_DRAW_INDEX);
         if (v < 0 || v >= num_positions) { e.err |= 4; v = 0; }
-      } else {
-        for (;;) {  // sequential rejection sampling (spec shared with the oracle)
-          v = (int)pg_umulhi(rng.word(PGTG_STREAM_CAR), (uint32_t)num_positions);
-          uint32_t& wd = p.occ[(size_t)(v >> 5) * c.N + env];
-          if (!((wd >> (v & 31)) & 1u)) { wd |= 1u << (v & 31); break; }
-        }
+        live[j] = (uint64_t)(uint32_t)v;
       }
-      car_slot(c, p, env, j) = (uint64_t)(uint32_t)v;
+    } else {  // Philox specification: keyed Feistel permutation of the lane squares (pgtg_device.cuh, CW_*)
+      uint32_t keys[4];
+      philox_car_block(p.key[env], e.elapsed, e.episode, -1, 0, keys);
+      const int h = feistel_half_bits(num_positions);
+      for (int j = 0; j < num_cars; j++) live[j] = (uint64_t)(uint32_t)initial_car_position(keys, h, num_positions, j);
     }
     for (int j = 0; j < num_cars; j++) {
-      int idx = (int)car_slot(c, p, env, j);
-      int lo = 0, hi = ncol;  // last column with colpre[X] <= idx
-      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)colpre[mid] <= idx) lo = mid; else hi = mid; }
-      int X = lo, tx = X / TILE, lx = X - tx * TILE, rest = idx - colpre[X], x = X, y = 0;
-      for (int ty = 0; ty < c.H; ty++) {
-        uint32_t col = col9(m.L.lane_any[td_exits(m.tiles[ty * c.W + tx])], lx);
-        int cnt = pg_popc(col);
-        if (rest < cnt) { while (rest--) col &= col - 1; y = ty * TILE + pg_ffs(col) - 1; break; }
-        rest -= cnt;
-      }
+      int x, y;
+      lane_square_at(c, m, colpre, (int)live[j], x, y);
       Car car;
-      car.profile = rng.choice_cdf(PGTG_STREAM_CAR, c.profile_cdf, PGTG_NUM_PROFILES);
-      car.route = random_route_at<RNG>(m, rng, e, x, y);
+      car.profile = rng.car_choice_cdf(j, CW0_PROFILE, c.profile_cdf, PGTG_NUM_PROFILES);
+      car.route = random_route_at<RNG>(m, rng, e, x, y, j, CW0_ROUTE);
       car.id = e.next_car_id++;
       car.x = x; car.y = y; car.patience = 0; car.delay = 0;
-      car_slot(c, p, env, j) = car_pack(car);
+      live[j] = car_pack(car);
     }
   }
   rng.flush();
@@ -318,15 +329,16 @@ PG_HDN bool apply_braking(const DevCfg& c, const DevPtrs& p, const MapView m, co
     if (type != rule.tile_type) continue;
     if (!(rule.vel_lo <= speed && speed <= rule.vel_hi)) continue;
     int in_tile = 0;
+    const uint64_t* live = car_list(c, p, env, misc_half(e.misc));
     for (int k = 0; k < n; k++) {
-      unsigned xy = car_xy(car_slot(c, p, env, k));
+      unsigned xy = car_xy(live[k]);
       if ((int)(xy & 255) / TILE == tx && (int)(xy >> 8) / TILE == ty) in_tile++;
     }
     if (in_tile < rule.min_traffic) continue;
     if (adir < 0) adir = agent_direction(c, p, m, e);
     int matching = 0;
     for (int k = 0; k < n; k++) {
-      uint64_t cv = car_slot(c, p, env, k);
+      uint64_t cv = live[k];
       unsigned xy = car_xy(cv);
       if ((int)(xy & 255) / TILE == tx && (int)(xy >> 8) / TILE == ty) matching += rule.weight[adir][(cv >> 16) & 31];
     }
@@ -363,7 +375,7 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
   e.elapsed++;
   int light = misc_light(e.misc) + 1;  // :1113-1115; the counter is below the period except after an arbitrary set_state
   if (light >= c.light_total) light = light == c.light_total ? 0 : light % c.light_total;
-  e.misc = misc_pack(misc_flat(e.misc), light, misc_ncars(e.misc));
+  e.misc = misc_pack(misc_flat(e.misc), light, misc_ncars(e.misc), misc_half(e.misc));
   int ax = action / 3 - 1, ay = action % 3 - 1;  // constants.py:6-16
   const int n_cars = LEAN ? 0 : misc_ncars(e.misc);
   if (n_cars > 0) {  // :1121-1127
@@ -406,7 +418,7 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
     if (!crash && !c.ignore_traffic_collisions && n_cars > 0) {
       int occ = n_cars >= OCC_MIN_CARS ? occ_get(c, p, env, cx, cy) : 3;
       crash = occ == 1 || occ == 2;
-      if (occ == 3) crash = any_car_at<RNG>(c, p, env, (unsigned)cx | (unsigned)cy << 8, 0, n_cars);
+      if (occ == 3) crash = any_car_at(car_list(c, p, env, misc_half(e.misc)), (unsigned)cx | (unsigned)cy << 8, 0, n_cars);
     }
     if (crash) {
       if (split_cost) r.cost += c.crash_penalty; else r.reward -= c.crash_penalty;
@@ -442,7 +454,7 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
     cx += sx; cy += sy;  // :1236
   }
   if (flat) { e.vx = 0; e.vy = 0; }  // :1240-1241
-  e.misc = misc_pack(flat, light, misc_ncars(e.misc));
+  e.misc = misc_pack(flat, light, misc_ncars(e.misc), misc_half(e.misc));
   if (!LEAN && c.vis_words) {  // :1244-1255
     bool was = visited_test_set(c, p, env, cx, cy, true);
     if (was && !(ax == 0 && ay == 0)) {
@@ -872,7 +884,7 @@ PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
     build_spawner_list(c, p, m, env);
     int64_t cur; uint32_t err;
     uint32_t r = create_initial_traffic<RNG>(c, p, m, e, env, rng.kcount[PGTG_STREAM_CAR], &cur, &err);
-    e.misc = misc_pack(misc_flat(e.misc), misc_light(e.misc), (int)(r & 0xFFFFu));
+    e.misc = misc_pack(misc_flat(e.misc), misc_light(e.misc), (int)(r & 0xFFFFu), misc_half(e.misc));
     e.next_car_id = r >> 16; e.cursor = cur; e.err |= err;
   }
 }
@@ -964,6 +976,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
   int tx = pix / TILE, ty = piy / TILE;
   int phase = light_phase(c, misc_light(e.misc));
   const int ncars = LEAN ? 0 : misc_ncars(e.misc);
+  const uint64_t* live = LEAN ? nullptr : car_list(c, p, env, misc_half(e.misc));
   int PP = c.P * c.P;
   if (LEAN || (!c.sliding && c.obs_fast)) {
     // Fixed window, kind by kind: a tile has walls, at most ONE obstacle / light plane, goal-ish
@@ -999,7 +1012,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
     if (!LEAN && ncars && (ch = c.kind_channel[PGTG_CH_TRAFFIC]) >= 0) {  // :1397-1409
       uint32_t w[3] = {0u, 0u, 0u};
       for (int k = 0; k < ncars; k++) {
-        unsigned xy = car_xy(car_slot(c, p, env, k));
+        unsigned xy = car_xy(live[k]);
         int lx = (int)(xy & 255) - tx * TILE, ly = (int)(xy >> 8) - ty * TILE;
         if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE) or_bit81(w, lx * TILE + ly);
       }
@@ -1021,7 +1034,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
       if (kind == PGTG_CH_TRAFFIC) {  // :1397-1409
         w[0] = w[1] = w[2] = 0;
         for (int k = 0; k < ncars; k++) {
-          unsigned xy = car_xy(car_slot(c, p, env, k));
+          unsigned xy = car_xy(live[k]);
           int lx = (int)(xy & 255) - tx * TILE, ly = (int)(xy >> 8) - ty * TILE;
           if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE) or_bit81(w, lx * TILE + ly);
         }
@@ -1039,7 +1052,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
       uint32_t off = base + ch * PP;
       if (kind == PGTG_CH_TRAFFIC) {
         for (int q = 0; q < ncars; q++) {
-          unsigned xy = car_xy(car_slot(c, p, env, q));
+          unsigned xy = car_xy(live[q]);
           int ix = (int)(xy & 255) - x0, iy = (int)(xy >> 8) - y0;
           if (ix >= 0 && ix < c.P && iy >= 0 && iy < c.P) emit_bits(bits, off + ix * c.P + iy, 1u);
         }
