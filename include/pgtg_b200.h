@@ -276,6 +276,8 @@ int pgtg_set_overlap(pgtg_env* env, int on);
 int pgtg_timing(pgtg_env* env, double* tick_ms, double* mapgen_ms, int* steps);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t pgtg_launch_count(pgtg_env* env);
+/* Which kernel instantiations a step of this handle launches, as text ("tick=traffic(G=32,NT=256) ..."). */
+int pgtg_kernel_info(pgtg_env* env, char* out, int out_bytes);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,7 @@ EXPORTS = {
     "pgtg_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgtg_reset_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgtg_launch_count": (C.c_int64, [C.c_void_p]),
+    "pgtg_kernel_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "pgtg_flatten": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "pgtg_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "pgtg_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),

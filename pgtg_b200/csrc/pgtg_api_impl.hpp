@@ -18,6 +18,7 @@
 //   void* bk_event_create();  void bk_event_destroy(void*);  int bk_event_record(void* ev, void* stream);
 //   double bk_event_elapsed(void* a, void* b);
 //   int bk_stats_reduce(pgtg_env*, void* stream);  int bk_stats_reset(pgtg_env*, void* stream);
+//   void bk_traffic_geometry(const DevCfg&, int* G, int* NT);   (G = 0: the traffic tick cannot run this configuration)
 #pragma once
 #include <math.h>
 #include <stdio.h>
@@ -225,6 +226,10 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   if (bk_pick_block(e->dc, &e->block, &e->smem)) { delete e; return fail(PGTG_ERR_INVALID, "observation window too large for shared memory"); }
   e->nblk = (dc.N + e->block - 1) / e->block;
   e->stats_rows = nullptr;
+  e->traffic_G = e->traffic_NT = 0;
+  if (cfg->rng_mode == PGTG_RNG_PHILOX && cfg->traffic_density > 0 && !getenv("PGTG_NO_TRAFFIC_KERNEL")) bk_traffic_geometry(e->dc, &e->traffic_G, &e->traffic_NT);
+  e->stats_nrows = e->nblk;
+  if (e->traffic_G > 0 && (dc.N + e->traffic_G - 1) / e->traffic_G > e->stats_nrows) e->stats_nrows = (dc.N + e->traffic_G - 1) / e->traffic_G;
   DevPtrs& p = e->dp;
   size_t N = (size_t)dc.N;
   bool ok = true;
@@ -244,7 +249,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     A(f_obs_map, int8_t, N * dc.obs_bits + 16); A(f_obs_position, int32_t, 2 * N); A(f_obs_velocity, int32_t, 2 * N); A(f_obs_nsd, int32_t, N);
   }
   A(stats, double, 8);
-  ok = ok && ((e->stats_rows = dev_alloc<double>(e, 8 * (size_t)e->nblk)) != nullptr);
+  ok = ok && ((e->stats_rows = dev_alloc<double>(e, 8 * (size_t)e->stats_nrows)) != nullptr);
   ok = ok && ((e->mask_dev = dev_alloc<uint8_t>(e, N)) != nullptr);
   ok = ok && ((e->seeds_dev = dev_alloc<int64_t>(e, N)) != nullptr);
   ok = ok && ((e->actions_dev = dev_alloc<int32_t>(e, N)) != nullptr);
@@ -724,6 +729,16 @@ extern "C" int pgtg_flatten(pgtg_env* e, const int32_t* plane_order, void* strea
 }
 
 extern "C" int64_t pgtg_launch_count(pgtg_env* e) { return e ? e->launches : 0; }
+
+// Which kernels a step of this handle launches, as text (bench / test reports).
+extern "C" int pgtg_kernel_info(pgtg_env* e, char* out, int out_bytes) {
+  if (!e || !out || out_bytes < 1) return fail(PGTG_ERR_INVALID, "null argument");
+  const char* rng = e->cfg.rng_mode == PGTG_RNG_TAPE ? "tape" : e->cfg.rng_mode == PGTG_RNG_NUMPY ? "numpy" : "philox";
+  if (e->traffic_G > 0) snprintf(out, (size_t)out_bytes, "tick=traffic(G=%d,NT=%d) mapgen=%s rng=%s", e->traffic_G, e->traffic_NT, e->dc.pregen ? (e->dc.conn_bits && e->dc.path_tab ? "tabled" : "general") : "none", rng);
+  else snprintf(out, (size_t)out_bytes, "tick=%s(B=%d) mapgen=%s rng=%s", e->dc.lean && e->dc.pregen && e->cfg.rng_mode != PGTG_RNG_TAPE ? "lean" : "general", e->block,
+                e->dc.pregen ? (e->dc.conn_bits && e->dc.path_tab ? "tabled" : "general") : "in-tick", rng);
+  return PGTG_OK;
+}
 
 // Per-kernel device timing: while enabled, pgtg_step brackets each of its kernels with CUDA events on
 // the launching stream (up to max_steps ticks). pgtg_timing synchronises and returns the summed

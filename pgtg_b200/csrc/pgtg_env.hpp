@@ -26,6 +26,8 @@ struct pgtg_env {
   bool have_fixed, have_tape, did_reset;
   bool cars_injected;   // pgtg_set_state put cars into the handle: the lean tick is off for good
   int nblk;             // CTAs per launch
+  int stats_nrows;      // rows of stats_rows (one per CTA of the kernel with the most CTAs)
+  int traffic_G, traffic_NT;  // geometry of the traffic tick (pgtg_traffic.cu); G = 0: not used for this handle
   // pregen pipeline: the persistent map-generation kernel runs on a side stream and overlaps the next tick
   void* side_stream; void* ev_tick; void* ev_map[2];
   uint64_t launch_index;

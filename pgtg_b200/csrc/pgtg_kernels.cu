@@ -57,6 +57,8 @@ static int bk_flatten(pgtg_env*, void* stream);
 static int bk_conn_table_max_bits() { return 24; }
 static int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
 static int bk_build_path_table(pgtg_env*, uint64_t* table_dev);
+int pgtg_traffic_geometry(const pgtg::DevCfg& c, int* G, int* NT, size_t* smem);  // pgtg_traffic.cu
+static void bk_traffic_geometry(const pgtg::DevCfg& c, int* G, int* NT) { size_t smem; pgtg_traffic_geometry(c, G, NT, &smem); }
 
 #include "pgtg_api_impl.hpp"
 
@@ -144,7 +146,11 @@ int pgtg_launch_mode_philox(pgtg_env*, int mode, const uint8_t* mask, const int6
 int pgtg_launch_mode_tape(pgtg_env*, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream);
 int pgtg_launch_mode_numpy(pgtg_env*, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream);
 
+int pgtg_launch_traffic_tick(pgtg_env* e, const void* actions, int action_bytes, void* stream);  // pgtg_traffic.cu
+
 static int bk_launch(pgtg_env* e, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void* stream) {
+  // configurations with cars (Philox mode): the traffic tick; reset / observe stay on the general kernel
+  if (mode == MODE_STEP && e->traffic_G > 0) return ck((cudaError_t)pgtg_launch_traffic_tick(e, actions, action_bytes, stream));
   switch (e->cfg.rng_mode) {
     case PGTG_RNG_TAPE: return ck((cudaError_t)pgtg_launch_mode_tape(e, mode, mask, seeds, actions, action_bytes, stream));
     case PGTG_RNG_NUMPY: return ck((cudaError_t)pgtg_launch_mode_numpy(e, mode, mask, seeds, actions, action_bytes, stream));
@@ -163,7 +169,7 @@ extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
 // Sum the per-CTA statistic rows into the 8-double `stats` buffer on the device (the buffer the
 // host all-reduces with NCCL), on `stream`, without synchronising.
 static int bk_stats_reduce(pgtg_env* e, void* stream) {
-  pgtg::pgtg_reduce_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->stats_rows, e->nblk, e->dp.stats);
+  pgtg::pgtg_reduce_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->stats_rows, e->stats_nrows, e->dp.stats);
   e->launches++;
   return ck(cudaGetLastError());
 }
@@ -189,6 +195,6 @@ static int bk_flatten(pgtg_env* e, void* stream) {
   return ck(cudaGetLastError());
 }
 static int bk_stats_reset(pgtg_env* e, void* stream) {
-  if (ck(cudaMemsetAsync(e->stats_rows, 0, sizeof(double) * pgtg::STATS_STRIDE * (size_t)e->nblk, (cudaStream_t)stream))) return -1;
+  if (ck(cudaMemsetAsync(e->stats_rows, 0, sizeof(double) * pgtg::STATS_STRIDE * (size_t)e->stats_nrows, (cudaStream_t)stream))) return -1;
   return ck(cudaMemsetAsync(e->dp.stats, 0, 64, (cudaStream_t)stream));
 }

@@ -363,31 +363,50 @@ PG_HD bool visited_test_set(const DevCfg& c, const DevPtrs& p, int env, int x, i
   return was;
 }
 
+// How the agent's part of the tick sees the traffic. SeqTraffic = the sequential tick: the cars advance inside
+// env_step, "is a car there" scans the list / the global occupancy counters. The warp-parallel traffic tick
+// (pgtg_traffic.cuh) advances the cars beforehand and answers from shared memory (external = true).
+struct SeqTraffic {
+  static constexpr bool external = false;
+  PG_MEMBER bool braking(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, int n_cars) const {
+    return (n_cars > 0 || c.rules_without_traffic) && apply_braking(c, p, m, e, env);  // the default rules need traffic in the agent's tile
+  }
+  PG_MEMBER bool car_at(const DevCfg& c, const DevPtrs& p, const EnvRegs& e, int env, int x, int y, int n_cars) const {
+    int occ = n_cars >= OCC_MIN_CARS ? occ_get(c, p, env, x, y) : 3;
+    if (occ == 3) return any_car_at(car_list(c, p, env, misc_half(e.misc)), (unsigned)x | (unsigned)y << 8, 0, n_cars);
+    return occ != 0;
+  }
+};
+
+// the first lines of PGTGEnv.step: tick counter and traffic-light counter (:1113-1115)
+PG_HD void tick_prologue(const DevCfg& c, EnvRegs& e) {
+  e.elapsed++;
+  int light = misc_light(e.misc) + 1;  // the counter is below the period except after an arbitrary set_state
+  if (light >= c.light_total) light = light == c.light_total ? 0 : light % c.light_total;
+  e.misc = misc_pack(misc_flat(e.misc), light, misc_ncars(e.misc), misc_half(e.misc));
+}
+
 // LEAN = compile-time promise of the plain configuration (no traffic and no rule that can fire
 // without it, fixed window written kind by kind, no next_subgoal_direction / visited penalty /
 // cost split): the corresponding code is not even emitted, which is what keeps the hot kernel small.
-template <int RNG, bool LEAN = false>
-PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env, int action) {
+template <int RNG, bool LEAN = false, class TR = SeqTraffic>
+PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env, int action, const TR tr = TR()) {
   const bool split_cost = LEAN ? false : (bool)c.separate_reward_cost;
   StepResult r;
   r.reward = 0; r.cost = 0; r.terminated = 0; r.braking = 0; r.outcome = 0;
   double perf = 0;
-  e.elapsed++;
-  int light = misc_light(e.misc) + 1;  // :1113-1115; the counter is below the period except after an arbitrary set_state
-  if (light >= c.light_total) light = light == c.light_total ? 0 : light % c.light_total;
-  e.misc = misc_pack(misc_flat(e.misc), light, misc_ncars(e.misc), misc_half(e.misc));
+  if (!TR::external) tick_prologue(c, e);
+  const int light = misc_light(e.misc);
   int ax = action / 3 - 1, ay = action % 3 - 1;  // constants.py:6-16
   const int n_cars = LEAN ? 0 : misc_ncars(e.misc);
-  if (n_cars > 0) {  // :1121-1127
+  if (!TR::external && n_cars > 0) {  // :1121-1127
     TrafficIO io = advance_cars<RNG>(c, p, m, e, env);
     e.next_car_id = io.next_car_id; e.err |= io.err; e.cursor = io.cursor;
   }
   Rng<RNG> rng(p, e, env);  // ice / broken road / sand streams of this tick
   int cx = e.x, cy = e.y;
   e.vx += ax; e.vy += ay;  // :1139
-  if (!LEAN && (n_cars > 0 || c.rules_without_traffic)) {  // :1145 (the default rules need traffic in the agent's tile)
-    if (apply_braking(c, p, m, e, env)) { r.braking = 1; e.vx = 0; e.vy = 0; }
-  }
+  if (!LEAN && tr.braking(c, p, m, e, env, n_cars)) { r.braking = 1; e.vx = 0; e.vy = 0; }  // :1145
 
   // _decompose_velocity (:693-748), produced lazily one unit sub-step at a time; the float64
   // rounding of _round(i * m) is reproduced with explicitly unfused IEEE operations
@@ -415,11 +434,7 @@ PG_HD StepResult env_step(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs
     bool inside = m.inside(cx, cy);
     unsigned f = inside ? m.features(cx, cy) : (unsigned)SF_WALL;
     bool crash = !inside || (f & SF_WALL);
-    if (!crash && !c.ignore_traffic_collisions && n_cars > 0) {
-      int occ = n_cars >= OCC_MIN_CARS ? occ_get(c, p, env, cx, cy) : 3;
-      crash = occ == 1 || occ == 2;
-      if (occ == 3) crash = any_car_at(car_list(c, p, env, misc_half(e.misc)), (unsigned)cx | (unsigned)cy << 8, 0, n_cars);
-    }
+    if (!crash && !c.ignore_traffic_collisions && n_cars > 0) crash = tr.car_at(c, p, e, env, cx, cy, n_cars);
     if (crash) {
       if (split_cost) r.cost += c.crash_penalty; else r.reward -= c.crash_penalty;
       r.terminated = 1; r.outcome = 1;
@@ -863,7 +878,8 @@ PG_HD void build_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
 }
 
 // the rest of PGTGEnv.reset (environment.py:635-656) on a finished map
-template <int RNG, bool LEAN = false>
+// (EXT: the warp-parallel traffic tick creates the spawner list and the initial traffic itself)
+template <int RNG, bool LEAN = false, bool EXT = false>
 PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, Rng<RNG>& rng, int env) {
   e.flags |= EF_TILES_DIRTY | EF_RESET;
   int stile = m.start_tile(), sd = plan_sd(e.plan);
@@ -880,7 +896,7 @@ PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
     visited_test_set(c, p, env, e.x, e.y, true);  // positions_path = [position] (:643)
   }
   if (RNG == PGTG_RNG_NUMPY) rng.np_begin_episode();  // children 5r+1..5r+4 of this reset (:593-599)
-  if (!LEAN && c.traffic_density > 0) {  // :652-653
+  if (!LEAN && !EXT && c.traffic_density > 0) {  // :652-653
     build_spawner_list(c, p, m, env);
     int64_t cur; uint32_t err;
     uint32_t r = create_initial_traffic<RNG>(c, p, m, e, env, rng.kcount[PGTG_STREAM_CAR], &cur, &err);
@@ -890,17 +906,17 @@ PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
 }
 
 // PGTGEnv.reset (environment.py:581-656), map built in place
-template <int RNG, int TMAX>
+template <int RNG, int TMAX, bool EXT = false>
 PG_HD void env_reset(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
   e.episode++;
   e.elapsed = 0;
   Rng<RNG> rng(p, e, env);
   build_map<RNG, TMAX>(c, p, m, e, rng);
-  begin_episode<RNG>(c, p, m, e, rng, env);
+  begin_episode<RNG, false, EXT>(c, p, m, e, rng, env);
 }
 
 // the same with the map taken from the pre-generated "next map" of this env
-template <int RNG, bool LEAN = false>
+template <int RNG, bool LEAN = false, bool EXT = false>
 PG_HD void env_reset_pregenerated(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, int env) {
   e.episode++;
   e.elapsed = 0;
@@ -916,7 +932,7 @@ PG_HD void env_reset_pregenerated(const DevCfg& c, const DevPtrs& p, MapView& m,
   }
   e.plan = p.next_plan[slot * c.N + env];
   m.plan = e.plan;
-  begin_episode<RNG, LEAN>(c, p, m, e, rng, env);
+  begin_episode<RNG, LEAN, EXT>(c, p, m, e, rng, env);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,453 @@
+// pgtg_traffic.cuh -- the traffic tick: phases of the kernel that runs every configuration with cars
+// (Philox mode). Compiled by nvcc into pgtg_traffic.cu and by g++ into tests/emu (phases as loops).
+//
+// The sequential tick (one env per thread, cars in a loop) cannot fill a B200: 10 of 32 lanes active,
+// one wave of warps, every car drawing Philox words inside a divergent loop. Here a CTA owns G envs and
+// switches between two mappings, phase by phase, through shared memory:
+//
+//   flat over cars   every thread takes one (env, car) item of the CTA's G car lists: the per-car work
+//                    that does not depend on other cars -- Philox block, move gating, probe of the four
+//                    neighbour squares in the lane tables, traffic-light decision, push-through draw,
+//                    respawn square / profile / route -- becomes an INTENT word; later the commit of the
+//                    resolved list, the creation of a new episode's cars, and the traffic plane;
+//   one env/thread   what the reference defines sequentially: blocking in list order (a car sees the cars
+//                    before it at their new squares and the ones after it at their old squares,
+//                    environment.py:944-962, 1121-1127), then the agent's move, reward, termination,
+//                    auto-reset and the map planes of the observation. With the intents precomputed this
+//                    pass is a few instructions per car and every lane of the warp has an env.
+//
+// Per-env shared state: tile descriptors, TEnv, intents (4 B / car), 16-bit car squares, optional 4-bit
+// occupancy counters per square (envs with >= TK_OCC_MIN cars), the lane-column prefix of a new map, and
+// the env's slice of the CTA's observation bitstring. Car lists live in HBM as [env][2][max_cars]: the
+// tick reads the live half and writes the other one (order-stable compaction of despawned cars without
+// hazards), then flips misc bit 15.
+#pragma once
+#include "pgtg_phases.cuh"
+
+namespace pgtg {
+
+constexpr int TK_DESPAWN_CAP = 6;
+constexpr int TK_OCC_MIN = 24;  // fewer cars: "is a car there" scans the env's 16-bit square list instead
+
+// intent word: kind 0-1 | target square x 2-9, y 10-17 | route 18-22 | delay 23-24 | push 25 | profile 26-28 | moved 31
+enum : uint32_t { IK_STAY = 0, IK_LANE = 1, IK_ENTER = 2, IK_DESPAWN = 3, IK_PUSH = 1u << 25, IK_MOVED = 1u << 31 };
+PG_HD uint32_t intent_pack(uint32_t kind, int tx, int ty, int route, int delay, bool push, int profile) {
+  return kind | (uint32_t)tx << 2 | (uint32_t)ty << 10 | (uint32_t)route << 18 | (uint32_t)delay << 23 | (push ? IK_PUSH : 0u) | (uint32_t)profile << 26;
+}
+PG_HD unsigned intent_xy(uint32_t w) { return (w >> 2) & 0xFFFFu; }
+PG_HD int intent_route(uint32_t w) { return (int)((w >> 18) & 31u); }
+PG_HD int intent_delay(uint32_t w) { return (int)((w >> 23) & 3u); }
+PG_HD int intent_profile(uint32_t w) { return (int)((w >> 26) & 7u); }
+
+struct TEnv {
+  EnvRegs e;
+  uint64_t key;
+  int32_t action, n_cars;        // cars when the tick starts (constant within an episode)
+  int32_t tile_x, tile_y;        // the agent's tile before its move (rule engine, environment.py:208-224)
+  int32_t in_tile;               // cars in that tile after the traffic advance
+  uint32_t hist[5];              // their routes: 8-bit counter per route id
+  int32_t n_despawn;
+  uint16_t despawn[TK_DESPAWN_CAP];  // list slots of the cars that left the map, ascending
+  int32_t done;                  // StepResult.outcome of this tick
+  int32_t new_cars, num_positions, perm_h;  // initial traffic of the episode that starts in this tick
+  uint32_t perm_keys[4];
+};
+
+struct TkShared {
+  Lut* lut; uint2* spread;
+  uint16_t* tiles;     // [G][tile_stride]
+  TEnv* env;           // [G]
+  uint32_t* intent;    // [G][MC]
+  uint16_t* fxy;       // [G][MC] car squares: old ones until the resolve pass, final ones after it
+  uint32_t* occ;       // [G][occ_words] 4-bit counters per square, 15 = sticky "unknown" (null when MC < TK_OCC_MIN)
+  uint32_t* bits;      // CTA observation bitstring, env g at bit g * obs_bits
+  uint16_t* colpre;    // [G][ncolp]
+  int* off;            // [G + 1] car items of the tick
+  int* off2;           // [G + 1] car items of the episodes that start in this tick
+  int* counters;       // [16]
+  double* dsum;        // [2]
+  int* done_list;      // [G]
+  int bits_words, G, MC, occ_words, ncolp;
+};
+struct TkLayout {
+  uint32_t lut, spread, tiles, env, intent, fxy, occ, bits, colpre, off, off2, counters, dsum, done_list, total;
+  int bits_words, G, MC, occ_words, ncolp;
+};
+PG_HOSTDEV TkLayout tk_layout(const DevCfg& c, int G) {
+  TkLayout L;
+  uint32_t o = 0;
+  auto take = [&](size_t bytes) { uint32_t at = o; o += (uint32_t)align16(bytes); return at; };
+  L.G = G; L.MC = c.max_cars;
+  L.occ_words = c.max_cars >= TK_OCC_MIN ? (c.WS * c.HS + 7) / 8 : 0;
+  L.ncolp = (c.W * TILE + 2) & ~1;
+  L.bits_words = (G * c.obs_bits + 31) / 32 + 4;
+  L.lut = take(sizeof(Lut)); L.spread = take(256 * sizeof(uint2));
+  L.tiles = take(sizeof(uint16_t) * G * c.tile_stride);
+  L.env = take(sizeof(TEnv) * G);
+  L.intent = take(sizeof(uint32_t) * G * L.MC);
+  L.fxy = take(sizeof(uint16_t) * G * L.MC);
+  L.occ = take(sizeof(uint32_t) * G * L.occ_words);
+  L.bits = take(sizeof(uint32_t) * L.bits_words);
+  L.colpre = take(sizeof(uint16_t) * G * L.ncolp);
+  L.off = take(sizeof(int) * (G + 1)); L.off2 = take(sizeof(int) * (G + 1));
+  L.counters = take(sizeof(int) * 16); L.dsum = take(sizeof(double) * 2);
+  L.done_list = take(sizeof(int) * G);
+  L.total = o;
+  return L;
+}
+PG_HOSTDEV TkShared tk_carve(unsigned char* base, const TkLayout& L) {
+  TkShared s;
+  s.lut = (Lut*)(base + L.lut); s.spread = (uint2*)(base + L.spread); s.tiles = (uint16_t*)(base + L.tiles);
+  s.env = (TEnv*)(base + L.env); s.intent = (uint32_t*)(base + L.intent); s.fxy = (uint16_t*)(base + L.fxy);
+  s.occ = L.occ_words ? (uint32_t*)(base + L.occ) : nullptr; s.bits = (uint32_t*)(base + L.bits);
+  s.colpre = (uint16_t*)(base + L.colpre); s.off = (int*)(base + L.off); s.off2 = (int*)(base + L.off2);
+  s.counters = (int*)(base + L.counters); s.dsum = (double*)(base + L.dsum); s.done_list = (int*)(base + L.done_list);
+  s.bits_words = L.bits_words; s.G = L.G; s.MC = L.MC; s.occ_words = L.occ_words; s.ncolp = L.ncolp;
+  return s;
+}
+
+PG_HD MapView tk_map(const DevCfg& c, const TkShared& sh, int g) {
+  MapView m = {c, *sh.lut, sh.tiles + g * c.tile_stride, sh.env[g].e.plan, nullptr, nullptr, nullptr, 0u, false};
+  return m;
+}
+
+// ---- 4-bit occupancy counters (exact below 15; 15 is sticky and means "scan the list") ----------------
+PG_HD int occ4_index(const DevCfg& c, unsigned xy) { return (int)(xy & 255u) * c.HS + (int)(xy >> 8); }
+PG_HD int occ4_get(const uint32_t* o, int i) { return (int)((o[i >> 3] >> ((i & 7) * 4)) & 15u); }
+PG_HD void occ4_inc(uint32_t* o, int i) {
+  const int sh = (i & 7) * 4;
+  if (((o[i >> 3] >> sh) & 15u) < 15u) o[i >> 3] += 1u << sh;
+}
+PG_HD void occ4_dec(uint32_t* o, int i) {
+  const int sh = (i & 7) * 4;
+  const uint32_t v = (o[i >> 3] >> sh) & 15u;
+  if (v >= 1u && v < 15u) o[i >> 3] -= 1u << sh;
+}
+PG_HD void occ4_inc_atomic(uint32_t* o, int i) {
+  const int sh = (i & 7) * 4;
+  uint32_t* w = o + (i >> 3);
+  uint32_t old = *(volatile uint32_t*)w;
+  for (;;) {
+    if (((old >> sh) & 15u) == 15u) return;
+    const uint32_t seen = pg_atomic_cas(w, old, old + (1u << sh));
+    if (seen == old) return;
+    old = seen;
+  }
+}
+PG_HD bool tk_use_occ(const TkShared& sh, int n_cars) { return sh.occ_words != 0 && n_cars >= TK_OCC_MIN; }
+PG_HD bool tk_scan(const uint16_t* fx, int n, unsigned xy) {
+  for (int j = 0; j < n; j++)
+    if (fx[j] == xy) return true;
+  return false;
+}
+
+// ---- stage: one env per thread ----------------------------------------------------------------------
+PG_HD void tk_stage_env(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env, int action) {
+  TEnv& t = sh.env[g];
+  EnvRegs e = load_regs(c, p, env);
+  if (c.pregen) {  // the env's next map, should the episode end in this tick
+    const size_t slot = (e.episode + 1u) & 1u;
+    pg_prefetch_l2(p.next_tiles + (slot * c.N + (size_t)env) * c.T);
+    pg_prefetch_l2(p.next_plan + slot * c.N + env);
+  }
+  if ((unsigned)action > 8u) { e.err |= 128; action = 4; }  // the reference would raise KeyError
+  tick_prologue(c, e);
+  t.e = e;
+  t.key = p.key[env];
+  t.action = action;
+  t.n_cars = misc_ncars(e.misc);
+  int tx = floordiv9(e.x), ty = floordiv9(e.y);
+  t.tile_x = tx < 0 ? 0 : (tx > c.W - 1 ? c.W - 1 : tx);
+  t.tile_y = ty < 0 ? 0 : (ty > c.H - 1 ? c.H - 1 : ty);
+  t.in_tile = 0; t.n_despawn = 0; t.done = 0; t.new_cars = 0; t.num_positions = 0; t.perm_h = 1;
+#pragma unroll
+  for (int i = 0; i < 5; i++) t.hist[i] = 0;
+}
+// exclusive prefix of a per-env count (thread g sums the envs before it; G <= 128)
+PG_HD void tk_prefix(const TkShared& sh, int* off, int g, int nvalid, bool new_cars) {
+  int s = 0;
+  for (int j = 0; j < g; j++) s += new_cars ? sh.env[j].new_cars : sh.env[j].n_cars;
+  off[g] = s;
+  if (g == nvalid - 1) {
+    s += new_cars ? sh.env[g].new_cars : sh.env[g].n_cars;
+    for (int j = nvalid; j <= sh.G; j++) off[j] = s;
+  }
+}
+// item -> env of the CTA: last g with off[g] <= item
+PG_HD int tk_item_env(const int* off, int G, int item) {
+  int lo = 0, hi = G;
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= item) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// ---- intents: one car per thread (_get_next_car_position_and_route, environment.py:881-968) -----------
+PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int r, int env) {
+  TEnv& t = sh.env[g];
+  const EnvRegs& e = t.e;
+  const MapView m = tk_map(c, sh, g);
+  const uint64_t rec = car_list(c, p, env, misc_half(e.misc))[r];
+  const Car car = car_unpack(rec);
+  const unsigned xy_old = car_xy(rec);
+  sh.fxy[g * sh.MC + r] = (uint16_t)xy_old;
+  if (tk_use_occ(sh, t.n_cars)) occ4_inc_atomic(sh.occ + g * sh.occ_words, occ4_index(c, xy_old));
+  // _should_car_move (:678-691)
+  uint32_t w0[4] = {0u, 0u, 0u, 0u}, w1[4];
+  bool have1 = false, move = false;
+  int delay = car.delay;
+  if (delay > 0) delay--;
+  else {
+    philox_car_block(t.key, e.elapsed, e.episode, r, 0, w0);
+    if (car_u32_to_uniform(w0[CW_DELAY]) < c.drv_reaction_delay[car.profile]) delay = 1 + (int)pg_umulhi(w0[CW_IDX], 3u);
+    else move = car_u32_to_uniform(w0[CW_SPEED]) < c.drv_speed_multiplier[car.profile];
+  }
+  uint32_t word = intent_pack(IK_STAY, 0, 0, car.route, delay, false, car.profile);
+  if (move) {
+    bool found = false;
+#pragma unroll 1
+    for (int d = 0; d < 4 && !found; d++) {  // up, down, left, right (:891-902)
+      const int px = car.x + (d == 2 ? -1 : d == 3 ? 1 : 0), py = car.y + (d == 0 ? -1 : d == 1 ? 1 : 0);
+      if (!m.inside(px, py)) continue;
+      const uint64_t ld = lane_desc(m.tile_type_at(px, py), m.local_sq(px, py));
+      if (ld == 0) continue;
+      if (ld_all(ld) == d + 1) {  // entering a new tile: uniform new route, never blocked (:915-928)
+        const int n = ld_n(ld);
+        word = intent_pack(IK_ENTER, px, py, ld_route(ld, n > 1 ? (int)pg_umulhi(w0[CW_IDX], (uint32_t)n) : 0), delay, false, car.profile);
+        found = true;
+        break;
+      }
+      const int nl = ld_n(ld);
+      for (int i = 0; i < nl; i++) {
+        if (ld_route(ld, i) != car.route || ld_dir(ld, i) != d) continue;  // :932
+        found = true;
+        bool stop = false;
+        if (m.light_at(px, py)) {  // :934-942
+          const int phase = light_phase(c, misc_light(e.misc));
+          if (phase != 0) {
+            philox_car_block(t.key, e.elapsed, e.episode, r, 1, w1);
+            have1 = true;
+            const double u = car_u32_to_uniform(w1[CW_LIGHT & 3]);
+            stop = phase == 1 ? u < c.drv_yellow_stop[car.profile] : u >= c.drv_red_violation[car.profile];
+          }
+        }
+        if (!stop) {
+          const bool impatient = c.drv_min_following[car.profile] == 0 || (double)car.patience > c.drv_patience_threshold[car.profile];
+          const bool push = impatient && car_u32_to_uniform(w0[CW_PUSH]) < c.drv_push_probability[car.profile];  // :950-958
+          word = intent_pack(IK_LANE, px, py, car.route, delay, push, car.profile);
+        }
+        break;
+      }
+    }
+    if (!found) {  // leaves the map; its replacement (_spawn_new_car, :970-1002) is appended to the list
+      if (!have1) philox_car_block(t.key, e.elapsed, e.episode, r, 1, w1);
+      int sx = 0, sy = 0;
+      const int ns = p.spawner_count[env];
+      if (ns > 0) {
+        const unsigned v = p.spawners[(size_t)env * c.spawner_cap + (ns > 1 ? (int)pg_umulhi(w1[CW_SPAWNER & 3], (uint32_t)ns) : 0)];
+        sx = (int)(v & 255u); sy = (int)(v >> 8);
+      }
+      const double u = car_u32_to_uniform(w1[CW_PROFILE & 3]);
+      int prof = 0;
+      while (prof < PGTG_NUM_PROFILES - 1 && c.profile_cdf[prof] <= u) prof++;
+      const uint64_t sd = lane_desc(m.tile_type_at(sx, sy), m.local_sq(sx, sy));
+      const int n = ld_n(sd);
+      int route = 0;
+      if (n == 0) pg_atomic_or(&t.e.err, 16u);
+      else route = ld_route(sd, n > 1 ? (int)pg_umulhi(w1[CW_SPAWN_ROUTE & 3], (uint32_t)n) : 0);
+      word = intent_pack(IK_DESPAWN, sx, sy, route, 0, false, prof);
+    }
+  }
+  sh.intent[g * sh.MC + r] = word;
+}
+
+// ---- resolve: one env per thread, cars in list order (environment.py:944-965, 1121-1127) -------------------
+PG_HD void tk_resolve(const DevCfg& c, const TkShared& sh, int g) {
+  TEnv& t = sh.env[g];
+  const int n = t.n_cars;
+  uint32_t* it = sh.intent + g * sh.MC;
+  uint16_t* fx = sh.fxy + g * sh.MC;
+  const bool use_occ = tk_use_occ(sh, n);
+  uint32_t* occ = use_occ ? sh.occ + g * sh.occ_words : nullptr;
+  int nd = 0;
+  for (int r = 0; r < n; r++) {
+    const uint32_t w = it[r];
+    const uint32_t kind = w & 3u;
+    if (kind == IK_STAY) continue;
+    const unsigned T = intent_xy(w);
+    if (kind == IK_LANE) {
+      // cars_on_next_position over the live list: earlier cars (and replacements) at their new squares, later
+      // ones at their old squares -- exactly what fx holds at this point
+      bool blocked;
+      if (use_occ) {
+        const int v = occ4_get(occ, occ4_index(c, T));
+        blocked = v == 15 ? tk_scan(fx, n, T) : v != 0;
+      } else blocked = tk_scan(fx, n, T);
+      if (blocked && !(w & IK_PUSH)) continue;
+      it[r] = w | IK_MOVED;
+    } else if (kind == IK_DESPAWN) {
+      if (nd < TK_DESPAWN_CAP) t.despawn[nd] = (uint16_t)r;
+      nd++;
+    }
+    if (use_occ) { occ4_dec(occ, occ4_index(c, fx[r])); occ4_inc(occ, occ4_index(c, T)); }
+    fx[r] = (uint16_t)T;
+  }
+  t.n_despawn = nd;
+}
+
+// ---- commit: one car per thread; live half -> other half, order-stable ------------------------------------------
+PG_HD void tk_commit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int r, int env) {
+  TEnv& t = sh.env[g];
+  const uint32_t* it = sh.intent + g * sh.MC;
+  const uint32_t w = it[r];
+  const uint32_t kind = w & 3u;
+  const int half = misc_half(t.e.misc), n = t.n_cars, nd = t.n_despawn;
+  Car car = car_unpack(car_list(c, p, env, half)[r]);
+  int before = 0;  // cars ahead of r that left the map
+  if (nd <= TK_DESPAWN_CAP) { for (int k = 0; k < nd; k++) before += t.despawn[k] < r; }
+  else { for (int j = 0; j < r; j++) before += (it[j] & 3u) == IK_DESPAWN; }
+  const unsigned fxy = sh.fxy[g * sh.MC + r];
+  int slot;
+  if (kind == IK_DESPAWN) {
+    slot = n - nd + before;
+    car.id = t.e.next_car_id + (unsigned)before;
+    car.route = intent_route(w); car.profile = intent_profile(w); car.patience = 0; car.delay = 0;
+  } else {
+    slot = r - before;
+    car.delay = intent_delay(w);
+    if (kind == IK_ENTER || (w & IK_MOVED)) { car.patience = 0; car.route = intent_route(w); }
+    else car.patience++;
+  }
+  car.x = (int)(fxy & 255u); car.y = (int)(fxy >> 8);
+  car_list(c, p, env, half ^ 1)[slot] = car_pack(car);
+  if (c.num_rules > 0 && n <= 255 && car.x / TILE == t.tile_x && car.y / TILE == t.tile_y) {
+    pg_atomic_add(&t.in_tile, 1);
+    pg_atomic_add(&t.hist[car.route >> 2], 1u << (8 * (car.route & 3)));
+  }
+}
+
+// ---- the agent's part of the tick: one env per thread -----------------------------------------------------
+struct ExtTraffic {
+  static constexpr bool external = true;
+  const TkShared* sh;
+  int g;
+  PG_MEMBER bool braking(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, int n_cars) const {
+    // apply_braking / evaluate_rule (environment.py:226-294) on the counters the commit phase collected
+    if (c.num_rules == 0 || !(n_cars > 0 || c.rules_without_traffic)) return false;
+    if (n_cars > 255) return apply_braking(c, p, m, e, env);  // 8-bit route counters: fall back to the list scan
+    const TEnv& t = sh->env[g];
+    const int type = td_exits(m.tiles[t.tile_y * c.W + t.tile_x]);
+    const double speed = sqrt((double)(e.vx * e.vx + e.vy * e.vy));
+    int adir = -1;
+    for (int i = 0; i < c.num_rules; i++) {
+      const pgtg_rule& rule = p.rules[i];
+      if (type != rule.tile_type) continue;
+      if (!(rule.vel_lo <= speed && speed <= rule.vel_hi)) continue;
+      if (t.in_tile < rule.min_traffic) continue;
+      if (adir < 0) adir = agent_direction(c, p, m, e);
+      int matching = 0;
+      for (int q = 0; q < PGTG_NUM_ROUTE_IDS; q++) matching += (int)((t.hist[q >> 2] >> (8 * (q & 3))) & 255u) * rule.weight[adir][q];
+      if (matching >= rule.min_matching_traffic) return true;
+    }
+    return false;
+  }
+  PG_MEMBER bool car_at(const DevCfg& c, const DevPtrs&, const EnvRegs&, int, int x, int y, int n_cars) const {
+    const unsigned xy = (unsigned)x | (unsigned)y << 8;
+    const uint16_t* fx = sh->fxy + g * sh->MC;
+    if (tk_use_occ(*sh, n_cars)) {
+      const int v = occ4_get(sh->occ + g * sh->occ_words, occ4_index(c, xy));
+      return v == 15 ? tk_scan(fx, n_cars, xy) : v != 0;
+    }
+    return tk_scan(fx, n_cars, xy);
+  }
+};
+
+PG_HD StepResult tk_agent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env) {
+  TEnv& t = sh.env[g];
+  EnvRegs& e = t.e;
+  e.next_car_id += (uint32_t)t.n_despawn;
+  e.misc ^= 1u << 15;  // the commit phase wrote the other half: it is the live list now
+  MapView m = tk_map(c, sh, g);
+  ExtTraffic tr = {&sh, g};
+  StepResult r = env_step<PGTG_RNG_PHILOX, false, ExtTraffic>(c, p, m, e, env, t.action, tr);
+  write_step_outputs<false>(c, p, env, e, r);
+  t.done = r.outcome;
+  return r;
+}
+
+// ---- observation ---------------------------------------------------------------------------------------
+// the traffic plane bit of one car (environment.py:1397-1409) in the observation of an agent at (ex, ey)
+PG_HD void tk_car_bit(const DevCfg& c, uint32_t* bits, uint32_t base, int ex, int ey, unsigned xy) {
+  const int ch = c.kind_channel[PGTG_CH_TRAFFIC];
+  if (ch < 0) return;
+  const int cx = (int)(xy & 255u), cy = (int)(xy >> 8);
+  if (!c.sliding) {
+    const int pix = ex < 0 ? 0 : (ex > c.WS - 1 ? c.WS - 1 : ex), piy = ey < 0 ? 0 : (ey > c.HS - 1 ? c.HS - 1 : ey);
+    const int lx = cx - (pix / TILE) * TILE, ly = cy - (piy / TILE) * TILE;
+    if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE) emit_bits(bits, base + (uint32_t)(ch * 81 + lx * TILE + ly), 1u);
+  } else {
+    const int ix = cx - (ex - c.window_k), iy = cy - (ey - c.window_k);
+    if (ix >= 0 && ix < c.P && iy >= 0 && iy < c.P) emit_bits(bits, base + (uint32_t)(ch * c.P * c.P + ix * c.P + iy), 1u);
+  }
+}
+// map planes + scalars of env g (the traffic plane comes from the car threads); final = terminal observation
+PG_HD void tk_emit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env, bool final_obs) {
+  const TEnv& t = sh.env[g];
+  EnvRegs e = t.e;
+  e.misc &= 0xFFFFu;  // no cars for env_observe's own traffic loop
+  const MapView m = tk_map(c, sh, g);
+  int32_t pos[2], vel[2], nsd;
+  env_observe<false>(c, p, m, e, env, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, pos, vel, &nsd);
+  if (final_obs) {
+    p.f_obs_position[2 * env] = pos[0]; p.f_obs_position[2 * env + 1] = pos[1];
+    p.f_obs_velocity[2 * env] = vel[0]; p.f_obs_velocity[2 * env + 1] = vel[1];
+    if (c.use_nsd) p.f_obs_nsd[env] = nsd;
+    return;
+  }
+  write_obs_scalars_and_state<false>(c, p, sh.tiles + g * c.tile_stride, env, t.e, pos, vel, nsd);
+}
+
+// ---- reset of a finished env: one env per thread (PGTGEnv.reset, environment.py:581-656, minus the cars) ------
+template <int TMAX, bool PREGEN>
+PG_HD void tk_reset(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env) {
+  TEnv& t = sh.env[g];
+  EnvRegs& e = t.e;
+  MapView m = tk_map(c, sh, g);
+  if (PREGEN) env_reset_pregenerated<PGTG_RNG_PHILOX, false, true>(c, p, m, e, env);
+  else env_reset<PGTG_RNG_PHILOX, TMAX, true>(c, p, m, e, env);
+  m.plan = e.plan;
+  build_spawner_list(c, p, m, env);
+  uint16_t* colpre = sh.colpre + g * sh.ncolp;
+  const int np = lane_column_prefix(c, m, colpre);
+  int nc = initial_car_count(c, np);
+  if (nc > c.max_cars) { e.err |= 32; nc = c.max_cars; }
+  t.num_positions = np; t.new_cars = nc;
+  if (nc > 0) {
+    philox_car_block(t.key, e.elapsed, e.episode, -1, 0, t.perm_keys);
+    t.perm_h = feistel_half_bits(np);
+  }
+  e.misc = misc_pack(0, 0, nc, 0);
+  e.next_car_id = (uint32_t)nc;  // ids follow the slots (_create_initial_traffic, :830-879)
+}
+// one car of the new episode per thread
+PG_HD void tk_new_car(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int j, int env) {
+  TEnv& t = sh.env[g];
+  const MapView m = tk_map(c, sh, g);
+  const int idx = initial_car_position(t.perm_keys, t.perm_h, t.num_positions, j);
+  int x, y;
+  lane_square_at(c, m, sh.colpre + g * sh.ncolp, idx, x, y);
+  uint32_t w[4];
+  philox_car_block(t.key, t.e.elapsed, t.e.episode, j, 0, w);
+  const double u = car_u32_to_uniform(w[CW0_PROFILE]);
+  Car car;
+  car.profile = 0;
+  while (car.profile < PGTG_NUM_PROFILES - 1 && c.profile_cdf[car.profile] <= u) car.profile++;
+  const uint64_t d = lane_desc(m.tile_type_at(x, y), m.local_sq(x, y));
+  const int n = ld_n(d);
+  car.route = 0;
+  if (n == 0) pg_atomic_or(&p.error[env], 16u);  // (straight to HBM: the env's own thread may be past its emit)
+  else car.route = ld_route(d, n > 1 ? (int)pg_umulhi(w[CW0_ROUTE], (uint32_t)n) : 0);
+  car.id = (unsigned)j; car.x = x; car.y = y; car.patience = 0; car.delay = 0;
+  car_list(c, p, env, 0)[j] = car_pack(car);
+  tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, (unsigned)x | (unsigned)y << 8);
+}
+
+}  // namespace pgtg

@@ -122,6 +122,11 @@ class RawEnv:
     def launch_count(self) -> int:
         return int(self.lib.pgtg_launch_count(self._h))
 
+    def kernel_info(self) -> str:
+        buf = C.create_string_buffer(256)
+        _lib.check(self.lib, self.lib.pgtg_kernel_info(self._h, buf, 256))
+        return buf.value.decode()
+
     def dlpack_capsule(self, name: str):
         """-> a PyCapsule named "dltensor" for `torch.from_dlpack` / any DLPack consumer."""
         mt = C.c_void_p()

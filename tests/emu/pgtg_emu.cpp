@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "../../pgtg_b200/csrc/pgtg_phases.cuh"
+#include "../../pgtg_b200/csrc/pgtg_traffic.cuh"
 
 struct pgtg_env;
 static void* bk_alloc(size_t n) { void* p = nullptr; if (posix_memalign(&p, 256, n)) return nullptr; return p; }
@@ -37,6 +38,7 @@ static int bk_flatten(pgtg_env*, void*);
 static int bk_conn_table_max_bits() { return 13; }  // CPU tests: tables up to 8192 entries (e.g. 3x3 maps)
 static int bk_build_conn_table(pgtg_env*, uint32_t*);
 static int bk_build_path_table(pgtg_env*, uint64_t*);
+static void bk_traffic_geometry(const pgtg::DevCfg&, int* G, int* NT) { *G = 32; *NT = 96; }  // (96 emulated threads: flat loops get several rounds)
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
@@ -119,8 +121,88 @@ static void run_mapgen(pgtg_env* h) {
   free(smem);
 }
 
+// The traffic tick (pgtg_traffic.cu) with its barriers turned into loop boundaries.
+template <int TMAX, bool PREGEN>
+static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes, int blk, unsigned char* smem) {
+  const DevCfg& c = h->dc;
+  const DevPtrs& p = h->dp;
+  const TkLayout L = tk_layout(c, h->traffic_G);
+  const TkShared sh = tk_carve(smem, L);
+  const int G = L.G, NT = h->traffic_NT, env0 = blk * G, nvalid = c.N - env0 < G ? c.N - env0 : G;
+  BlockShared bs;
+  memset(&bs, 0, sizeof bs);
+  bs.lut = sh.lut; bs.spread = sh.spread; bs.tiles = sh.tiles; bs.bits = sh.bits; bs.bits_words = sh.bits_words; bs.done_list = sh.done_list;
+  for (int t = 0; t < NT; t++) phase_stage(c, p, bs, t, NT, env0, nvalid, true, false);
+  for (int i = 0; i < G * sh.occ_words; i++) sh.occ[i] = 0;
+  for (int g = 0; g < nvalid; g++) {
+    int env = env0 + g;
+    int a = action_bytes == 8 ? (int)((const int64_t*)actions)[env] : ((const int32_t*)actions)[env];
+    tk_stage_env(c, p, sh, g, env, a);
+  }
+  for (int g = 0; g < nvalid; g++) tk_prefix(sh, sh.off, g, nvalid, false);
+  const int total = sh.off[G];
+  for (int t = 0; t < NT; t++)
+    for (int item = t; item < total; item += NT) { int g = tk_item_env(sh.off, G, item); tk_intent(c, p, sh, g, item - sh.off[g], env0 + g); }
+  for (int g = 0; g < nvalid; g++) if (sh.env[g].n_cars > 0) tk_resolve(c, sh, g);
+  for (int t = 0; t < NT; t++)
+    for (int item = t; item < total; item += NT) { int g = tk_item_env(sh.off, G, item); tk_commit(c, p, sh, g, item - sh.off[g], env0 + g); }
+  int n_done = 0;
+  double st[8] = {0};
+  for (int g = 0; g < nvalid; g++) {
+    StepResult r = tk_agent(c, p, sh, g, env0 + g);
+    if (r.outcome) {
+      sh.done_list[n_done++] = g;
+      st[0] += 1; st[1] += r.ep_return; st[2] += sh.env[g].e.elapsed;
+      st[3] += r.outcome == 2; st[4] += r.outcome == 1; st[5] += r.outcome == 3;
+      if (PREGEN) {
+        uint2 q; q.x = (uint32_t)(env0 + g); q.y = sh.env[g].e.episode + 3u;
+        p.regen_list[(size_t)p.parity * 2 * c.N + p.regen_count[p.parity]++] = q;
+      }
+    }
+  }
+  if (c.write_final_obs && n_done) {
+    for (int item = 0; item < total; item++) {
+      int g = tk_item_env(sh.off, G, item);
+      const TEnv& t = sh.env[g];
+      if (t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
+    }
+    for (int k = 0; k < n_done; k++) tk_emit(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true);
+    for (int t = 0; t < NT; t++) phase_expand_final(c, p.f_obs_map, bs, t, NT, env0, n_done);
+    for (int i = 0; i < sh.bits_words; i++) sh.bits[i] = 0;
+  }
+  if (n_done) {
+    for (int k = 0; k < n_done; k++) tk_reset<TMAX, PREGEN>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+    for (int g = 0; g < nvalid; g++) tk_prefix(sh, sh.off2, g, nvalid, true);
+    const int total2 = sh.off2[G];
+    for (int t = 0; t < NT; t++)
+      for (int item = t; item < total2; item += NT) { int g = tk_item_env(sh.off2, G, item); tk_new_car(c, p, sh, g, item - sh.off2[g], env0 + g); }
+  }
+  for (int item = 0; item < total; item++) {
+    int g = tk_item_env(sh.off, G, item);
+    const TEnv& t = sh.env[g];
+    if (!t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
+  }
+  for (int g = 0; g < nvalid; g++) tk_emit(c, p, sh, g, env0 + g, false);
+  for (int t = 0; t < NT; t++) phase_expand(c, p.obs_map, bs, t, NT, env0, nvalid);
+  for (int k = 0; k < 8; k++) p.stats[k] += st[k];
+}
+
 static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, void*) {
   int T = h->dc.T;  // same TMAX dispatch as the CUDA backend
+  if (mode == MODE_STEP && h->traffic_G > 0) {
+    const TkLayout L = tk_layout(h->dc, h->traffic_G);
+    unsigned char* smem = (unsigned char*)bk_alloc(L.total);
+    int nblk = (h->dc.N + L.G - 1) / L.G;
+    for (int b = 0; b < nblk; b++) {
+      memset(smem, 0xA5, L.total);
+      if (h->dc.pregen) run_traffic_block<16, true>(h, actions, action_bytes, b, smem);
+      else if (T <= 16) run_traffic_block<16, false>(h, actions, action_bytes, b, smem);
+      else if (T <= 64) run_traffic_block<64, false>(h, actions, action_bytes, b, smem);
+      else run_traffic_block<256, false>(h, actions, action_bytes, b, smem);
+    }
+    free(smem);
+    return 0;
+  }
   if (mode == MODE_MAPGEN) {
     const bool tabled = h->dc.conn_bits && h->dc.path_tab;  // same dispatch as the CUDA launch code
     if (h->cfg.rng_mode == PGTG_RNG_NUMPY) { if (tabled) run_mapgen<PGTG_RNG_NUMPY, 16, true>(h); else if (T <= 16) run_mapgen<PGTG_RNG_NUMPY, 16>(h); else if (T <= 64) run_mapgen<PGTG_RNG_NUMPY, 64>(h); else run_mapgen<PGTG_RNG_NUMPY, 256>(h); }

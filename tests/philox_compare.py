@@ -16,7 +16,7 @@ def _eq(name, a, b, t):
         raise AssertionError(f"tick {t}: {name} differs at {bad[:5].tolist()} ({len(bad)} cells): got {a[tuple(bad[0])]} want {b[tuple(bad[0])]}")
 
 
-def compare(env, ora, ticks, action_seed=0, final_obs=True, state_every=0, check_obs_every=1):
+def compare(env, ora, ticks, action_seed=0, final_obs=True, state_every=0, check_obs_every=1, stay=0.0):
     """env: implementation under test; ora: the oracle. Returns the number of finished episodes."""
     N = ora.N
     rng = np.random.default_rng(action_seed)
@@ -27,6 +27,8 @@ def compare(env, ora, ticks, action_seed=0, final_obs=True, state_every=0, check
     episodes = 0
     for t in range(ticks):
         a = rng.integers(0, 9, N).astype(np.int32)
+        if stay > 0:  # mostly "no acceleration": the agent idles on the start line, so episodes (and their traffic) live long
+            a = np.where(rng.random(N) < stay, 4, a).astype(np.int32)
         env.step(a)
         ora.step(a)
         for name in ARRAYS:
@@ -74,4 +76,31 @@ CONFIGS = {
     "wide_16x16": (dict(random_map_width=16, random_map_height=16, random_map_percentage_of_connections=0.6, traffic_density=0.01,
                         random_map_obstacle_probability=0.3, use_next_subgoal_direction=True), 4, 12),
     "tiny_1x1": (dict(random_map_width=1, random_map_height=1, traffic_density=0.5, ignore_traffic_collisions=True), 130, 30),
+}
+
+# long-lived episodes (the agent mostly idles) for the traffic dynamics: blocking chains, patience, push-through,
+# lights, despawn / respawn bursts, occupancy counters; name -> (kwargs, num_envs, ticks, stay probability)
+_T = lambda n, e, s, w: {"exits": [n, e, s, w]}  # noqa: E731
+CROSSING = dict(width=1, height=1, start=[0, 0, "west"], goal=[0, 0, "east"], map=[[_T(1, 1, 1, 1)]])
+RING_3X3 = dict(width=3, height=3, start=[0, 2, "west"], goal=[2, 0, "east"], map=[
+    [_T(0, 1, 1, 0), _T(1, 1, 0, 1), _T(0, 1, 1, 1)],
+    [_T(1, 1, 1, 0), _T(1, 1, 1, 1), _T(1, 0, 1, 1)],
+    [_T(1, 1, 0, 1), _T(0, 1, 1, 1), _T(1, 0, 0, 1)]])
+TRAFFIC_CONFIGS = {
+    "crossing_full": (dict(map_plan=CROSSING, traffic_density=1.0, ignore_traffic_collisions=True), 70, 120, 0.97),
+    "crossing_half_collide": (dict(map_plan=CROSSING, traffic_density=0.5), 70, 60, 0.9),
+    "ring_dense_lights": (dict(map_plan=RING_3X3, traffic_density=0.6, ignore_traffic_collisions=True, traffic_light_phases_duration=(4, 2, 5)), 40, 150, 0.97),
+    "train_py": (dict(random_map_width=4, random_map_height=4, random_map_obstacle_probability=0.2, random_map_percentage_of_connections=0.8,
+                      traffic_density=0.2, conservative_driver_percentage=0.15, normal_driver_percentage=0.50, aggressive_driver_percentage=0.20,
+                      elderly_driver_percentage=0.10, reckless_driver_percentage=0.05, sliding_observation_window_size=5,
+                      use_sliding_observation_window=True, use_next_subgoal_direction=True, final_goal_bonus=200, standing_still_penalty=1,
+                      max_episode_steps=100, ignore_traffic_collisions=True), 50, 130, 0.95),
+    "aggressive_push": (dict(traffic_density=0.5, conservative_driver_percentage=0, normal_driver_percentage=0, aggressive_driver_percentage=0.6,
+                             elderly_driver_percentage=0, reckless_driver_percentage=0.4, random_map_percentage_of_connections=0.9,
+                             ignore_traffic_collisions=True, random_map_obstacle_probability=0.7, random_map_traffic_light_probability_weight=8,
+                             traffic_light_phases_duration=(2, 1, 6)), 40, 120, 0.97),
+    "big_8x8_idle": (dict(random_map_width=8, random_map_height=8, random_map_percentage_of_connections=0.8, traffic_density=0.2,
+                          random_map_obstacle_probability=0.5, ignore_traffic_collisions=True), 5, 60, 0.97),
+    "rules_without_traffic": (dict(traffic_density=0.1, traffic_rules=[dict(name="always", tile_type="0101", velocity_range=[0.0, 50.0], min_traffic=0,
+                                                                            min_matching_traffic=0, maneuvers=[])]), 100, 30, 0.5),
 }

@@ -21,3 +21,17 @@ def test_emulation_matches_oracle(name):
     assert episodes > 0
     env.close()
     ora.close()
+
+
+@pytest.mark.parametrize("name", list(pc.TRAFFIC_CONFIGS))
+@pytest.mark.parametrize("final_obs", [True, False])
+def test_traffic_tick_matches_oracle(name, final_obs):
+    """The traffic tick (pgtg_traffic.cuh: flat car phases + per-env ordered pass) against the oracle's sequential car loop."""
+    kw, n, ticks, stay = pc.TRAFFIC_CONFIGS[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = NativeAdapter("emu", num_envs=n, seed=77, final_observation=final_obs, **kw)
+        ora = OracleVectorEnv(num_envs=n, seed=77, final_observation=final_obs, **kw)
+    pc.compare(env, ora, ticks, state_every=10, stay=stay, final_obs=final_obs)
+    env.close()
+    ora.close()

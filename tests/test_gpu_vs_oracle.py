@@ -95,3 +95,37 @@ def test_numpy_mode_traffic_obstacles_procedural():
     env, ora = _pair(2048, rng_mode="numpy", traffic_density=0.05, random_map_obstacle_probability=0.3, seed=77)
     assert pc.compare(env, ora, 40, state_every=20) > 500
     env.close(); ora.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(pc.TRAFFIC_CONFIGS))
+@pytest.mark.parametrize("final_obs", [True, False])
+def test_traffic_tick_matches_oracle(name, final_obs):
+    """The traffic tick kernel (pgtg_traffic.cu) against the oracle's sequential car loop on long-lived episodes:
+    blocking chains, patience, push-through, lights, despawn / respawn bursts, occupancy counters."""
+    from native_env import NativeAdapter
+
+    kw, n, ticks, stay = pc.TRAFFIC_CONFIGS[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = NativeAdapter("cuda", num_envs=n, seed=77, final_observation=final_obs, **kw)
+        ora = OracleVectorEnv(num_envs=n, seed=77, final_observation=final_obs, threads=8, **kw)
+    assert "tick=traffic" in env.raw.kernel_info()
+    pc.compare(env, ora, ticks, state_every=10, stay=stay, final_obs=final_obs)
+    env.close(); ora.close()
+
+
+@pytest.mark.gpu
+def test_traffic_tick_equals_sequential_tick(monkeypatch):
+    """Same handle configuration through the traffic tick and through the general (sequential) tick: bit-identical."""
+    from native_env import NativeAdapter
+
+    kw = dict(traffic_density=0.1, random_map_obstacle_probability=0.4, seed=5, final_observation=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = NativeAdapter("cuda", num_envs=3000, **kw)
+        monkeypatch.setenv("PGTG_NO_TRAFFIC_KERNEL", "1")
+        b = NativeAdapter("cuda", num_envs=3000, **kw)
+    assert "tick=traffic" in a.raw.kernel_info() and "tick=general" in b.raw.kernel_info()
+    pc.compare(a, b, 40, state_every=10, stay=0.6)
+    a.close(); b.close()
