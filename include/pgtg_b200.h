@@ -251,6 +251,12 @@ int pgtg_get_buffers(pgtg_env* env, pgtg_buffers* out);
  * deleter only frees the descriptor. */
 int pgtg_dlpack(pgtg_env* env, const char* name, void** out_managed_tensor);
 int pgtg_get_state(pgtg_env* env, pgtg_state* out);
+/* The computed parts of PGTGEnv.get_info (environment.py:1538-1578), host arrays, any pointer may be NULL:
+ * agent_direction int32[N] = index into {south_to_north, west_to_east, north_to_south, east_to_west, stationary,
+ * near_goal} (get_agent_direction_string, :185-206); current_tile_type int32[N] = exits N | E<<1 | S<<2 | W<<3 of the
+ * agent's tile (:1541-1549); profile_counts int32[N, 5] = cars per driver profile (get_driver_profile_stats,
+ * :1017-1035). Synchronises. */
+int pgtg_get_info(pgtg_env* env, int32_t* agent_direction, int32_t* current_tile_type, int32_t* profile_counts);
 /* set_to_state (environment.py:1301-1342): agent, flat_tire and cars only (quirk A.3-10). */
 int pgtg_set_state(pgtg_env* env, const pgtg_state* in);
 /* Episode statistics are accumulated per CTA on the device. pgtg_reduce_stats sums them into the

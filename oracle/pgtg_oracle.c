@@ -618,7 +618,29 @@ static void build_episode_map(ora_batch* b, ora_env* e) {
       if (f & F_LANE) { e->spawnable[e->n_spawnable][0] = (int16_t)x; e->spawnable[e->n_spawnable][1] = (int16_t)y; e->n_spawnable++; }
       if (f & F_SPAWNER) { e->spawners[e->n_spawners][0] = (int16_t)x; e->spawners[e->n_spawners][1] = (int16_t)y; e->n_spawners++; }
     }
-  (void)b;
+  if (b->cfg.rng_mode == PGTG_RNG_PHILOX) {
+    /* Philox specification (product, pgtg_logic.cuh): both index spaces of the car stream enumerate tile by tile
+     * (t = ty * W + tx ascending) -- lane squares by local index lx * 9 + ly, car spawners by slot: the native
+     * one, then the border spawners of the north, east, south and west map border. */
+    e->n_spawnable = e->n_spawners = 0;
+    for (int t = 0; t < W * H; t++) {
+      int tx = t % W, ty = t / W, ex = e->exits[t];
+      for (int x = 0; x < 9; x++)
+        for (int y = 0; y < 9; y++)
+          if (e->grid[(tx * TW + x) * e->height + ty * TH + y] & F_LANE) {
+            e->spawnable[e->n_spawnable][0] = (int16_t)(tx * TW + x); e->spawnable[e->n_spawnable][1] = (int16_t)(ty * TH + y); e->n_spawnable++;
+          }
+      if (ex == 0) continue;
+      for (int slot = 0; slot < 5; slot++)
+        for (int x = 0; x < 9; x++)
+          for (int y = 0; y < 9; y++) {
+            const ora_lane_sq* l = &ORA_LANES[ex][x][y];
+            int hit = slot == 0 ? l->spawner : slot == 1 ? (ty == 0 && l->all == 2) : slot == 2 ? (tx == W - 1 && l->all == 3)
+                    : slot == 3 ? (ty == H - 1 && l->all == 1) : (tx == 0 && l->all == 4);
+            if (hit) { e->spawners[e->n_spawners][0] = (int16_t)(tx * TW + x); e->spawners[e->n_spawners][1] = (int16_t)(ty * TH + y); e->n_spawners++; }
+          }
+    }
+  }
 }
 
 static inline int inside_map(const ora_env* e, int x, int y) {

@@ -46,6 +46,7 @@ EXPORTS = {
     "pgtg_dlpack": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "pgtg_get_state": (C.c_int, [C.c_void_p, C.POINTER(PgtgState)]),
     "pgtg_set_state": (C.c_int, [C.c_void_p, C.POINTER(PgtgState)]),
+    "pgtg_get_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgtg_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pgtg_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgtg_reset_stats": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -18,6 +18,7 @@
 //   void* bk_event_create();  void bk_event_destroy(void*);  int bk_event_record(void* ev, void* stream);
 //   double bk_event_elapsed(void* a, void* b);
 //   int bk_stats_reduce(pgtg_env*, void* stream);  int bk_stats_reset(pgtg_env*, void* stream);
+//   int bk_info(pgtg_env*, int32_t* out_dev);   (info_env for every env)
 //   void bk_traffic_geometry(const DevCfg&, int* G, int* NT);   (G = 0: the traffic tick cannot run this configuration)
 #pragma once
 #include <math.h>
@@ -129,6 +130,31 @@ static int lean_predicate(const pgtg_config& c, const DevCfg& d) {
           !d.use_nsd && !d.vis_words && !c.separate_reward_cost && !c.write_final_obs) ? 1 : 0;
 }
 
+// The LUT block the kernels stage into shared memory: the generated tables plus everything derived from them.
+static const LutInit h_lut_init = {PGTG_TAB_WALL, PGTG_TAB_EXIT_LINE, PGTG_TAB_MASK, PGTG_TAB_LANE_ANY, PGTG_TAB_NATIVE_SPAWNER, PGTG_TAB_ENTRY_SQ};
+static const uint64_t h_lane_desc[16][81] = PGTG_TAB_LANE_DESC;
+static void derive_lut(Lut& L) {
+  memset(&L, 0, sizeof L);
+  memcpy(L.wall, h_lut_init.wall, sizeof L.wall); memcpy(L.exit_line, h_lut_init.exit_line, sizeof L.exit_line);
+  memcpy(L.mask, h_lut_init.mask, sizeof L.mask); memcpy(L.lane_any, h_lut_init.lane_any, sizeof L.lane_any);
+  memcpy(L.native_spawner, h_lut_init.native_spawner, sizeof L.native_spawner); memcpy(L.entry_sq, h_lut_init.entry_sq, sizeof L.entry_sq);
+  // local columns that can hold a car_spawner: native spawners and tile-entry squares
+  for (int e = 0; e < 16; e++) { int ns = L.native_spawner[e]; if (ns != 255) L.spawner_cols |= 1u << (ns / TILE); }
+  for (int d = 0; d < 4; d++) L.spawner_cols |= 1u << (L.entry_sq[d] / TILE);
+  for (int w = 0; w < 3; w++) L.exit_any[w] = L.exit_line[0][w] | L.exit_line[1][w] | L.exit_line[2][w] | L.exit_line[3][w];
+  for (int d = 0; d < 4; d++) {
+    int n = 0;
+    for (int sq = 0; sq < 81; sq++) if (((L.exit_line[d][sq >> 5] >> (sq & 31)) & 1u) && n < 4) L.line_sq[d][n++] = (uint8_t)sq;
+  }
+  for (int e = 0; e < 16; e++) {
+    L.lane_count[e] = (uint8_t)(__builtin_popcount(L.lane_any[e][0]) + __builtin_popcount(L.lane_any[e][1]) + __builtin_popcount(L.lane_any[e][2]));
+    // border spawners: the tile-entry square carries 'car_lane all <inward>' (parser.py:120-148); slots 1..4 = north, east,
+    // south, west border of the map <-> all down (2), all left (3), all up (1), all right (4) on entry_sq[1], [2], [0], [3]
+    static const int sq_of[4] = {1, 2, 0, 3}, all_of[4] = {2, 3, 1, 4};
+    for (int k = 0; k < 4; k++) if ((int)(h_lane_desc[e][L.entry_sq[sq_of[k]]] & 7) == all_of[k]) L.entry_ok[e] |= (uint8_t)(1u << k);
+  }
+}
+
 static int fill_devcfg(const pgtg_config& c, DevCfg& d, std::string& why) {
   memset(&d, 0, sizeof d);
   if (c.abi_version != PGTG_ABI_VERSION) { why = "pgtg_config.abi_version mismatch"; return -1; }
@@ -222,6 +248,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   e->side_stream = e->ev_tick = e->ev_map[0] = e->ev_map[1] = nullptr;
   e->launch_index = 0; e->mapgen_grid = 0;
   e->flat = nullptr; e->flat_dim = 0;
+  e->info_dev = nullptr;
   memset(&e->dp, 0, sizeof e->dp);
   if (bk_pick_block(e->dc, &e->block, &e->smem)) { delete e; return fail(PGTG_ERR_INVALID, "observation window too large for shared memory"); }
   e->nblk = (dc.N + e->block - 1) / e->block;
@@ -289,6 +316,15 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     bk_h2d(t2, e->edge_rev.data(), e->edge_rev.size() * 2, nullptr);
     bk_h2d(t3, e->border_slots.data(), e->border_slots.size() * 2, nullptr);
     p.edge_tab = t1; p.edge_rev = t2; p.border_slots = t3;
+  }
+  {
+    Lut L;
+    derive_lut(L);
+    Lut* ld = dev_alloc<Lut>(e, 1);
+    if (!ld) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }
+    bk_h2d(ld, &L, sizeof L, nullptr);
+    bk_sync(nullptr);  // (L is a stack object)
+    p.lut = ld;
   }
   {
     std::vector<uint8_t> lut;
@@ -672,6 +708,27 @@ extern "C" int pgtg_set_state(pgtg_env* e, const pgtg_state* s) {
   }
   bk_h2d(p.misc, misc.data(), N * 4, nullptr);
   bk_sync(nullptr);
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_get_info(pgtg_env* e, int32_t* agent_direction, int32_t* current_tile_type, int32_t* profile_counts) {
+  if (!e) return fail(PGTG_ERR_INVALID, "null handle");
+  if (!e->did_reset) return fail(PGTG_ERR_STATE, "get_info before reset");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  const size_t N = (size_t)e->dc.N;
+  if (!e->info_dev && !(e->info_dev = dev_alloc<int32_t>(e, 7 * N))) return fail(PGTG_ERR_CUDA, std::string("device allocation failed: ") + bk_error());
+  if (bk_info(e, e->info_dev)) return fail(PGTG_ERR_CUDA, std::string("info launch failed: ") + bk_error());
+  e->launches++;
+  if (agent_direction) bk_d2h(agent_direction, e->info_dev, N * 4, nullptr);
+  if (current_tile_type) bk_d2h(current_tile_type, e->info_dev + N, N * 4, nullptr);
+  if (profile_counts) {  // device layout [5][N] -> caller layout [N][5]
+    std::vector<int32_t> tmp(5 * N);
+    bk_d2h(tmp.data(), e->info_dev + 2 * N, 5 * N * 4, nullptr);
+    bk_sync(nullptr);
+    for (size_t i = 0; i < N; i++) for (int q = 0; q < 5; q++) profile_counts[i * 5 + q] = tmp[(size_t)q * N + i];
+  }
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
   return PGTG_OK;
 }
 

@@ -164,6 +164,8 @@ struct PcgState {
   uint32_t buf, has;  // PCG64's buffered upper half of the last 64-bit output (next_uint32)
 };
 
+struct Lut;
+
 // Device pointers (all owned by the handle).
 struct DevPtrs {
   // state, SoA
@@ -205,6 +207,7 @@ struct DevPtrs {
   const uint16_t* border_slots; // [n_border_slots] tile | dir << 8
   const uint8_t* dirlut;        // (2R+1)^2
   const uint32_t* conn_table;   // [2^conn_bits / 32] or null
+  const Lut* lut;               // the LUTs with their derived fields, built once per handle
   const uint64_t* path_table;   // [2^conn_bits] or null: 3-bit subgoal direction of every tile | ns << 48 | unreachable << 63
   const pgtg_rule* rules;
   // outputs
@@ -224,12 +227,14 @@ struct Lut {
   uint32_t lane_any[16][3];
   uint8_t native_spawner[16];
   uint8_t entry_sq[4];
-  uint32_t spawner_cols;  // local columns that can hold a car_spawner (derived when staging)
-  uint32_t exit_any[3];   // union of the four exit lines (derived when staging)
-  uint8_t line_sq[4][4];  // the three squares of each exit line in ascending order (derived when staging)
+  // derived once per handle on the host (derive_lut, pgtg_api_impl.hpp):
+  uint32_t spawner_cols;  // local columns that can hold a car_spawner
+  uint32_t exit_any[3];   // union of the four exit lines
+  uint8_t line_sq[4][4];  // the three squares of each exit line in ascending order
+  uint8_t lane_count[16]; // lane squares of a tile type
+  uint8_t entry_ok[16];   // per tile type, bit k: the border spawner of slot k + 1 exists (spawner slots, pgtg_logic.cuh)
 };
 struct LutInit { uint32_t wall[16][3], exit_line[4][3], mask[PGTG_NUM_MASKS][3], lane_any[16][3]; uint8_t native_spawner[16], entry_sq[4]; };
-PG_DEVCONST LutInit g_lut = {PGTG_TAB_WALL, PGTG_TAB_EXIT_LINE, PGTG_TAB_MASK, PGTG_TAB_LANE_ANY, PGTG_TAB_NATIVE_SPAWNER, PGTG_TAB_ENTRY_SQ};
 PG_DEVCONST uint64_t g_lane_desc[16][81] = PGTG_TAB_LANE_DESC;
 
 PG_HD bool bit81(const uint32_t* w, int sq) { return (w[sq >> 5] >> (sq & 31)) & 1u; }

@@ -37,6 +37,7 @@ struct pgtg_env {
   bool timing; std::vector<void*> tev; int tev_used;
   // flattened observation (FlattenObservation view for SB3-style consumers), allocated on first use
   float* flat; int flat_dim; int flat_order[PGTG_MAX_CHANNELS];
+  int32_t* info_dev;    // [7][N] scratch of pgtg_get_info, allocated on first use
   double* stats_rows;   // [nblk][8] per-CTA episode statistics (CUDA backend)
   // device scratch for reset arguments and host-buffer steps
   uint8_t* mask_dev;

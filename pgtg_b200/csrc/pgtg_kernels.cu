@@ -54,6 +54,7 @@ static int bk_launch(pgtg_env*, int mode, const uint8_t* mask, const int64_t* se
 static int bk_stats_reduce(pgtg_env*, void* stream);
 static int bk_stats_reset(pgtg_env*, void* stream);
 static int bk_flatten(pgtg_env*, void* stream);
+static int bk_info(pgtg_env*, int32_t* out_dev);
 static int bk_conn_table_max_bits() { return 24; }
 static int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
 static int bk_build_path_table(pgtg_env*, uint64_t* table_dev);
@@ -80,6 +81,17 @@ __global__ void pgtg_build_conn_table_kernel(const __grid_constant__ DevCfg c, u
 }
 
 struct FlatOrder { int plane[PGTG_MAX_CHANNELS]; };
+
+// get_info extras, one env per thread (tile descriptors read straight from HBM)
+__global__ void __launch_bounds__(128) pgtg_info_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int32_t* __restrict__ out) {
+  __shared__ __align__(16) Lut lut;
+  BlockShared sh;
+  sh.lut = &lut;
+  stage_tables(c, p, sh, threadIdx.x, blockDim.x, false);
+  __syncthreads();
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env < c.N) info_env(c, p, lut, env, out);
+}
 
 // one thread per entry of the subgoal-path table
 __global__ void __launch_bounds__(128) pgtg_build_path_table_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, uint64_t* __restrict__ table) {
@@ -184,6 +196,10 @@ static int bk_build_path_table(pgtg_env* e, uint64_t* table_dev) {
   uint32_t total = 1u << e->dc.conn_bits;
   int blocks = (int)((total + B - 1) / B < 148u * 12u ? (total + B - 1) / B : 148u * 12u);
   pgtg::pgtg_build_path_table_kernel<<<blocks, B, smem>>>(e->dc, e->dp, table_dev);
+  return ck(cudaGetLastError());
+}
+static int bk_info(pgtg_env* e, int32_t* out_dev) {
+  pgtg::pgtg_info_kernel<<<(e->dc.N + 127) / 128, 128>>>(e->dc, e->dp, out_dev);
   return ck(cudaGetLastError());
 }
 static int bk_flatten(pgtg_env* e, void* stream) {

@@ -7,6 +7,8 @@
 
 namespace pgtg {
 
+PG_HD int select32(uint32_t v, int n);
+
 // car lists: [env][half][slot]; `half` = misc bit 15 (the live list), the other half is scratch / write target
 PG_HD uint64_t* car_list(const DevCfg& c, const DevPtrs& p, int env, int half) { return p.cars + ((size_t)env * 2 + half) * c.max_cars; }
 
@@ -63,6 +65,57 @@ PG_HDN void build_spawner_list(const DevCfg& c, const DevPtrs& p, const MapView 
       }
     }
   p.spawner_count[env] = (uint16_t)(n < c.spawner_cap ? n : c.spawner_cap);
+}
+
+// Philox specification of the two index spaces the car stream draws from (the reference's x-major lists are only
+// reproduced in the tape / numpy modes): both enumerate TILE BY TILE (t = ty * W + tx ascending), which needs no
+// scan over the 9W x 9H squares:
+//   lane squares   within a tile by local square index lx * 9 + ly ascending;
+//   car spawners   within a tile by slot: 0 the tile type's native spawner (dead ends), then the border spawners of
+//                  the north, east, south and west map border (slots 1-4; parser.py:120-148).
+PG_HD unsigned spawner_slots(const DevCfg& c, const Lut& L, int ex, int tx, int ty) {  // 5-bit slot mask of tile (tx, ty)
+  if (ex == 0) return 0u;  // no lanes on wall-only tiles (parser.py:113-118)
+  unsigned border = (ty == 0 ? 1u : 0u) | (tx == c.W - 1 ? 2u : 0u) | (ty == c.H - 1 ? 4u : 0u) | (tx == 0 ? 8u : 0u);
+  return (L.native_spawner[ex] != 255 ? 1u : 0u) | (L.entry_ok[ex] & border) << 1;
+}
+PG_HD int spawner_slot_square(const Lut& L, int ex, int slot) {  // local square of a slot
+  return slot == 0 ? L.native_spawner[ex] : L.entry_sq[slot == 1 ? 1 : slot == 2 ? 2 : slot == 3 ? 0 : 3];
+}
+PG_HD void build_spawner_list_tile_major(const DevCfg& c, const DevPtrs& p, const MapView& m, int env) {
+  int n = 0;
+  uint16_t* list = p.spawners + (size_t)env * c.spawner_cap;
+  for (int t = 0; t < c.T; t++) {
+    const int ex = td_exits(m.tiles[t]), tx = t % c.W, ty = t / c.W;
+    unsigned slots = spawner_slots(c, m.L, ex, tx, ty);
+    while (slots) {
+      const int k = pg_ffs(slots) - 1, sq = spawner_slot_square(m.L, ex, k);
+      slots &= slots - 1;
+      if (n < c.spawner_cap) list[n] = (uint16_t)((tx * TILE + sq / TILE) | (ty * TILE + sq % TILE) << 8);
+      n++;
+    }
+  }
+  p.spawner_count[env] = (uint16_t)(n < c.spawner_cap ? n : c.spawner_cap);
+}
+// lane squares tile by tile: tpre[t] = lane squares of the tiles before t (T + 1 entries); returns the total
+PG_HD int lane_tile_prefix(const DevCfg& c, const MapView& m, uint16_t* tpre) {
+  int n = 0;
+  for (int t = 0; t < c.T; t++) { tpre[t] = (uint16_t)n; n += m.L.lane_count[td_exits(m.tiles[t])]; }
+  tpre[c.T] = (uint16_t)n;
+  return n;
+}
+PG_HD void lane_square_tile_major(const DevCfg& c, const MapView& m, const uint16_t* tpre, int idx, int& x, int& y) {
+  int lo = 0, hi = c.T;  // last tile with tpre[t] <= idx
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)tpre[mid] <= idx) lo = mid; else hi = mid; }
+  const uint32_t* la = m.L.lane_any[td_exits(m.tiles[lo])];
+  int rest = idx - tpre[lo], sq = 0;
+#pragma unroll
+  for (int w = 0; w < 3; w++) {
+    uint32_t bits = la[w];
+    const int cnt = pg_popc(bits);
+    if (rest >= 0 && rest < cnt) { sq = w * 32 + select32(bits, rest); rest = -1; }
+    else if (rest >= 0) rest -= cnt;
+  }
+  x = (lo % c.W) * TILE + sq / TILE; y = (lo / c.W) * TILE + sq % TILE;
 }
 
 // occupancy grid: per-tick 2-bit counters of the cars on every square (exact while < 3; the value 3
@@ -243,8 +296,8 @@ PG_HDN uint32_t create_initial_traffic(const DevCfg& c, const DevPtrs& p, const 
   EnvRegs e = e_in;
   Rng<RNG> rng(p, e, env);
   (void)car_words;
-  uint16_t colpre[TILE * 16 + 1];
-  int num_positions = lane_column_prefix(c, m, colpre);
+  uint16_t colpre[PGTG_MAX_TILES + 1];  // (>= 9 * 16 + 1) column prefix of the x-major list, or tile prefix in Philox mode
+  int num_positions = RNG == PGTG_RNG_PHILOX ? lane_tile_prefix(c, m, colpre) : lane_column_prefix(c, m, colpre);
   int num_cars = initial_car_count(c, num_positions);
   if (num_cars > c.max_cars) { e.err |= 32; num_cars = c.max_cars; }
   uint64_t* live = car_list(c, p, env, misc_half(e.misc));
@@ -282,7 +335,8 @@ PG_HDN uint32_t create_initial_traffic(const DevCfg& c, const DevPtrs& p, const 
     }
     for (int j = 0; j < num_cars; j++) {
       int x, y;
-      lane_square_at(c, m, colpre, (int)live[j], x, y);
+      if (RNG == PGTG_RNG_PHILOX) lane_square_tile_major(c, m, colpre, (int)live[j], x, y);
+      else lane_square_at(c, m, colpre, (int)live[j], x, y);
       Car car;
       car.profile = rng.car_choice_cdf(j, CW0_PROFILE, c.profile_cdf, PGTG_NUM_PROFILES);
       car.route = random_route_at<RNG>(m, rng, e, x, y, j, CW0_ROUTE);
@@ -897,7 +951,7 @@ PG_HD void begin_episode(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs&
   }
   if (RNG == PGTG_RNG_NUMPY) rng.np_begin_episode();  // children 5r+1..5r+4 of this reset (:593-599)
   if (!LEAN && !EXT && c.traffic_density > 0) {  // :652-653
-    build_spawner_list(c, p, m, env);
+    if (RNG == PGTG_RNG_PHILOX) build_spawner_list_tile_major(c, p, m, env); else build_spawner_list(c, p, m, env);
     int64_t cur; uint32_t err;
     uint32_t r = create_initial_traffic<RNG>(c, p, m, e, env, rng.kcount[PGTG_STREAM_CAR], &cur, &err);
     e.misc = misc_pack(misc_flat(e.misc), misc_light(e.misc), (int)(r & 0xFFFFu), misc_half(e.misc));

@@ -27,7 +27,7 @@
 namespace pgtg {
 
 constexpr int TK_DESPAWN_CAP = 6;
-constexpr int TK_OCC_MIN = 24;  // fewer cars: "is a car there" scans the env's 16-bit square list instead
+constexpr int TK_OCC_MIN = 40;  // fewer cars: "is a car there" scans the env's 16-bit square list instead
 
 // intent word: kind 0-1 | target square x 2-9, y 10-17 | route 18-22 | delay 23-24 | push 25 | profile 26-28 | moved 31
 enum : uint32_t { IK_STAY = 0, IK_LANE = 1, IK_ENTER = 2, IK_DESPAWN = 3, IK_PUSH = 1u << 25, IK_MOVED = 1u << 31 };
@@ -61,7 +61,7 @@ struct TkShared {
   uint16_t* fxy;       // [G][MC] car squares: old ones until the resolve pass, final ones after it
   uint32_t* occ;       // [G][occ_words] 4-bit counters per square, 15 = sticky "unknown" (null when MC < TK_OCC_MIN)
   uint32_t* bits;      // CTA observation bitstring, env g at bit g * obs_bits
-  uint16_t* colpre;    // [G][ncolp]
+  uint16_t* colpre;    // [G][ncolp] lane squares of the tiles before t (new episodes)
   int* off;            // [G + 1] car items of the tick
   int* off2;           // [G + 1] car items of the episodes that start in this tick
   int* counters;       // [16]
@@ -79,7 +79,7 @@ PG_HOSTDEV TkLayout tk_layout(const DevCfg& c, int G) {
   auto take = [&](size_t bytes) { uint32_t at = o; o += (uint32_t)align16(bytes); return at; };
   L.G = G; L.MC = c.max_cars;
   L.occ_words = c.max_cars >= TK_OCC_MIN ? (c.WS * c.HS + 7) / 8 : 0;
-  L.ncolp = (c.W * TILE + 2) & ~1;
+  L.ncolp = (c.T + 2) & ~1;
   L.bits_words = (G * c.obs_bits + 31) / 32 + 4;
   L.lut = take(sizeof(Lut)); L.spread = take(256 * sizeof(uint2));
   L.tiles = take(sizeof(uint16_t) * G * c.tile_stride);
@@ -414,9 +414,9 @@ PG_HD void tk_reset(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g
   if (PREGEN) env_reset_pregenerated<PGTG_RNG_PHILOX, false, true>(c, p, m, e, env);
   else env_reset<PGTG_RNG_PHILOX, TMAX, true>(c, p, m, e, env);
   m.plan = e.plan;
-  build_spawner_list(c, p, m, env);
+  build_spawner_list_tile_major(c, p, m, env);
   uint16_t* colpre = sh.colpre + g * sh.ncolp;
-  const int np = lane_column_prefix(c, m, colpre);
+  const int np = lane_tile_prefix(c, m, colpre);
   int nc = initial_car_count(c, np);
   if (nc > c.max_cars) { e.err |= 32; nc = c.max_cars; }
   t.num_positions = np; t.new_cars = nc;
@@ -433,7 +433,7 @@ PG_HD void tk_new_car(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int
   const MapView m = tk_map(c, sh, g);
   const int idx = initial_car_position(t.perm_keys, t.perm_h, t.num_positions, j);
   int x, y;
-  lane_square_at(c, m, sh.colpre + g * sh.ncolp, idx, x, y);
+  lane_square_tile_major(c, m, sh.colpre + g * sh.ncolp, idx, x, y);
   uint32_t w[4];
   philox_car_block(t.key, t.e.elapsed, t.e.episode, j, 0, w);
   const double u = car_u32_to_uniform(w[CW0_PROFILE]);

@@ -82,6 +82,14 @@ class RawEnv:
         _lib.check(self.lib, self.lib.pgtg_get_state(self._h, C.byref(st)))
         return out
 
+    def get_info(self) -> dict:
+        """The computed parts of PGTGEnv.get_info (environment.py:1538-1578) for every env."""
+        out = dict(agent_direction=np.zeros(self.N, np.int32), current_tile_type=np.zeros(self.N, np.int32),
+                   profile_counts=np.zeros((self.N, 5), np.int32))
+        _lib.check(self.lib, self.lib.pgtg_get_info(self._h, out["agent_direction"].ctypes.data, out["current_tile_type"].ctypes.data,
+                                                    out["profile_counts"].ctypes.data))
+        return out
+
     def set_state(self, agent=None, flat_tire=None, num_cars=None, cars=None):
         keep, kw = [], {}
         for name, arr, dt in (("agent", agent, np.int32), ("flat_tire", flat_tire, np.uint8),

@@ -35,6 +35,7 @@ static int bk_launch(pgtg_env*, int, const uint8_t*, const int64_t*, const void*
 static int bk_stats_reduce(pgtg_env*, void*);
 static int bk_stats_reset(pgtg_env*, void*);
 static int bk_flatten(pgtg_env*, void*);
+static int bk_info(pgtg_env*, int32_t*);
 static int bk_conn_table_max_bits() { return 13; }  // CPU tests: tables up to 8192 entries (e.g. 3x3 maps)
 static int bk_build_conn_table(pgtg_env*, uint32_t*);
 static int bk_build_path_table(pgtg_env*, uint64_t*);
@@ -241,6 +242,16 @@ extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
 // the emulation accumulates straight into the 8-double stats buffer
 static int bk_stats_reduce(pgtg_env*, void*) { return 0; }
 static int bk_stats_reset(pgtg_env* e, void*) { memset(e->dp.stats, 0, 64); return 0; }
+
+static int bk_info(pgtg_env* e, int32_t* out) {
+  Lut lut;
+  BlockShared sh;
+  memset(&sh, 0, sizeof sh);
+  sh.lut = &lut;
+  for (int t = 0; t < 128; t++) stage_tables(e->dc, e->dp, sh, t, 128, false);
+  for (int env = 0; env < e->dc.N; env++) info_env(e->dc, e->dp, lut, env, out);
+  return 0;
+}
 
 // host loop of the flatten kernel (same index arithmetic)
 static int bk_flatten(pgtg_env* e, void*) {

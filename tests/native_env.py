@@ -96,6 +96,9 @@ class NativeAdapter:
     def get_state(self):
         return self.raw.get_state()
 
+    def agent_direction(self):
+        return self.raw.get_info()["agent_direction"]
+
     def set_state(self, **kw):
         self.raw.set_state(**kw)
 
