@@ -9,10 +9,15 @@ on-device map regeneration, observation write) over every env of the rank's shar
 each rank owns `envs_per_gpu` envs (weak scaling, global env ids, no data-path collective); the only
 collective is the episode-statistics all-reduce at the end of the timed region.
 
-Prints ONE JSON line (rank 0): value = whole-job env-steps/s with inputs resident in HBM,
-e2e = the same through `pgtg_step_host` with pinned HOST buffers (copies inside the timed region),
-roofline = algorithmic bytes (SURVEY.md 8d formula) / measured kernel time vs MEASURED_PEAKS.json,
-cpu_baseline = the CPU oracle port timed on the host cores on a bounded sample.
+Prints ONE JSON line (rank 0):
+  value         whole-job env-steps/s of the headline workload (default-2M) with inputs resident in HBM
+  e2e           the same through `pgtg_step_host` with pinned HOST buffers (copies inside the timed region)
+  e2e_packed    through `pgtg_step_host_packed` (observation planes as bits, 92 B/env instead of 729)
+  roofline      algorithmic bytes (SURVEY.md 8d formula) / measured kernel time vs MEASURED_PEAKS.json
+  workloads     the other BASELINE configurations and the reference's consumer configuration, each timed
+                in this same invocation (N = 1 only): env-steps/s, kernel ms, roofline fraction
+  cpu_baseline  the CPU oracle port (C) on the host cores; cpu_baseline_python = the UNMODIFIED reference
+                PGTGEnv (oracle/_ref or /root/reference) in a forked runner, one worker per host core
 """
 from __future__ import annotations
 
@@ -29,28 +34,50 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-# name -> (PGTGEnv kwargs, envs per GPU, cpu sample envs)
+# pgtg/train.py:21-38 of the reference, verbatim, + its TimeLimit(100) (train.py:39)
+TRAIN_PY = dict(random_map_width=4, random_map_height=4, random_map_obstacle_probability=0.2, random_map_percentage_of_connections=0.8,
+                traffic_density=0.2, conservative_driver_percentage=0.15, normal_driver_percentage=0.50, aggressive_driver_percentage=0.20,
+                elderly_driver_percentage=0.10, reckless_driver_percentage=0.05, sliding_observation_window_size=5, max_allowed_deviation=15,
+                use_sliding_observation_window=True, use_next_subgoal_direction=True, final_goal_bonus=200, standing_still_penalty=1)
+
+# name -> (PGTGEnv kwargs, envs per GPU, cpu sample envs, extras)
 WORKLOADS = {
     # BASELINE config 5 per-GPU shard == the "default map settings" the north star quotes the target on
-    "default-2M": (dict(), 2 * 1024 * 1024, 16384),
+    "default-2M": (dict(), 2 * 1024 * 1024, 16384, {}),
     # BASELINE config 3
-    "traffic-64k": (dict(traffic_density=0.05, random_map_obstacle_probability=0.2), 65536, 4096),
+    "traffic-64k": (dict(traffic_density=0.05, random_map_obstacle_probability=0.2), 65536, 4096, {}),
     # BASELINE config 4
     "large-1M": (dict(random_map_width=8, random_map_height=8, random_map_percentage_of_connections=0.8, traffic_density=0.2,
-                      random_map_obstacle_probability=0.5), 1024 * 1024, 256),
+                      random_map_obstacle_probability=0.5), 1024 * 1024, 256, {}),
+    # the reference's real consumer: train.py's constructor arguments, TimeLimit(100), FlattenObservation each step
+    "train-py": (TRAIN_PY, 262144, 1024, dict(max_episode_steps=100, flat=True)),
+    # gymnasium's vector contract: terminal observations of auto-reset envs are written too
+    "default-2M+final_observation": (dict(), 2 * 1024 * 1024, 16384, dict(final_observation=True)),
     # small smoke-sized run
-    "default-64k": (dict(), 65536, 8192),
+    "default-64k": (dict(), 65536, 8192, {}),
 }
+EXTRA = ["traffic-64k", "large-1M", "train-py", "default-2M+final_observation"]
 
 
-def algorithmic_bytes(kw: dict) -> float:
+def mean_cars(kw: dict) -> float:
+    """Mean number of cars per env of a configuration, from a small probe handle."""
+    if not kw.get("traffic_density"):
+        return 0.0
+    from pgtg_b200 import PGTGVectorEnv
+
+    env = PGTGVectorEnv(2048, seed=1, **kw)
+    env.reset()
+    n = float(env.get_state()["num_cars"].mean())
+    env.close()
+    return n
+
+
+def algorithmic_bytes(kw: dict, n_cars: float) -> float:
     """bytes one env-step must move (int8 planes, scalars, agent state r/w, tile
     descriptors + used bits, car records r/w)."""
     C = len(kw.get("features_to_include_in_observation", [0] * 9))
     P = 9 if not kw.get("use_sliding_observation_window") else 1 + 2 * kw.get("sliding_observation_window_size", 4)
     T = kw.get("random_map_width", 4) * kw.get("random_map_height", 4)
-    lane_sq = {4: 304, 64: 1150}.get(T, 19 * T)  # measured mean lane squares per map (SURVEY a8 / probe)
-    n_cars = int(lane_sq * kw.get("traffic_density", 0.0))
     return C * P * P + 16 + 8 + 2 + 1 + 2 * 16 + T * 2 + 2 * ((T + 7) // 8) + 2 * 8 * n_cars
 
 
@@ -106,11 +133,12 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, samples=len(rows))
 
 
-def cpu_baseline(kw: dict, n_envs: int, seconds: float, threads: int) -> dict:
+# ---- CPU arms ------------------------------------------------------------------------------------
+def cpu_port(kw: dict, n_envs: int, seconds: float, threads: int, extras: dict) -> dict:
     """The oracle (C port of the reference tick, oracle/pgtg_oracle.c) on the host cores."""
     from oracle.oracle import OracleVectorEnv
 
-    env = OracleVectorEnv(num_envs=n_envs, threads=threads, seed=1, **kw)
+    env = OracleVectorEnv(num_envs=n_envs, threads=threads, seed=1, max_episode_steps=extras.get("max_episode_steps"), **kw)
     env.reset()
     rng = np.random.default_rng(0)
     acts = [rng.integers(0, 9, n_envs).astype(np.int32) for _ in range(4)]
@@ -125,36 +153,146 @@ def cpu_baseline(kw: dict, n_envs: int, seconds: float, threads: int) -> dict:
                 sample=f"{n_envs} envs x {steps} ticks ({dt:.1f} s) of the same workload, C oracle port, {threads} threads, incl. auto-reset")
 
 
-def run_reference(args, kw, n_cpu):
-    """`--impl reference`: the reference's CPU implementation of the path -- here the oracle port
-    (the Python reference cannot travel to the GPU box) -- with all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    from oracle.oracle import OracleVectorEnv
+def cpu_python(kw: dict, seconds: float, extras: dict) -> dict | None:
+    """The UNMODIFIED reference PGTGEnv (environment.py:581, 1092), forked runner with one worker per host core
+    (oracle/ref_pool.py: how train.py:54 consumes it), same kwargs, uniform random actions, same-step auto-reset."""
+    from oracle.ref_pool import ReferencePool, reference_root
 
-    env = OracleVectorEnv(num_envs=n_cpu, threads=threads, seed=1, **kw)
-    env.reset()
+    if reference_root() is None:
+        return None
+    cores = os.cpu_count() or 1
+    ref_kw = {k: v for k, v in kw.items()}
+    pool = ReferencePool(ref_kw, workers=cores, envs_per_worker=4, seed=0, max_episode_steps=extras.get("max_episode_steps"))
+    try:
+        r = pool.run(seconds)
+    finally:
+        pool.close()
+    return dict(value=r["value"], unit="env-steps/s", cores=cores, kind="reference",
+                sample=f"{pool.num_envs} reference PGTGEnv ({cores} forked workers x 4) x {r['env_steps'] // pool.num_envs} ticks ({r['seconds']:.1f} s), "
+                       f"{r['resets']} auto-resets, source {os.path.relpath(pool.root, ROOT) if pool.root.startswith(ROOT) else pool.root}")
+
+
+def run_reference(args, kw, n_cpu, extras):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, all of them:
+    the unmodified Python PGTGEnv from oracle/_ref (kind "reference") when staged, else the C oracle port."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle.ref_pool import ReferencePool, reference_root
+
+    cores = os.cpu_count() or 1
     rng = np.random.default_rng(0)
-    acts = [rng.integers(0, 9, n_cpu).astype(np.int32) for _ in range(4)]
-    inner = 8  # ticks per "step" of this arm: a bounded sample of the workload
-    for i in range(args.warmup):
-        env.step(acts[i % 4])
+    if reference_root() is not None:
+        pool = ReferencePool(dict(kw), workers=cores, envs_per_worker=4, seed=0, max_episode_steps=extras.get("max_episode_steps"))
+        n = pool.num_envs
+        t0 = time.perf_counter()
+        pool.step(rng.integers(0, 9, n))
+        tick_s = max(time.perf_counter() - t0, 1e-3)
+        # one "step" of this arm = `inner` ticks of every env of the pool: ~0.5 s, the whole run within ~2.5 minutes
+        inner = max(1, min(int(0.5 / tick_s), int(150.0 / (tick_s * max(args.steps + args.warmup, 1)))))
+        step = lambda: [pool.step(rng.integers(0, 9, n)) for _ in range(inner)]  # noqa: E731
+        kind, close = "reference", pool.close
+        sample = (f"{n} unmodified reference PGTGEnv ({cores} forked workers x 4, {os.path.basename(pool.root)}) x {inner} ticks per step, "
+                  "uniform random actions, same-step auto-reset")
+    else:
+        from oracle.oracle import OracleVectorEnv
+
+        env = OracleVectorEnv(num_envs=n_cpu, threads=cores, seed=1, max_episode_steps=extras.get("max_episode_steps"), **kw)
+        env.reset()
+        n, inner = n_cpu, 8
+        step = lambda: [env.step(rng.integers(0, 9, n).astype(np.int32)) for _ in range(inner)]  # noqa: E731
+        kind, close = "port", env.close
+        sample = f"{n} envs x {inner} ticks per step, C oracle port of the reference tick (oracle/_ref not staged), {cores} threads, incl. auto-reset"
+    for _ in range(args.warmup):
+        step()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        for i in range(inner):
-            env.step(acts[(s + i) % 4])
+    for _ in range(args.steps):
+        step()
     dt = time.perf_counter() - t0
-    value = n_cpu * inner * args.steps / dt
-    sample = f"{n_cpu} envs x {inner} ticks per step, C oracle port of the reference tick, {threads} threads, incl. auto-reset"
+    close()
+    value = n * inner * args.steps / dt
     print(json.dumps({
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32+f64", "data": "synthetic", "config": {"workload": args.workload, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ---- GPU side ------------------------------------------------------------------------------------
+def make_env(name, N, dev, rank, final_observation=False):
+    from pgtg_b200 import PGTGVectorEnv
+
+    kw, _, _, extras = WORKLOADS[name]
+    return PGTGVectorEnv(N, device=dev, seed=2026, env_id_base=rank * N, final_observation=final_observation or extras.get("final_observation", False),
+                         max_episode_steps=extras.get("max_episode_steps"), **kw)
+
+
+def action_pool(N, dev, rank):
+    import torch
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    return [torch.randint(0, 9, (N,), device=dev, dtype=torch.int32, generator=g) for _ in range(8)]
+
+
+def time_kernels_alone(env, pool, steps, flat):
+    """The tick kernel timed ALONE (overlap off: kernels back to back on this stream), CUDA events around each launch."""
+    env.raw.set_overlap(False)
+    for i in range(3):
+        env.step(pool[i % 8])
+    env.raw.enable_timing(steps)
+    for i in range(steps):
+        env.step(pool[i % 8])
+        if flat:
+            env.flat_observation()
+    alone = env.raw.timing()
+    env.raw.enable_timing(0)
+    env.raw.set_overlap(True)
+    return alone
+
+
+def measure_workload(name, dev, peak, steps=None):
+    """One of the other configurations, timed in this invocation: a short device-timed loop + the kernels alone."""
+    import torch
+
+    kw, N, _, extras = WORKLOADS[name]
+    flat = bool(extras.get("flat"))
+    env = make_env(name, N, dev, 0)
+    env.reset()
+    pool = action_pool(N, dev, 0)
+    for i in range(4):
+        env.step(pool[i % 8])
+        if flat:
+            env.flat_observation()
+    torch.cuda.synchronize()
+    # size the loop from a probe step: ~0.4 s of device time, 8..200 steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); env.step(pool[0]); e1.record(); torch.cuda.synchronize()
+    k = steps or int(max(8, min(200, 400.0 / max(e0.elapsed_time(e1), 1e-3))))
+    launches0 = env.launch_count()
+    e0.record()
+    for i in range(k):
+        env.step(pool[i % 8])
+        if flat:
+            env.flat_observation()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    launches = env.launch_count() - launches0
+    alone = time_kernels_alone(env, pool, min(k, 30), flat)
+    info = env.raw.kernel_info()
+    stats = env.episode_stats(reset=True, all_reduce=False)
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    b_alg = algorithmic_bytes(kw, mean_cars(kw))
+    return dict(env_steps_per_s=N * 1e3 / ms, envs=N, steps=k, ms_per_step=ms, kernel_ms=alone["tick_ms"], mapgen_ms=alone["mapgen_ms"],
+                gpu_launches=int(launches), kernels=info, flat_observation=flat, final_observation=bool(extras.get("final_observation")),
+                max_episode_steps=extras.get("max_episode_steps"), mean_episode_length=stats["mean_length"],
+                roofline={"bound": "hbm", "algorithmic_bytes_per_env_step": b_alg, "achieved": b_alg * N / (alone["tick_ms"] * 1e-3) / 1e9,
+                          "peak": peak, "unit": "GB/s", "frac": b_alg * N / (alone["tick_ms"] * 1e-3) / 1e9 / peak,
+                          "whole_step_frac": b_alg * N / (ms * 1e-3) / 1e9 / peak})
 
 
 def main():
@@ -166,14 +304,16 @@ def main():
     ap.add_argument("--workload", default="default-2M", choices=list(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (overrides the workload's)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=6.0)
+    ap.add_argument("--python-seconds", type=float, default=4.0, help="the unmodified Python reference beside the GPU path (0 = skip)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other workloads")
     ap.add_argument("--final-observation", action="store_true")
     args = ap.parse_args()
-    kw, n_gpu_envs, n_cpu = WORKLOADS[args.workload]
+    kw, n_gpu_envs, n_cpu, extras = WORKLOADS[args.workload]
     if args.envs:
         n_gpu_envs = args.envs
     if args.impl == "reference":
-        run_reference(args, kw, n_cpu)
+        run_reference(args, kw, n_cpu, extras)
         return
 
     import torch
@@ -186,16 +326,16 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from pgtg_b200 import PGTGVectorEnv
 
     N = n_gpu_envs
-    env = PGTGVectorEnv(N, device=dev, seed=2026, env_id_base=rank * N, final_observation=args.final_observation, **kw)
+    flat = bool(extras.get("flat"))
+    env = make_env(args.workload, N, dev, rank, args.final_observation)
     env.reset()
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    pool = [torch.randint(0, 9, (N,), device=dev, dtype=torch.int32, generator=g) for _ in range(8)]
+    pool = action_pool(N, dev, rank)
     for i in range(max(args.warmup, 3)):
         env.step(pool[i % 8])
+        if flat:
+            env.flat_observation()
     env.episode_stats(reset=True)  # first call loads the reduction kernel; not part of the timed region
     torch.cuda.synchronize()
 
@@ -220,59 +360,65 @@ def main():
     for i in range(args.steps):
         kev[i][0].record()
         env.step(pool[i % 8])
+        if flat:
+            env.flat_observation()
         kev[i][1].record()
     stats = env.episode_stats(all_reduce=True)  # the only collective: 8 doubles, once
     ev1.record()
     barrier()
-    if sampler:
-        sampler.end()
     ms = ev0.elapsed_time(ev1)
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     ktime = env.raw.timing()
     env.raw.enable_timing(0)
-    kernel_ms = ktime["tick_ms"]  # the dominant kernel: the fused tick
     launches = env.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * N * args.steps / (ms * 1e-3)
 
-    # ---- the dominant kernel timed ALONE (overlap off: kernels back to back on this stream) --------
+    # ---- the dominant kernel timed ALONE ------------------------------------------------------------
     alone_steps = min(args.steps, 40)
-    env.raw.set_overlap(False)
-    for i in range(3):
-        env.step(pool[i % 8])
-    env.raw.enable_timing(alone_steps)
-    for i in range(alone_steps):
-        env.step(pool[i % 8])
-    alone = env.raw.timing()
-    env.raw.enable_timing(0)
-    env.raw.set_overlap(True)
+    alone = time_kernels_alone(env, pool, alone_steps, flat)
     env.episode_stats(reset=True)
 
-    # ---- end to end through the host-buffer entry (pgtg_step_host) ------------------------------
+    # ---- end to end through the host-buffer entries -------------------------------------------------
     C, P = env.hc.pod.num_channels, env.hc.window
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
     out = dict(obs_map=pin((N, C, P, P), torch.int8), obs_position=pin((N, 2), torch.int32), obs_velocity=pin((N, 2), torch.int32),
                reward=pin((N,), torch.float64), terminated=pin((N,), torch.uint8), truncated=pin((N,), torch.uint8))
     hact = [torch.randint(0, 9, (N,), dtype=torch.int32).pin_memory().numpy() for _ in range(2)]
-    e2e_value = None
-    if args.e2e_steps > 0:
-        env.step_host(hact[0], out)
+
+    def timed_host_loop(fn, steps):
+        fn(hact[0])
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.e2e_steps):
-            env.step_host(hact[i % 2], out)
+        for i in range(steps):
+            fn(hact[i % 2])
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        s = time.perf_counter() - t0
+        tt = torch.tensor([s], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = world * N * args.e2e_steps / float(t.item())
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * N * steps / float(tt.item())
+
+    e2e_value = e2e_packed = None
+    packed_bytes = 0
+    if args.e2e_steps > 0:
+        e2e_value = timed_host_loop(lambda a: env.step_host(a, out), args.e2e_steps)
+        if hasattr(env, "step_host_packed"):
+            pout = env.packed_host_buffers(pinned=True)
+            packed_bytes = sum(v.nbytes for v in pout.values())
+            e2e_packed = timed_host_loop(lambda a: env.step_host_packed(a, pout), args.e2e_steps * 4)
+    if sampler:
+        sampler.end()
+    clocks = sampler.stop() if sampler else None
     h2d = N * 4
     d2h = sum(v.nbytes for v in out.values())
+    info = env.raw.kernel_info()
+    env.close()
+    del env
+    torch.cuda.empty_cache()
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -280,40 +426,57 @@ def main():
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        b_alg = algorithmic_bytes(kw)
-        overlapped_kernel_ms = kernel_ms
+        b_alg = algorithmic_bytes(kw, mean_cars(kw))
         kernel_ms = alone["tick_ms"]
         achieved = b_alg * N / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, "not measured in this run (ncu is not run inside bench.py)"
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload)
-        cpu = cpu_baseline(kw, n_cpu, args.cpu_seconds, os.cpu_count() or 1) if args.cpu_seconds > 0 else None
+            rec = json.load(open(tpath)).get(args.workload)
+            if isinstance(rec, dict):
+                traffic, traffic_src = rec.get("bytes_per_launch"), rec.get("source")
+        workloads = {}
+        if world == 1 and not args.no_extra and args.workload == "default-2M":
+            for name in EXTRA:
+                try:
+                    workloads[name] = measure_workload(name, dev, peak)
+                except Exception as exc:  # keep the headline line even if an extra workload fails
+                    workloads[name] = {"error": repr(exc)}
+        cpu = cpu_port(kw, n_cpu, args.cpu_seconds, os.cpu_count() or 1, extras) if args.cpu_seconds > 0 else None
+        cpu_py = None
+        if args.python_seconds > 0:
+            try:
+                cpu_py = cpu_python(kw, args.python_seconds, extras)
+            except Exception as exc:
+                cpu_py = {"error": repr(exc)}
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": args.workload, "envs_per_gpu": N, "kwargs": kw, "actions": "uniform random, 8 resident int32 tensors cycled",
-                       "rng": "philox4x32-10 per env", "auto_reset": "same step, on-device map regeneration",
-                       "final_observation": bool(args.final_observation),
+                       "rng": "philox4x32-10 per env", "auto_reset": "same step, on-device map regeneration", "kernels": info,
+                       "final_observation": bool(args.final_observation or extras.get("final_observation")), "flat_observation": flat,
                        "l2": f"working set {(b_alg * N) / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "path": "pgtg_step_host: pinned host actions in, observation/reward/flags out"},
+                    "steps": args.e2e_steps, "path": "pgtg_step_host: pinned host actions in, int8 observation planes / reward / flags out"},
+            "e2e_packed": {"value": e2e_packed, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": packed_bytes,
+                           "path": "pgtg_step_host_packed: observation planes as bits (pgtg_unpack_obs restores the int8 planes on the host), double-buffered"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg, "kernel_ms": kernel_ms,
-                         "kernel": "pgtg_tick_kernel (fused tick: step + auto-reset + observation write)",
+                         "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg, "kernel_ms": kernel_ms,
+                         "kernel": info,
                          "note": "kernel_ms/achieved/frac: the tick kernel timed alone (overlap off, CUDA events around the launch, "
                                  f"{alone_steps} launches); in the pipeline it shares the SMs with the map-generation kernel",
-                         "tick_ms_in_pipeline": overlapped_kernel_ms, "mapgen_ms_in_pipeline": ktime["mapgen_ms"],
+                         "tick_ms_in_pipeline": ktime["tick_ms"], "mapgen_ms_in_pipeline": ktime["mapgen_ms"],
                          "mapgen_ms_alone": alone["mapgen_ms"], "step_ms": step_ms,
                          "whole_step_frac": b_alg * N / (step_ms * 1e-3) / 1e9 / peak},
+            "workloads": workloads,
             "cpu_baseline": cpu,
+            "cpu_baseline_python": cpu_py,
             "episode_stats": stats,
         }
         print(json.dumps(line))
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -156,19 +156,24 @@ static uint32_t philox_car_word(rctx* r, int slot, int pos) {
   }
   return e->cblk[pos & 3];
 }
-static uint32_t feistel_round(uint32_t x, uint32_t k, int h) {
-  uint32_t t = (x + k) * 0x9E3779B1u;
-  t ^= t >> 15; t *= 0x85EBCA6Bu; t ^= t >> 13; t *= 0xC2B2AE35u; t ^= t >> 16;
-  return t >> (32 - h);
+static uint32_t feistel_mix(uint32_t x, uint32_t k) {
+  uint32_t t = (x ^ k) * 0x9E3779B1u;
+  t ^= t >> 15; t *= 0x85EBCA6Bu; t ^= t >> 13;
+  return t;
 }
+/* Feistel network over [0, 2^m), m = bits of n - 1 (at least 2), halves of a = m / 2 and m - a bits, cycle-walked into [0, n) */
 static int initial_car_position(const uint32_t keys[4], int n, int slot) {
-  int h = 1;
-  while ((1 << (2 * h)) < n) h++;
-  uint32_t v = (uint32_t)slot, mask = (1u << h) - 1u;
+  int m = 2;
+  while ((1 << m) < n) m++;
+  int a = m >> 1, b = m - a;
+  uint32_t ma = (1u << a) - 1u, mb = (1u << b) - 1u, v = (uint32_t)slot;
   do {
-    uint32_t L = v >> h, R = v & mask;
-    for (int i = 0; i < 4; i++) { uint32_t t = L ^ feistel_round(R, keys[i], h); L = R; R = t; }
-    v = L << h | R;
+    uint32_t lo = v & ma, hi = v >> a;
+    lo ^= feistel_mix(hi, keys[0]) & ma;
+    hi ^= feistel_mix(lo, keys[1]) & mb;
+    lo ^= feistel_mix(hi, keys[2]) & ma;
+    hi ^= feistel_mix(lo, keys[3]) & mb;
+    v = hi << a | lo;
   } while (v >= (uint32_t)n);
   return (int)v;
 }

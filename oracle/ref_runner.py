@@ -18,8 +18,9 @@ import sys
 
 import numpy as np
 
-REF = os.environ.get("PGTG_REFERENCE", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference tree: the read-only checkout in the build container, else the copy staged by oracle/stage_ref.py
+REF = os.environ.get("PGTG_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/pgtg") else os.path.join(_HERE, "_ref"))
 
 
 def reference_available() -> bool:

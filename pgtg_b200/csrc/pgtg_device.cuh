@@ -358,7 +358,7 @@ PG_HD uint32_t pcg_bounded(PcgState& s, uint32_t rng) {
 // with s = the car's index in the list when the tick starts, and FIXED word meanings (CW_*). A car-stream
 // uniform is one word scaled by 2^-32; an index draw is (word * n) >> 32; one-element choices draw nothing.
 // Initial traffic (tick 0 of the episode): car slot j takes lane square perm(j) of the x-major list, perm = a
-// 4-round Feistel permutation of [0, 4^h) keyed by the block of slot -1 (field 0), cycle-walked into [0, n);
+// 4-round Feistel permutation of [0, 2^m) keyed by the block of slot -1 (field 0), cycle-walked into [0, n);
 // its profile and route come from words CW0_* of its own block.
 enum { CW_DELAY = 0, CW_SPEED = 1, CW_IDX = 2 /* reaction delay length, or the route drawn on tile entry */, CW_PUSH = 3,
        CW_LIGHT = 4, CW_SPAWNER = 5, CW_SPAWN_ROUTE = 6, CW_PROFILE = 7, CW0_PROFILE = 0, CW0_ROUTE = 1 };
@@ -367,20 +367,26 @@ PG_HD void philox_car_block(uint64_t key, uint32_t tick, uint32_t episode, int s
   philox4x32_10(w[0], w[1], w[2], w[3], (uint32_t)key, (uint32_t)(key >> 32));
 }
 PG_HD double car_u32_to_uniform(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
-PG_HD int feistel_half_bits(int n) { int h = 1; while ((1 << (2 * h)) < n) h++; return h; }
-PG_HD uint32_t feistel_round(uint32_t x, uint32_t k, int h) {
-  uint32_t t = (x + k) * 0x9E3779B1u;
-  t ^= t >> 15; t *= 0x85EBCA6Bu; t ^= t >> 13; t *= 0xC2B2AE35u; t ^= t >> 16;
-  return t >> (32 - h);
+// Feistel network over [0, 2^m), m = bits of n - 1 (at least 2), halves of a = m / 2 and m - a bits: even rounds
+// XOR the low half with F(high half), odd rounds the high half with F(low half); cycle-walked into [0, n).
+PG_HD int feistel_bits(int n) { int m = 2; while ((1 << m) < n) m++; return m; }
+PG_HD uint32_t feistel_mix(uint32_t x, uint32_t k) {
+  uint32_t t = (x ^ k) * 0x9E3779B1u;
+  t ^= t >> 15; t *= 0x85EBCA6Bu; t ^= t >> 13;
+  return t;
 }
 // position of initial car `slot` among n lane squares (n >= 1, slot < n)
-PG_HD int initial_car_position(const uint32_t keys[4], int h, int n, int slot) {
-  uint32_t v = (uint32_t)slot, mask = (1u << h) - 1u;
+PG_HD int initial_car_position(const uint32_t keys[4], int m, int n, int slot) {
+  const int a = m >> 1, b = m - a;
+  const uint32_t ma = (1u << a) - 1u, mb = (1u << b) - 1u;
+  uint32_t v = (uint32_t)slot;
   do {
-    uint32_t L = v >> h, R = v & mask;
-#pragma unroll
-    for (int i = 0; i < 4; i++) { uint32_t t = L ^ feistel_round(R, keys[i], h); L = R; R = t; }
-    v = L << h | R;
+    uint32_t lo = v & ma, hi = v >> a;
+    lo ^= feistel_mix(hi, keys[0]) & ma;
+    hi ^= feistel_mix(lo, keys[1]) & mb;
+    lo ^= feistel_mix(hi, keys[2]) & ma;
+    hi ^= feistel_mix(lo, keys[3]) & mb;
+    v = hi << a | lo;
   } while (v >= (uint32_t)n);
   return (int)v;
 }

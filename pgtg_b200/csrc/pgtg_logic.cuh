@@ -330,8 +330,8 @@ PG_HDN uint32_t create_initial_traffic(const DevCfg& c, const DevPtrs& p, const 
     } else {  // Philox specification: keyed Feistel permutation of the lane squares (pgtg_device.cuh, CW_*)
       uint32_t keys[4];
       philox_car_block(p.key[env], e.elapsed, e.episode, -1, 0, keys);
-      const int h = feistel_half_bits(num_positions);
-      for (int j = 0; j < num_cars; j++) live[j] = (uint64_t)(uint32_t)initial_car_position(keys, h, num_positions, j);
+      const int m_bits = feistel_bits(num_positions);
+      for (int j = 0; j < num_cars; j++) live[j] = (uint64_t)(uint32_t)initial_car_position(keys, m_bits, num_positions, j);
     }
     for (int j = 0; j < num_cars; j++) {
       int x, y;

@@ -45,14 +45,14 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
 
   // ---- the cars: intents (flat), blocking in list order (per env), commit (flat) ----------------------------
   for (int item = tid; item < total; item += NT) {
-    const int g = tk_item_env(sh.off, G, item);
+    const int g = sh.item_g[item];
     tk_intent(c, p, sh, g, item - sh.off[g], env0 + g);
   }
   __syncthreads();
   if (mine && sh.env[tid].n_cars > 0) tk_resolve(c, sh, tid);
   __syncthreads();
   for (int item = tid; item < total; item += NT) {
-    const int g = tk_item_env(sh.off, G, item);
+    const int g = sh.item_g[item];
     tk_commit(c, p, sh, g, item - sh.off[g], env0 + g);
   }
   __syncthreads();
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
   // ---- terminal observation of the finished envs (optional output) ------------------------------------------
   if (c.write_final_obs && n_done) {  // CTA-uniform
     for (int item = tid; item < total; item += NT) {
-      const int g = tk_item_env(sh.off, G, item);
+      const int g = sh.item_g[item];
       const TEnv& t = sh.env[g];
       if (t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
     }
@@ -110,25 +110,27 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
     __syncthreads();
   }
 
+  // ---- traffic plane of the running envs (flat) ------------------------------------------------------------------
+  for (int item = tid; item < total; item += NT) {
+    const int g = sh.item_g[item];
+    const TEnv& t = sh.env[g];
+    if (!t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
+  }
+
   // ---- same-step auto-reset: the map (per env), then the new episode's cars (flat) ------------------------------
   if (n_done) {
     if (done) tk_reset<TMAX, PREGEN>(c, p, sh, tid, env);
     __syncthreads();
-    if (mine) tk_prefix(sh, sh.off2, tid, nvalid, true);
+    if (mine) tk_prefix(sh, sh.off2, tid, nvalid, true);  // (rewrites the item table: the tick's items are done with)
     __syncthreads();
     const int total2 = sh.off2[G];
     for (int item = tid; item < total2; item += NT) {
-      const int g = tk_item_env(sh.off2, G, item);
+      const int g = sh.item_g[item];
       tk_new_car(c, p, sh, g, item - sh.off2[g], env0 + g);
     }
   }
 
-  // ---- observation: traffic plane of the running envs (flat), map planes + scalars + state (per env) ------------
-  for (int item = tid; item < total; item += NT) {
-    const int g = tk_item_env(sh.off, G, item);
-    const TEnv& t = sh.env[g];
-    if (!t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
-  }
+  // ---- map planes + scalars + state (per env) ---------------------------------------------------------------------
   if (mine) tk_emit(c, p, sh, tid, env, false);
   __syncthreads();
   if (tid == 0 && n_done) {
@@ -150,7 +152,10 @@ int pgtg_traffic_geometry(const pgtg::DevCfg& c, int* G, int* NT, size_t* smem) 
   *G = 0; *NT = 0; *smem = 0;
   if (L.total > 220u * 1024u || c.max_cars > 0xFFFF) return 0;
   *G = g; *smem = L.total;
-  *NT = L.total > 72u * 1024u ? 1024 : 256;  // one CTA per SM: make it a big one
+  // the per-env phases keep one warp per CTA busy: small CTAs (many per SM) while shared memory allows, one big CTA otherwise
+  *NT = L.total > 72u * 1024u ? 1024 : (L.total > 28u * 1024u ? 256 : 128);
+  const char* forced = getenv("PGTG_TRAFFIC_NT");  // experiment knob
+  if (forced && (atoi(forced) == 64 || atoi(forced) == 128 || atoi(forced) == 256 || atoi(forced) == 1024)) *NT = atoi(forced);
   return 1;
 }
 
@@ -177,6 +182,8 @@ static int launch_traffic(pgtg_env* e, const void* actions, int action_bytes, cu
 template <int TMAX, bool PREGEN>
 static int launch_traffic_nt(pgtg_env* e, const void* actions, int action_bytes, cudaStream_t st) {
   if (e->traffic_NT == 1024) return launch_traffic<TMAX, PREGEN, 1024, 1>(e, actions, action_bytes, st);
+  if (e->traffic_NT == 128) return launch_traffic<TMAX, PREGEN, 128, 8>(e, actions, action_bytes, st);
+  if (e->traffic_NT == 64) return launch_traffic<TMAX, PREGEN, 64, 16>(e, actions, action_bytes, st);
   return launch_traffic<TMAX, PREGEN, 256, 3>(e, actions, action_bytes, st);
 }
 

@@ -46,6 +46,8 @@ struct TEnv {
   int32_t tile_x, tile_y;        // the agent's tile before its move (rule engine, environment.py:208-224)
   int32_t in_tile;               // cars in that tile after the traffic advance
   uint32_t hist[5];              // their routes: 8-bit counter per route id
+  int32_t hist_overflow;         // a route counter wrapped: the rule engine falls back to the list scan
+  uint64_t bloom;                // 64-bit filter over the squares that hold (or held, this tick) a car: a clear bit = no car there
   int32_t n_despawn;
   uint16_t despawn[TK_DESPAWN_CAP];  // list slots of the cars that left the map, ascending
   int32_t done;                  // StepResult.outcome of this tick
@@ -62,6 +64,7 @@ struct TkShared {
   uint32_t* occ;       // [G][occ_words] 4-bit counters per square, 15 = sticky "unknown" (null when MC < TK_OCC_MIN)
   uint32_t* bits;      // CTA observation bitstring, env g at bit g * obs_bits
   uint16_t* colpre;    // [G][ncolp] lane squares of the tiles before t (new episodes)
+  uint8_t* item_g;     // [G * MC] item -> env of the CTA (the tick's cars, later the new episodes' cars)
   int* off;            // [G + 1] car items of the tick
   int* off2;           // [G + 1] car items of the episodes that start in this tick
   int* counters;       // [16]
@@ -70,7 +73,7 @@ struct TkShared {
   int bits_words, G, MC, occ_words, ncolp;
 };
 struct TkLayout {
-  uint32_t lut, spread, tiles, env, intent, fxy, occ, bits, colpre, off, off2, counters, dsum, done_list, total;
+  uint32_t lut, spread, tiles, env, intent, fxy, occ, bits, colpre, item_g, off, off2, counters, dsum, done_list, total;
   int bits_words, G, MC, occ_words, ncolp;
 };
 PG_HOSTDEV TkLayout tk_layout(const DevCfg& c, int G) {
@@ -89,6 +92,7 @@ PG_HOSTDEV TkLayout tk_layout(const DevCfg& c, int G) {
   L.occ = take(sizeof(uint32_t) * G * L.occ_words);
   L.bits = take(sizeof(uint32_t) * L.bits_words);
   L.colpre = take(sizeof(uint16_t) * G * L.ncolp);
+  L.item_g = take((size_t)G * L.MC);
   L.off = take(sizeof(int) * (G + 1)); L.off2 = take(sizeof(int) * (G + 1));
   L.counters = take(sizeof(int) * 16); L.dsum = take(sizeof(double) * 2);
   L.done_list = take(sizeof(int) * G);
@@ -100,7 +104,7 @@ PG_HOSTDEV TkShared tk_carve(unsigned char* base, const TkLayout& L) {
   s.lut = (Lut*)(base + L.lut); s.spread = (uint2*)(base + L.spread); s.tiles = (uint16_t*)(base + L.tiles);
   s.env = (TEnv*)(base + L.env); s.intent = (uint32_t*)(base + L.intent); s.fxy = (uint16_t*)(base + L.fxy);
   s.occ = L.occ_words ? (uint32_t*)(base + L.occ) : nullptr; s.bits = (uint32_t*)(base + L.bits);
-  s.colpre = (uint16_t*)(base + L.colpre); s.off = (int*)(base + L.off); s.off2 = (int*)(base + L.off2);
+  s.colpre = (uint16_t*)(base + L.colpre); s.item_g = (uint8_t*)(base + L.item_g); s.off = (int*)(base + L.off); s.off2 = (int*)(base + L.off2);
   s.counters = (int*)(base + L.counters); s.dsum = (double*)(base + L.dsum); s.done_list = (int*)(base + L.done_list);
   s.bits_words = L.bits_words; s.G = L.G; s.MC = L.MC; s.occ_words = L.occ_words; s.ncolp = L.ncolp;
   return s;
@@ -134,6 +138,7 @@ PG_HD void occ4_inc_atomic(uint32_t* o, int i) {
     old = seen;
   }
 }
+PG_HD uint64_t bloom_bit(unsigned xy) { return 1ull << (((xy * 40503u) >> 10) & 63u); }
 PG_HD bool tk_use_occ(const TkShared& sh, int n_cars) { return sh.occ_words != 0 && n_cars >= TK_OCC_MIN; }
 PG_HD bool tk_scan(const uint16_t* fx, int n, unsigned xy) {
   for (int j = 0; j < n; j++)
@@ -159,25 +164,22 @@ PG_HD void tk_stage_env(const DevCfg& c, const DevPtrs& p, const TkShared& sh, i
   int tx = floordiv9(e.x), ty = floordiv9(e.y);
   t.tile_x = tx < 0 ? 0 : (tx > c.W - 1 ? c.W - 1 : tx);
   t.tile_y = ty < 0 ? 0 : (ty > c.H - 1 ? c.H - 1 : ty);
-  t.in_tile = 0; t.n_despawn = 0; t.done = 0; t.new_cars = 0; t.num_positions = 0; t.perm_h = 1;
+  t.in_tile = 0; t.n_despawn = 0; t.done = 0; t.new_cars = 0; t.num_positions = 0; t.perm_h = 2; t.hist_overflow = 0; t.bloom = 0;
 #pragma unroll
   for (int i = 0; i < 5; i++) t.hist[i] = 0;
 }
-// exclusive prefix of a per-env count (thread g sums the envs before it; G <= 128)
+// exclusive prefix of a per-env count (thread g sums the envs before it; G <= 128) ...
+// ... and the item -> env table of the flat phases that follow
 PG_HD void tk_prefix(const TkShared& sh, int* off, int g, int nvalid, bool new_cars) {
   int s = 0;
   for (int j = 0; j < g; j++) s += new_cars ? sh.env[j].new_cars : sh.env[j].n_cars;
   off[g] = s;
+  const int mine = new_cars ? sh.env[g].new_cars : sh.env[g].n_cars;
+  for (int k = 0; k < mine; k++) sh.item_g[s + k] = (uint8_t)g;
   if (g == nvalid - 1) {
-    s += new_cars ? sh.env[g].new_cars : sh.env[g].n_cars;
+    s += mine;
     for (int j = nvalid; j <= sh.G; j++) off[j] = s;
   }
-}
-// item -> env of the CTA: last g with off[g] <= item
-PG_HD int tk_item_env(const int* off, int G, int item) {
-  int lo = 0, hi = G;
-  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= item) lo = mid; else hi = mid; }
-  return lo;
 }
 
 // ---- intents: one car per thread (_get_next_car_position_and_route, environment.py:881-968) -----------
@@ -203,12 +205,19 @@ PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
   uint32_t word = intent_pack(IK_STAY, 0, 0, car.route, delay, false, car.profile);
   if (move) {
     bool found = false;
+    const int ctx = car.x / TILE, cty = car.y / TILE, clx = car.x - ctx * TILE, cly = car.y - cty * TILE;
 #pragma unroll 1
     for (int d = 0; d < 4 && !found; d++) {  // up, down, left, right (:891-902)
-      const int px = car.x + (d == 2 ? -1 : d == 3 ? 1 : 0), py = car.y + (d == 0 ? -1 : d == 1 ? 1 : 0);
-      if (!m.inside(px, py)) continue;
-      const uint64_t ld = lane_desc(m.tile_type_at(px, py), m.local_sq(px, py));
+      // the neighbour square as (tile, local square): one step from (ctx, cty, clx, cly), no divisions
+      int ntx = ctx, nty = cty, nlx = clx + (d == 2 ? -1 : d == 3 ? 1 : 0), nly = cly + (d == 0 ? -1 : d == 1 ? 1 : 0);
+      if (nlx < 0) { nlx = TILE - 1; ntx--; } else if (nlx >= TILE) { nlx = 0; ntx++; }
+      if (nly < 0) { nly = TILE - 1; nty--; } else if (nly >= TILE) { nly = 0; nty++; }
+      if (ntx < 0 || nty < 0 || ntx >= c.W || nty >= c.H) continue;  // inside_map
+      const unsigned td = m.tiles[nty * c.W + ntx];
+      const int ex = td_exits(td), sq = nlx * TILE + nly;
+      const uint64_t ld = lane_desc(ex, sq);
       if (ld == 0) continue;
+      const int px = ntx * TILE + nlx, py = nty * TILE + nly;
       if (ld_all(ld) == d + 1) {  // entering a new tile: uniform new route, never blocked (:915-928)
         const int n = ld_n(ld);
         word = intent_pack(IK_ENTER, px, py, ld_route(ld, n > 1 ? (int)pg_umulhi(w0[CW_IDX], (uint32_t)n) : 0), delay, false, car.profile);
@@ -220,7 +229,7 @@ PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
         if (ld_route(ld, i) != car.route || ld_dir(ld, i) != d) continue;  // :932
         found = true;
         bool stop = false;
-        if (m.light_at(px, py)) {  // :934-942
+        if (td_otype(td) == 4 && bit81(m.L.mask[td_omask(td)], sq) && !bit81(m.L.wall[ex], sq)) {  // a traffic light (:934-942)
           const int phase = light_phase(c, misc_light(e.misc));
           if (phase != 0) {
             philox_car_block(t.key, e.elapsed, e.episode, r, 1, w1);
@@ -268,6 +277,10 @@ PG_HD void tk_resolve(const DevCfg& c, const TkShared& sh, int g) {
   const bool use_occ = tk_use_occ(sh, n);
   uint32_t* occ = use_occ ? sh.occ + g * sh.occ_words : nullptr;
   int nd = 0;
+  // 64-bit filter over every square that holds a car now or receives one during the pass (bits are never cleared):
+  // most targets hit a clear bit and need neither the list scan nor the counters
+  uint64_t bloom = 0;
+  for (int r = 0; r < n; r++) bloom |= bloom_bit(fx[r]);
   for (int r = 0; r < n; r++) {
     const uint32_t w = it[r];
     const uint32_t kind = w & 3u;
@@ -276,11 +289,13 @@ PG_HD void tk_resolve(const DevCfg& c, const TkShared& sh, int g) {
     if (kind == IK_LANE) {
       // cars_on_next_position over the live list: earlier cars (and replacements) at their new squares, later
       // ones at their old squares -- exactly what fx holds at this point
-      bool blocked;
-      if (use_occ) {
-        const int v = occ4_get(occ, occ4_index(c, T));
-        blocked = v == 15 ? tk_scan(fx, n, T) : v != 0;
-      } else blocked = tk_scan(fx, n, T);
+      bool blocked = false;
+      if (bloom & bloom_bit(T)) {
+        if (use_occ) {
+          const int v = occ4_get(occ, occ4_index(c, T));
+          blocked = v == 15 ? tk_scan(fx, n, T) : v != 0;
+        } else blocked = tk_scan(fx, n, T);
+      }
       if (blocked && !(w & IK_PUSH)) continue;
       it[r] = w | IK_MOVED;
     } else if (kind == IK_DESPAWN) {
@@ -289,8 +304,10 @@ PG_HD void tk_resolve(const DevCfg& c, const TkShared& sh, int g) {
     }
     if (use_occ) { occ4_dec(occ, occ4_index(c, fx[r])); occ4_inc(occ, occ4_index(c, T)); }
     fx[r] = (uint16_t)T;
+    bloom |= bloom_bit(T);
   }
   t.n_despawn = nd;
+  t.bloom = bloom;
 }
 
 // ---- commit: one car per thread; live half -> other half, order-stable ------------------------------------------
@@ -318,9 +335,10 @@ PG_HD void tk_commit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
   }
   car.x = (int)(fxy & 255u); car.y = (int)(fxy >> 8);
   car_list(c, p, env, half ^ 1)[slot] = car_pack(car);
-  if (c.num_rules > 0 && n <= 255 && car.x / TILE == t.tile_x && car.y / TILE == t.tile_y) {
+  if (c.num_rules > 0 && car.x / TILE == t.tile_x && car.y / TILE == t.tile_y) {
     pg_atomic_add(&t.in_tile, 1);
-    pg_atomic_add(&t.hist[car.route >> 2], 1u << (8 * (car.route & 3)));
+    const uint32_t old = pg_atomic_add(&t.hist[car.route >> 2], 1u << (8 * (car.route & 3)));
+    if (((old >> (8 * (car.route & 3))) & 255u) == 255u) t.hist_overflow = 1;  // > 255 cars of one route in one tile
   }
 }
 
@@ -332,8 +350,8 @@ struct ExtTraffic {
   PG_MEMBER bool braking(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, int n_cars) const {
     // apply_braking / evaluate_rule (environment.py:226-294) on the counters the commit phase collected
     if (c.num_rules == 0 || !(n_cars > 0 || c.rules_without_traffic)) return false;
-    if (n_cars > 255) return apply_braking(c, p, m, e, env);  // 8-bit route counters: fall back to the list scan
     const TEnv& t = sh->env[g];
+    if (t.hist_overflow) return apply_braking(c, p, m, e, env);  // 8-bit route counters wrapped: fall back to the list scan
     const int type = td_exits(m.tiles[t.tile_y * c.W + t.tile_x]);
     const double speed = sqrt((double)(e.vx * e.vx + e.vy * e.vy));
     int adir = -1;
@@ -351,6 +369,7 @@ struct ExtTraffic {
   }
   PG_MEMBER bool car_at(const DevCfg& c, const DevPtrs&, const EnvRegs&, int, int x, int y, int n_cars) const {
     const unsigned xy = (unsigned)x | (unsigned)y << 8;
+    if (!(sh->env[g].bloom & bloom_bit(xy))) return false;
     const uint16_t* fx = sh->fxy + g * sh->MC;
     if (tk_use_occ(*sh, n_cars)) {
       const int v = occ4_get(sh->occ + g * sh->occ_words, occ4_index(c, xy));
@@ -422,7 +441,7 @@ PG_HD void tk_reset(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g
   t.num_positions = np; t.new_cars = nc;
   if (nc > 0) {
     philox_car_block(t.key, e.elapsed, e.episode, -1, 0, t.perm_keys);
-    t.perm_h = feistel_half_bits(np);
+    t.perm_h = feistel_bits(np);
   }
   e.misc = misc_pack(0, 0, nc, 0);
   e.next_car_id = (uint32_t)nc;  // ids follow the slots (_create_initial_traffic, :830-879)

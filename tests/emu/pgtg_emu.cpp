@@ -143,10 +143,10 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
   for (int g = 0; g < nvalid; g++) tk_prefix(sh, sh.off, g, nvalid, false);
   const int total = sh.off[G];
   for (int t = 0; t < NT; t++)
-    for (int item = t; item < total; item += NT) { int g = tk_item_env(sh.off, G, item); tk_intent(c, p, sh, g, item - sh.off[g], env0 + g); }
+    for (int item = t; item < total; item += NT) { int g = sh.item_g[item]; tk_intent(c, p, sh, g, item - sh.off[g], env0 + g); }
   for (int g = 0; g < nvalid; g++) if (sh.env[g].n_cars > 0) tk_resolve(c, sh, g);
   for (int t = 0; t < NT; t++)
-    for (int item = t; item < total; item += NT) { int g = tk_item_env(sh.off, G, item); tk_commit(c, p, sh, g, item - sh.off[g], env0 + g); }
+    for (int item = t; item < total; item += NT) { int g = sh.item_g[item]; tk_commit(c, p, sh, g, item - sh.off[g], env0 + g); }
   int n_done = 0;
   double st[8] = {0};
   for (int g = 0; g < nvalid; g++) {
@@ -163,7 +163,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
   }
   if (c.write_final_obs && n_done) {
     for (int item = 0; item < total; item++) {
-      int g = tk_item_env(sh.off, G, item);
+      int g = sh.item_g[item];
       const TEnv& t = sh.env[g];
       if (t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
     }
@@ -171,17 +171,17 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
     for (int t = 0; t < NT; t++) phase_expand_final(c, p.f_obs_map, bs, t, NT, env0, n_done);
     for (int i = 0; i < sh.bits_words; i++) sh.bits[i] = 0;
   }
+  for (int item = 0; item < total; item++) {
+    int g = sh.item_g[item];
+    const TEnv& t = sh.env[g];
+    if (!t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
+  }
   if (n_done) {
     for (int k = 0; k < n_done; k++) tk_reset<TMAX, PREGEN>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
     for (int g = 0; g < nvalid; g++) tk_prefix(sh, sh.off2, g, nvalid, true);
     const int total2 = sh.off2[G];
     for (int t = 0; t < NT; t++)
-      for (int item = t; item < total2; item += NT) { int g = tk_item_env(sh.off2, G, item); tk_new_car(c, p, sh, g, item - sh.off2[g], env0 + g); }
-  }
-  for (int item = 0; item < total; item++) {
-    int g = tk_item_env(sh.off, G, item);
-    const TEnv& t = sh.env[g];
-    if (!t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
+      for (int item = t; item < total2; item += NT) { int g = sh.item_g[item]; tk_new_car(c, p, sh, g, item - sh.off2[g], env0 + g); }
   }
   for (int g = 0; g < nvalid; g++) tk_emit(c, p, sh, g, env0 + g, false);
   for (int t = 0; t < NT; t++) phase_expand(c, p.obs_map, bs, t, NT, env0, nvalid);
