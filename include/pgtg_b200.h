@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PGTG_ABI_VERSION 1
+#define PGTG_ABI_VERSION 2
 #define PGTG_MAX_CHANNELS 16
 #define PGTG_MAX_RULES 8
 #define PGTG_NUM_PROFILES 5
@@ -180,7 +180,8 @@ typedef struct pgtg_buffers {
   int32_t* final_obs_velocity;     /* [N, 2] or NULL */
   int32_t* final_obs_next_subgoal_direction; /* [N] or NULL */
   /* episode statistics accumulated on device: episodes, sum_return, sum_length, goals,
-   * crashes, truncations (doubles so one NCCL all-reduce(sum) covers them) */
+   * crashes, truncations, sum of discounted returns, negative discounted returns (the last two with
+   * pgtg_set_evaluation; doubles so one NCCL all-reduce(sum) covers them) */
   double* stats;           /* [8] */
 } pgtg_buffers;
 
@@ -237,6 +238,16 @@ int pgtg_step_host(pgtg_env* env, const int32_t* actions, int8_t* obs_map, int32
                    int32_t* obs_velocity, double* reward, uint8_t* terminated, uint8_t* truncated,
                    void* stream);
 
+/* The same with the observation planes as BITS (env i at bit i * C*P*P of obs_packed, pgtg_packed_obs_bytes bytes in
+ * all: 92 B per env instead of 729 at the defaults) and the copies double-buffered on a copy stream: the tick of the next
+ * call does not wait for this call's device-to-host copies. wait != 0 returns when the host buffers are complete;
+ * wait == 0 leaves them in flight until pgtg_host_sync. pgtg_unpack_obs turns the bits back into int8 cells on the host. */
+int64_t pgtg_packed_obs_bytes(pgtg_env* env);
+int pgtg_step_host_packed(pgtg_env* env, const int32_t* actions, uint32_t* obs_packed, int32_t* obs_position, int32_t* obs_velocity,
+                          double* reward, uint8_t* terminated, uint8_t* truncated, int wait, void* stream);
+int pgtg_host_sync(pgtg_env* env);
+int pgtg_unpack_obs(const uint32_t* obs_packed, int8_t* obs_map, int64_t n_cells, int threads);
+
 /* Recompute the observation buffers from the current state without ticking (the second half of
  * set_to_state, environment.py:1342). */
 int pgtg_observe(pgtg_env* env, void* stream);
@@ -259,6 +270,20 @@ int pgtg_get_state(pgtg_env* env, pgtg_state* out);
 int pgtg_get_info(pgtg_env* env, int32_t* agent_direction, int32_t* current_tile_type, int32_t* profile_counts);
 /* set_to_state (environment.py:1301-1342): agent, flat_tire and cars only (quirk A.3-10). */
 int pgtg_set_state(pgtg_env* env, const pgtg_state* in);
+/* Full-state checkpoint / clone (PGTGEnv.light_step deep-copies the env, environment.py:1283-1299; the reference's
+ * set_to_state restores only a part, quirk A.3-10): everything a tick reads or writes -- SoA state, both ring slots and the
+ * map-request queues, car lists, RNG state / tape cursors, light counters, patience and delays, consumed subgoals, episode
+ * statistics and the output buffers. save/load go through a host blob of pgtg_state_bytes bytes; copy is device to device
+ * between two handles of the same configuration on the same device. All three synchronise. */
+int64_t pgtg_state_bytes(pgtg_env* env);
+int pgtg_save_state(pgtg_env* env, void* out, int64_t out_bytes);
+int pgtg_load_state(pgtg_env* env, const void* in, int64_t in_bytes);
+int pgtg_copy_state(pgtg_env* dst, pgtg_env* src);
+/* Evaluator statistics (ModularEvaluator.evaluate, evaluator.py:292-339): gamma > 0 switches on the per-env discounted
+ * return (total += reward * pow(gamma, t), the powers evaluated on the host) and sets the episode cap to max_steps;
+ * stats[6] = sum of the discounted returns of the finished episodes, stats[7] = how many of them were negative
+ * (terminated = stats[3] + stats[4], over max_steps = stats[5]). gamma <= 0 switches it off. Synchronises. */
+int pgtg_set_evaluation(pgtg_env* env, double gamma, int max_steps);
 /* Episode statistics are accumulated per CTA on the device. pgtg_reduce_stats sums them into the
  * 8-double `stats` buffer on `stream` without synchronising (so the host can NCCL-all-reduce that
  * device buffer); pgtg_reset_stats clears them. */
@@ -280,6 +305,9 @@ int pgtg_enable_timing(pgtg_env* env, int max_steps);
  * kernels back to back on the caller's stream instead, e.g. to time each kernel alone. Synchronises. */
 int pgtg_set_overlap(pgtg_env* env, int on);
 int pgtg_timing(pgtg_env* env, double* tick_ms, double* mapgen_ms, int* steps);
+/* OR of every env's sticky error flags (bit 7 = 128: an action outside 0..8 was replaced by the no-op 4, where the
+ * reference raises KeyError; the other bits are listed in pgtg_api_impl.hpp). Synchronises. */
+int pgtg_error_summary(pgtg_env* env, uint32_t* out_flags);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t pgtg_launch_count(pgtg_env* env);
 /* Which kernel instantiations a step of this handle launches, as text ("tick=traffic(G=32,NT=256) ..."). */

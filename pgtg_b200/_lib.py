@@ -40,6 +40,15 @@ EXPORTS = {
     "pgtg_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgtg_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pgtg_step_host": (C.c_int, [C.c_void_p] * 9),
+    "pgtg_packed_obs_bytes": (C.c_int64, [C.c_void_p]),
+    "pgtg_step_host_packed": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_void_p]),
+    "pgtg_host_sync": (C.c_int, [C.c_void_p]),
+    "pgtg_unpack_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "pgtg_state_bytes": (C.c_int64, [C.c_void_p]),
+    "pgtg_save_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "pgtg_load_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "pgtg_copy_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pgtg_set_evaluation": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
     "pgtg_observe": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgtg_update_rules": (C.c_int, [C.c_void_p, C.POINTER(PgtgRule), C.c_int]),
     "pgtg_get_buffers": (C.c_int, [C.c_void_p, C.POINTER(PgtgBuffers)]),
@@ -51,6 +60,7 @@ EXPORTS = {
     "pgtg_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgtg_reset_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgtg_launch_count": (C.c_int64, [C.c_void_p]),
+    "pgtg_error_summary": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "pgtg_kernel_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "pgtg_flatten": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "pgtg_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
@@ -73,7 +83,7 @@ def load(path: str | None = None) -> C.CDLL:
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the declared ABI
         fn.restype, fn.argtypes = res, args
-    if lib.pgtg_abi_version() != 1:
+    if lib.pgtg_abi_version() != 2:
         raise RuntimeError("pgtg_b200: ABI version mismatch between the Python host and the native library")
     _cache[path] = lib
     return lib

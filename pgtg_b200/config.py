@@ -19,7 +19,7 @@ import numpy as np
 
 from ._names import CARDINALS, MASK_NAMES, OBSTACLE_NAMES, ROUTE_NAMES
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CHANNELS = 16
 MAX_RULES = 8
 NUM_PROFILES = 5

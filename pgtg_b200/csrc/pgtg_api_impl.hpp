@@ -18,7 +18,8 @@
 //   void* bk_event_create();  void bk_event_destroy(void*);  int bk_event_record(void* ev, void* stream);
 //   double bk_event_elapsed(void* a, void* b);
 //   int bk_stats_reduce(pgtg_env*, void* stream);  int bk_stats_reset(pgtg_env*, void* stream);
-//   int bk_info(pgtg_env*, int32_t* out_dev);   (info_env for every env)
+//   int bk_d2d(void* dst, const void* src, size_t n, void* stream);  void* bk_stream_create();  void bk_stream_destroy(void*);
+//   int bk_info(pgtg_env*, int32_t* out_dev);  int bk_error_or(pgtg_env*, uint32_t* out_dev);   (*out_dev = OR of p.error[0..N))   (info_env for every env)
 //   void bk_traffic_geometry(const DevCfg&, int* G, int* NT);   (G = 0: the traffic tick cannot run this configuration)
 #pragma once
 #include <math.h>
@@ -249,6 +250,8 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   e->launch_index = 0; e->mapgen_grid = 0;
   e->flat = nullptr; e->flat_dim = 0;
   e->info_dev = nullptr;
+  e->packed_dev = nullptr; e->stage_dev[0] = e->stage_dev[1] = nullptr; e->stage_bytes = 0; e->copy_stream = nullptr;
+  e->ev_stage[0] = e->ev_stage[1] = e->ev_copied[0] = e->ev_copied[1] = nullptr; e->host_steps = 0;
   memset(&e->dp, 0, sizeof e->dp);
   if (bk_pick_block(e->dc, &e->block, &e->smem)) { delete e; return fail(PGTG_ERR_INVALID, "observation window too large for shared memory"); }
   e->nblk = (dc.N + e->block - 1) / e->block;
@@ -260,7 +263,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   DevPtrs& p = e->dp;
   size_t N = (size_t)dc.N;
   bool ok = true;
-#define A(field, type, count) ok = ok && ((p.field = dev_alloc<type>(e, (count))) != nullptr)
+#define A(field, type, count) ok = ok && ((p.field = dev_alloc<type>(e, (count))) != nullptr) && (e->state_allocs.push_back({p.field, sizeof(type) * (size_t)(count)}), true)
   A(agent, short4, N); A(misc, uint32_t, N); A(elapsed, uint32_t, N); A(episode, uint32_t, N); A(next_car_id, uint32_t, N);
   A(plan, uint32_t, N); A(tiles, uint16_t, N * dc.T + 8);
   if (dc.pregen) { A(next_tiles, uint16_t, 2 * N * dc.T + 8); A(next_plan, uint32_t, 2 * N); A(regen_list, uint2, 4 * N); A(regen_count, uint32_t, 4); } A(cars, uint64_t, 2 * (size_t)dc.max_cars * N);
@@ -276,7 +279,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     A(f_obs_map, int8_t, N * dc.obs_bits + 16); A(f_obs_position, int32_t, 2 * N); A(f_obs_velocity, int32_t, 2 * N); A(f_obs_nsd, int32_t, N);
   }
   A(stats, double, 8);
-  ok = ok && ((e->stats_rows = dev_alloc<double>(e, 8 * (size_t)e->stats_nrows)) != nullptr);
+  ok = ok && ((e->stats_rows = dev_alloc<double>(e, 8 * (size_t)e->stats_nrows)) != nullptr) && (e->state_allocs.push_back({e->stats_rows, 64 * (size_t)e->stats_nrows}), true);
   ok = ok && ((e->mask_dev = dev_alloc<uint8_t>(e, N)) != nullptr);
   ok = ok && ((e->seeds_dev = dev_alloc<int64_t>(e, N)) != nullptr);
   ok = ok && ((e->actions_dev = dev_alloc<int32_t>(e, N)) != nullptr);
@@ -369,6 +372,8 @@ extern "C" int pgtg_destroy(pgtg_env* e) {
   bk_side_destroy(e->side_stream, e->ev_tick, e->ev_map[0], e->ev_map[1]);
   bk_sync(nullptr);
   for (void* ev : e->tev) bk_event_destroy(ev);
+  for (int i = 0; i < 2; i++) { if (e->ev_stage[i]) bk_event_destroy(e->ev_stage[i]); if (e->ev_copied[i]) bk_event_destroy(e->ev_copied[i]); }
+  if (e->copy_stream) bk_stream_destroy(e->copy_stream);
   for (void* a : e->allocs) bk_free(a);
   delete e;
   return PGTG_OK;
@@ -732,6 +737,172 @@ extern "C" int pgtg_get_info(pgtg_env* e, int32_t* agent_direction, int32_t* cur
   return PGTG_OK;
 }
 
+
+// ---- full-state checkpoint / clone (PGTGEnv.light_step deep-copies the env, environment.py:1283-1299) ------------
+// Everything a tick reads or writes: SoA state, both ring slots and the map-request queues, car lists, RNG state
+// (numpy mode) / tape cursors, episode statistics, the output buffers, plus the host-side pipeline position.
+struct StateHeader { uint64_t magic, total_bytes, launch_index; int32_t parity, did_reset, cars_injected, lean, n_allocs, reserved; };
+static const uint64_t STATE_MAGIC = 0x5047544753544132ull;  // "PGTGSTA2"
+static size_t state_payload_bytes(const pgtg_env* e) { size_t n = 0; for (auto& s : e->state_allocs) n += (s.bytes + 15) & ~(size_t)15; return n; }
+
+extern "C" int64_t pgtg_state_bytes(pgtg_env* e) { return e ? (int64_t)(sizeof(StateHeader) + state_payload_bytes(e)) : 0; }
+
+extern "C" int pgtg_save_state(pgtg_env* e, void* out, int64_t out_bytes) {
+  if (!e || !out) return fail(PGTG_ERR_INVALID, "null argument");
+  if (out_bytes < pgtg_state_bytes(e)) return fail(PGTG_ERR_INVALID, "state buffer too small (see pgtg_state_bytes)");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  StateHeader h = {STATE_MAGIC, (uint64_t)pgtg_state_bytes(e), e->launch_index, e->dp.parity, e->did_reset, e->cars_injected, e->dc.lean, (int32_t)e->state_allocs.size(), 0};
+  memcpy(out, &h, sizeof h);
+  unsigned char* dst = (unsigned char*)out + sizeof h;
+  for (auto& s : e->state_allocs) { bk_d2h(dst, s.ptr, s.bytes, nullptr); dst += (s.bytes + 15) & ~(size_t)15; }
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  return PGTG_OK;
+}
+
+extern "C" int pgtg_load_state(pgtg_env* e, const void* in, int64_t in_bytes) {
+  if (!e || !in) return fail(PGTG_ERR_INVALID, "null argument");
+  StateHeader h;
+  if (in_bytes < (int64_t)sizeof h) return fail(PGTG_ERR_INVALID, "not a pgtg state blob");
+  memcpy(&h, in, sizeof h);
+  if (h.magic != STATE_MAGIC || (int64_t)h.total_bytes != pgtg_state_bytes(e) || in_bytes < (int64_t)h.total_bytes || h.n_allocs != (int32_t)e->state_allocs.size())
+    return fail(PGTG_ERR_INVALID, "state blob does not belong to a handle of this configuration");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  const unsigned char* src = (const unsigned char*)in + sizeof h;
+  for (auto& s : e->state_allocs) { bk_h2d(s.ptr, src, s.bytes, nullptr); src += (s.bytes + 15) & ~(size_t)15; }
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  e->launch_index = h.launch_index; e->dp.parity = h.parity; e->did_reset = h.did_reset != 0; e->cars_injected = h.cars_injected != 0; e->dc.lean = h.lean;
+  return PGTG_OK;
+}
+
+// device-to-device: dst becomes an exact copy of src (same configuration, same device)
+extern "C" int pgtg_copy_state(pgtg_env* dst, pgtg_env* src) {
+  if (!dst || !src) return fail(PGTG_ERR_INVALID, "null argument");
+  if (dst->device != src->device || dst->state_allocs.size() != src->state_allocs.size()) return fail(PGTG_ERR_INVALID, "handles differ in configuration or device");
+  for (size_t i = 0; i < src->state_allocs.size(); i++)
+    if (dst->state_allocs[i].bytes != src->state_allocs[i].bytes) return fail(PGTG_ERR_INVALID, "handles differ in configuration");
+  bk_set_device(src->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  for (size_t i = 0; i < src->state_allocs.size(); i++) bk_d2d(dst->state_allocs[i].ptr, src->state_allocs[i].ptr, src->state_allocs[i].bytes, nullptr);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  dst->launch_index = src->launch_index; dst->dp.parity = src->dp.parity; dst->did_reset = src->did_reset; dst->cars_injected = src->cars_injected;
+  dst->dc.lean = src->dc.lean; dst->dc.num_rules = src->dc.num_rules; dst->dc.rules_without_traffic = src->dc.rules_without_traffic;
+  dst->dc.max_episode_steps = src->dc.max_episode_steps;
+  return PGTG_OK;
+}
+
+// ---- evaluator statistics (ModularEvaluator.evaluate, evaluator.py:292-339) ----------------------------------------
+// gamma > 0 switches on the per-env discounted return total += reward * pow(gamma, t) (t = tick of the episode) and the
+// two statistics built on it: stats[6] = sum of the discounted returns of finished episodes, stats[7] = how many of them
+// were negative. max_steps becomes the episode cap (the evaluator's "over max_steps" = truncations, stats[5]).
+extern "C" int pgtg_set_evaluation(pgtg_env* e, double gamma, int max_steps) {
+  if (!e) return fail(PGTG_ERR_INVALID, "null handle");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  if (!(gamma > 0)) { e->dc.eval_on = 0; return PGTG_OK; }
+  if (max_steps < 1) return fail(PGTG_ERR_INVALID, "max_steps must be >= 1");
+  std::vector<double> tab((size_t)max_steps);
+  for (int t = 0; t < max_steps; t++) tab[(size_t)t] = pow(gamma, (double)t);  // np.power(GAMMA, t) calls the same libm pow
+  double* td = dev_alloc<double>(e, (size_t)max_steps, false);
+  if (!td) return fail(PGTG_ERR_CUDA, std::string("device allocation failed: ") + bk_error());
+  bk_h2d(td, tab.data(), tab.size() * 8, nullptr);
+  if (!e->dp.ep_disc) {
+    e->dp.ep_disc = dev_alloc<double>(e, (size_t)e->dc.N);
+    if (!e->dp.ep_disc) return fail(PGTG_ERR_CUDA, std::string("device allocation failed: ") + bk_error());
+    e->state_allocs.push_back({e->dp.ep_disc, 8 * (size_t)e->dc.N});
+  } else bk_memset(e->dp.ep_disc, 0, 8 * (size_t)e->dc.N);
+  bk_sync(nullptr);
+  e->dp.gamma_pow = td;
+  e->dc.eval_on = 1; e->dc.gamma_len = max_steps; e->dc.max_episode_steps = max_steps; e->cfg.max_episode_steps = max_steps;
+  return PGTG_OK;
+}
+
+// ---- host-buffer step with the observation planes as bits, double-buffered ------------------------------------------
+// H2D actions -> tick -> one device-to-device gather of the step's outputs into staging slot (k & 1) -> D2H of that slot on
+// a copy stream. The tick of call k + 1 does not wait for the copies of call k (it only needs slot (k + 1) & 1, whose
+// copies belong to call k - 1). wait != 0: return when this call's outputs are in the host buffers; wait == 0: they are
+// complete after the next pgtg_host_sync (or the next call with the same slot parity).
+struct HostLayout { size_t packed, pos, vel, reward, term, trunc, total; };
+static HostLayout host_layout(const pgtg_env* e) {
+  HostLayout L; size_t N = (size_t)e->dc.N, o = 0;
+  auto take = [&](size_t b) { size_t at = o; o += (b + 255) & ~(size_t)255; return at; };
+  L.packed = take(4 * ((N * e->dc.obs_bits + 31) / 32)); L.pos = take(8 * N); L.vel = take(8 * N); L.reward = take(8 * N); L.term = take(N); L.trunc = take(N);
+  L.total = o;
+  return L;
+}
+extern "C" int64_t pgtg_packed_obs_bytes(pgtg_env* e) { return e ? (int64_t)(4 * (((size_t)e->dc.N * e->dc.obs_bits + 31) / 32)) : 0; }
+
+extern "C" int pgtg_step_host_packed(pgtg_env* e, const int32_t* actions, uint32_t* obs_packed, int32_t* obs_position, int32_t* obs_velocity,
+                                     double* reward, uint8_t* terminated, uint8_t* truncated, int wait, void* stream) {
+  if (!e || !actions) return fail(PGTG_ERR_INVALID, "null argument");
+  bk_set_device(e->device);
+  const size_t N = (size_t)e->dc.N;
+  const HostLayout L = host_layout(e);
+  if (!e->packed_dev) {
+    e->packed_dev = dev_alloc<uint32_t>(e, (size_t)pgtg_packed_obs_bytes(e) / 4 + 8);
+    e->stage_dev[0] = dev_alloc<unsigned char>(e, L.total); e->stage_dev[1] = dev_alloc<unsigned char>(e, L.total);
+    e->copy_stream = bk_stream_create();
+    for (int i = 0; i < 2; i++) { e->ev_stage[i] = bk_event_create(); e->ev_copied[i] = bk_event_create(); }
+    if (!e->packed_dev || !e->stage_dev[0] || !e->stage_dev[1] || !e->copy_stream || !e->ev_copied[1]) return fail(PGTG_ERR_CUDA, std::string("allocation failed: ") + bk_error());
+    e->stage_bytes = L.total;
+    e->dp.obs_packed = e->packed_dev;  // from now on the ticks also store the planes as bits
+  }
+  const int slot = (int)(e->host_steps & 1);
+  bk_h2d(e->actions_dev, actions, N * 4, stream);
+  int rc = pgtg_step(e, e->actions_dev, 4, stream);
+  if (rc) return rc;
+  // slot's previous copies (call k - 2) must have left the staging buffer
+  if (e->host_steps >= 2 && bk_stream_wait(stream, e->ev_copied[slot])) return fail(PGTG_ERR_CUDA, std::string("stream wait failed: ") + bk_error());
+  unsigned char* st = e->stage_dev[slot];
+  bk_d2d(st + L.packed, e->dp.obs_packed, (size_t)pgtg_packed_obs_bytes(e), stream);
+  bk_d2d(st + L.pos, e->dp.obs_position, 8 * N, stream); bk_d2d(st + L.vel, e->dp.obs_velocity, 8 * N, stream);
+  bk_d2d(st + L.reward, e->dp.reward, 8 * N, stream); bk_d2d(st + L.term, e->dp.terminated, N, stream); bk_d2d(st + L.trunc, e->dp.truncated, N, stream);
+  if (bk_event_record(e->ev_stage[slot], stream) || bk_stream_wait(e->copy_stream, e->ev_stage[slot])) return fail(PGTG_ERR_CUDA, std::string("event failed: ") + bk_error());
+  void* cs = e->copy_stream;
+  if (obs_packed) bk_d2h(obs_packed, st + L.packed, (size_t)pgtg_packed_obs_bytes(e), cs);
+  if (obs_position) bk_d2h(obs_position, st + L.pos, 8 * N, cs);
+  if (obs_velocity) bk_d2h(obs_velocity, st + L.vel, 8 * N, cs);
+  if (reward) bk_d2h(reward, st + L.reward, 8 * N, cs);
+  if (terminated) bk_d2h(terminated, st + L.term, N, cs);
+  if (truncated) bk_d2h(truncated, st + L.trunc, N, cs);
+  if (bk_event_record(e->ev_copied[slot], cs)) return fail(PGTG_ERR_CUDA, std::string("event failed: ") + bk_error());
+  e->host_steps++;
+  if (wait && bk_sync(cs)) return fail(PGTG_ERR_CUDA, std::string("step failed: ") + bk_error());
+  return PGTG_OK;
+}
+
+// wait for every copy of the host-buffer steps issued so far
+extern "C" int pgtg_host_sync(pgtg_env* e) {
+  if (!e) return fail(PGTG_ERR_INVALID, "null handle");
+  bk_set_device(e->device);
+  if (e->copy_stream && bk_sync(e->copy_stream)) return fail(PGTG_ERR_CUDA, std::string("copy failed: ") + bk_error());
+  return PGTG_OK;
+}
+
+// bits -> int8 cells on the host (callers that want the [N, C, P, P] planes back), `threads` worker threads
+#include <thread>
+extern "C" int pgtg_unpack_obs(const uint32_t* packed, int8_t* obs_map, int64_t n_cells, int threads) {
+  if (!packed || !obs_map || n_cells < 0) return fail(PGTG_ERR_INVALID, "null argument");
+  if (threads < 1) threads = 1;
+  auto work = [&](int64_t lo, int64_t hi) {  // [lo, hi) in units of 32 cells
+    for (int64_t w = lo; w < hi; w++) {
+      const uint32_t v = packed[w];
+      uint64_t* out = (uint64_t*)(obs_map + 32 * w);
+      for (int b = 0; b < 4; b++) {  // 8 bits -> 8 bytes: replicate the byte, keep bit k in byte k, normalise to 0 / 1
+        const uint64_t x = (v >> (8 * b)) & 255u;
+        out[b] = ((((x * 0x0101010101010101ull) & 0x8040201008040201ull) + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
+      }
+    }
+  };
+  const int64_t words = n_cells / 32;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) pool.emplace_back(work, words * t / threads, words * (t + 1) / threads);
+  for (auto& th : pool) th.join();
+  for (int64_t i = words * 32; i < n_cells; i++) obs_map[i] = (int8_t)((packed[i >> 5] >> (i & 31)) & 1u);
+  return PGTG_OK;
+}
+
 extern "C" int pgtg_reduce_stats(pgtg_env* e, void* stream) {
   if (!e) return fail(PGTG_ERR_INVALID, "null handle");
   bk_set_device(e->device);
@@ -782,6 +953,20 @@ extern "C" int pgtg_flatten(pgtg_env* e, const int32_t* plane_order, void* strea
   e->launches++;
   if (out_dev) *out_dev = e->flat;
   if (out_dim) *out_dim = dim;
+  return PGTG_OK;
+}
+
+// OR of every env's sticky error flags (1 tape overrun, 2 tape tag mismatch, 4 tape index out of range, 8 goal unreachable,
+// 16 no route at a spawn square, 32 more cars than max_cars, 64 no start square, 128 action outside 0..8). Synchronises.
+extern "C" int pgtg_error_summary(pgtg_env* e, uint32_t* out_flags) {
+  if (!e || !out_flags) return fail(PGTG_ERR_INVALID, "null argument");
+  bk_set_device(e->device);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
+  if (!e->info_dev && !(e->info_dev = dev_alloc<int32_t>(e, 7 * (size_t)e->dc.N))) return fail(PGTG_ERR_CUDA, std::string("device allocation failed: ") + bk_error());
+  if (bk_error_or(e, (uint32_t*)e->info_dev)) return fail(PGTG_ERR_CUDA, std::string("launch failed: ") + bk_error());
+  e->launches++;
+  bk_d2h(out_flags, e->info_dev, 4, nullptr);
+  if (bk_sync(nullptr)) return fail(PGTG_ERR_CUDA, std::string("device error: ") + bk_error());
   return PGTG_OK;
 }
 

@@ -77,6 +77,31 @@ static inline void pg_store_streaming32(void* ptr, uint2 a, uint2 b, uint2 c2, u
 #include "../../include/pgtg_b200.h"
 #include "pgtg_tables.h"
 
+// Warp-collective phases, written once for both builds. On the device the function body runs on every lane of a
+// warp (`l` = the lane), PG_FOR_LANES is empty and a per-lane variable is a register; the emulation runs the 32 lanes
+// of the warp as a loop around each per-lane block and keeps per-lane variables as arrays. Lanes exchange data only
+// through the collectives below or through shared memory, and collectives stand between per-lane blocks.
+#ifdef __CUDACC__
+#define PG_WARP_LANE const int l = (int)(threadIdx.x & 31u);
+#define PG_FOR_LANES
+#define PG_LV(type, name) type name
+#define LV(name) name
+#define PG_BALLOT(out, pred) out = __ballot_sync(0xffffffffu, (pred))
+#define PG_REDUCE_OR(out, expr) out = __reduce_or_sync(0xffffffffu, (uint32_t)(expr))
+#define PG_MATCH_ANY(name, expr) name = __match_any_sync(0xffffffffu, (uint32_t)(expr))
+#define PG_SYNCWARP() __syncwarp()
+#else
+#define PG_WARP_LANE
+#define PG_FOR_LANES for (int l = 0; l < 32; l++)
+#define PG_LV(type, name) type name[32]
+#define LV(name) name[l]
+#define PG_BALLOT(out, pred) { out = 0; for (int l = 0; l < 32; l++) if (pred) out |= 1u << l; }
+#define PG_REDUCE_OR(out, expr) { out = 0; for (int l = 0; l < 32; l++) out |= (uint32_t)(expr); }
+#define PG_MATCH_ANY(name, expr) { uint32_t k_[32]; for (int l = 0; l < 32; l++) k_[l] = (uint32_t)(expr); \
+    for (int l = 0; l < 32; l++) { uint32_t m_ = 0; for (int q = 0; q < 32; q++) if (k_[q] == k_[l]) m_ |= 1u << q; name[l] = m_; } }
+#define PG_SYNCWARP()
+#endif
+
 namespace pgtg {
 
 constexpr int TILE = 9;
@@ -154,6 +179,7 @@ struct DevCfg {
   // bit [compress(E) | S << conn_ne] = start and goal connected in the subgraph (E, S)
   int conn_bits, conn_ne;
   int path_tab;                 // 1: subgoal paths come from DevPtrs.path_table (T <= 16, same index as conn_table)
+  int eval_on, gamma_len;        // evaluator statistics (pgtg_set_evaluation): discounted returns with DevPtrs.gamma_pow
   int64_t env_id_base;
   uint64_t seed;
 };
@@ -199,6 +225,8 @@ struct DevPtrs {
   const uint8_t* tape_tags;
   uint32_t* error;      // [N] sticky
   double* ep_return;    // [N]
+  double* ep_disc;      // [N] running discounted return of the episode (evaluator statistics), or null
+  const double* gamma_pow;  // [gamma_len] pow(gamma, t) evaluated on the host
   // tables
   const uint16_t* fixed_tiles;  // [T] (fixed map)
   uint32_t fixed_plan;
@@ -211,6 +239,7 @@ struct DevPtrs {
   const uint64_t* path_table;   // [2^conn_bits] or null: 3-bit subgoal direction of every tile | ns << 48 | unreachable << 63
   const pgtg_rule* rules;
   // outputs
+  uint32_t* obs_packed;  // [ceil(N * obs_bits / 32)] the observation planes as bits (env i at bit i * obs_bits), or null
   int8_t* obs_map; int32_t* obs_position; int32_t* obs_velocity; int32_t* obs_nsd;
   double* reward; double* cost; uint8_t* terminated; uint8_t* truncated;
   int32_t* step_state; uint8_t* step_flags;

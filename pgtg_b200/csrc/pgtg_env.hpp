@@ -23,6 +23,8 @@ struct pgtg_env {
   size_t smem;
   int64_t launches;
   std::vector<void*> allocs;
+  struct StateAlloc { void* ptr; size_t bytes; };
+  std::vector<StateAlloc> state_allocs;  // everything pgtg_save_state / pgtg_copy_state must carry (SoA state, rings, queues, outputs)
   bool have_fixed, have_tape, did_reset;
   bool cars_injected;   // pgtg_set_state put cars into the handle: the lean tick is off for good
   int nblk;             // CTAs per launch
@@ -37,6 +39,8 @@ struct pgtg_env {
   bool timing; std::vector<void*> tev; int tev_used;
   // flattened observation (FlattenObservation view for SB3-style consumers), allocated on first use
   float* flat; int flat_dim; int flat_order[PGTG_MAX_CHANNELS];
+  // host-buffer steps: packed observation bits + staging for the double-buffered copies (allocated on first use)
+  uint32_t* packed_dev; unsigned char* stage_dev[2]; size_t stage_bytes; void* copy_stream; void* ev_stage[2]; void* ev_copied[2]; uint64_t host_steps;
   int32_t* info_dev;    // [7][N] scratch of pgtg_get_info, allocated on first use
   double* stats_rows;   // [nblk][8] per-CTA episode statistics (CUDA backend)
   // device scratch for reset arguments and host-buffer steps

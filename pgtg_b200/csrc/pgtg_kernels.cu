@@ -21,6 +21,9 @@ static void bk_free(void* p) { cudaFree(p); }
 static int bk_set_device(int d) { return ck(cudaSetDevice(d)); }
 static int bk_h2d(void* d, const void* s, size_t n, void* st) { return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, (cudaStream_t)st)); }
 static int bk_d2h(void* d, const void* s, size_t n, void* st) { return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st)); }
+static int bk_d2d(void* d, const void* s, size_t n, void* st) { return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, (cudaStream_t)st)); }
+static void* bk_stream_create() { cudaStream_t s; if (ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking))) return nullptr; return s; }
+static void bk_stream_destroy(void* s) { cudaStreamDestroy((cudaStream_t)s); }
 static int bk_memset(void* d, int v, size_t n) { return ck(cudaMemset(d, v, n)); }
 static int bk_memset_async(void* d, int v, size_t n, void* st) { return ck(cudaMemsetAsync(d, v, n, (cudaStream_t)st)); }
 static int bk_sync(void* st) { return ck(st ? cudaStreamSynchronize((cudaStream_t)st) : cudaDeviceSynchronize()); }
@@ -55,6 +58,7 @@ static int bk_stats_reduce(pgtg_env*, void* stream);
 static int bk_stats_reset(pgtg_env*, void* stream);
 static int bk_flatten(pgtg_env*, void* stream);
 static int bk_info(pgtg_env*, int32_t* out_dev);
+static int bk_error_or(pgtg_env*, uint32_t* out_dev);
 static int bk_conn_table_max_bits() { return 24; }
 static int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
 static int bk_build_path_table(pgtg_env*, uint64_t* table_dev);
@@ -81,6 +85,13 @@ __global__ void pgtg_build_conn_table_kernel(const __grid_constant__ DevCfg c, u
 }
 
 struct FlatOrder { int plane[PGTG_MAX_CHANNELS]; };
+
+__global__ void pgtg_error_or_kernel(const uint32_t* __restrict__ err, int n, uint32_t* __restrict__ out) {
+  uint32_t v = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v |= err[i];
+  v = __reduce_or_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
+}
 
 // get_info extras, one env per thread (tile descriptors read straight from HBM)
 __global__ void __launch_bounds__(128) pgtg_info_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int32_t* __restrict__ out) {
@@ -196,6 +207,11 @@ static int bk_build_path_table(pgtg_env* e, uint64_t* table_dev) {
   uint32_t total = 1u << e->dc.conn_bits;
   int blocks = (int)((total + B - 1) / B < 148u * 12u ? (total + B - 1) / B : 148u * 12u);
   pgtg::pgtg_build_path_table_kernel<<<blocks, B, smem>>>(e->dc, e->dp, table_dev);
+  return ck(cudaGetLastError());
+}
+static int bk_error_or(pgtg_env* e, uint32_t* out_dev) {
+  if (ck(cudaMemsetAsync(out_dev, 0, 4, nullptr))) return -1;
+  pgtg::pgtg_error_or_kernel<<<148 * 4, 256>>>(e->dp.error, e->dc.N, out_dev);
   return ck(cudaGetLastError());
 }
 static int bk_info(pgtg_env* e, int32_t* out_dev) {

@@ -407,6 +407,7 @@ struct StepResult {
   double reward, cost;
   int terminated, braking, outcome;  // outcome: 0 running, 1 crash, 2 final goal (3 truncated, set by phase_step)
   double ep_return;                  // return of the episode that just finished (phase_step)
+  double ep_disc;                    // ... and its discounted return (evaluator statistics, when enabled)
 };
 
 PG_HD bool visited_test_set(const DevCfg& c, const DevPtrs& p, int env, int x, int y, bool set) {

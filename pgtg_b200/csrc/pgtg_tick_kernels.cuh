@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
   bool done = false;
   if (MODE == MODE_STEP) {
     StepResult r;
-    r.outcome = 0; r.ep_return = 0;
+    r.outcome = 0; r.ep_return = 0; r.ep_disc = 0;
     int len = 0;
     EnvRegs er;  // lean instantiation: the env's registers stay in registers from step to emit
     if (valid) {
@@ -87,6 +87,12 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
         atomicAdd(&sh.counters[8], __popc(g)); atomicAdd(&sh.counters[9], __popc(cr)); atomicAdd(&sh.counters[10], __popc(tr));
         atomicAdd(&sh.counters[11], lsum); atomicAdd(&sh.counters[12], __popc(any));
         atomicAdd(&sh.dsum[0], rs);
+      }
+      if (c.eval_on) {  // evaluator statistics: sum of discounted returns, episodes with a negative one
+        const unsigned neg = __ballot_sync(0xffffffffu, done && r.ep_disc < 0);
+        double ds = r.ep_disc;
+        for (int o = 16; o > 0; o >>= 1) ds += __shfl_down_sync(0xffffffffu, ds, o);
+        if (lane == 0) { atomicAdd(&sh.dsum[1], ds); atomicAdd(&sh.counters[13], __popc(neg)); }
       }
     }
     if (LEAN || (PREGEN && !c.write_final_obs)) {
@@ -118,8 +124,9 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
         double* row = sa.rows + (size_t)blockIdx.x * STATS_STRIDE;
         row[0] += sh.counters[12]; row[1] += sh.dsum[0]; row[2] += sh.counters[11];
         row[3] += sh.counters[8]; row[4] += sh.counters[9]; row[5] += sh.counters[10];
+        if (c.eval_on) { row[6] += sh.dsum[1]; row[7] += sh.counters[13]; }
       }
-      phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid);
+      phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid, p.obs_packed);
       PG_CLK(8)
       return;
     }
@@ -129,6 +136,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
       if (!mask || mask[env]) {
         if (seeds) { p.key[env] = (uint64_t)seeds[env]; e.episode = 0; }
         p.ep_return[env] = 0.0;
+        if (p.ep_disc) p.ep_disc[env] = 0.0;
         done = true;
       }
       sh.regs[tid] = e;
@@ -150,6 +158,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
     double* row = sa.rows + (size_t)blockIdx.x * STATS_STRIDE;
     row[0] += n_done; row[1] += sh.dsum[0]; row[2] += sh.counters[11];
     row[3] += sh.counters[8]; row[4] += sh.counters[9]; row[5] += sh.counters[10];
+    if (c.eval_on) { row[6] += sh.dsum[1]; row[7] += sh.counters[13]; }
   }
   __syncthreads();
 
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
   }
   if (valid) phase_emit(c, p, sh, tid, env, false);
   __syncthreads();
-  phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid);
+  phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid, p.obs_packed);
 }
 
 // Map generation ahead of time: dense over the envs queued by the tick that just ran (every lane

@@ -43,23 +43,19 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
   __syncthreads();
   const int total = sh.off[G];
 
-  // ---- the cars: intents (flat), blocking in list order (per env), commit (flat) ----------------------------
+  // ---- the cars: intents (flat), then blocking in list order + commit (one env per warp) ---------------------
   for (int item = tid; item < total; item += NT) {
     const int g = sh.item_g[item];
     tk_intent(c, p, sh, g, item - sh.off[g], env0 + g);
   }
   __syncthreads();
-  if (mine && sh.env[tid].n_cars > 0) tk_resolve(c, sh, tid);
-  __syncthreads();
-  for (int item = tid; item < total; item += NT) {
-    const int g = sh.item_g[item];
-    tk_commit(c, p, sh, g, item - sh.off[g], env0 + g);
-  }
+  for (int g = tid >> 5; g < nvalid; g += NT >> 5)  // one env per warp, 32 cars per step
+    if (sh.env[g].n_cars > 0) tk_resolve_commit(c, p, sh, g, env0 + g);
   __syncthreads();
 
   // ---- the agent --------------------------------------------------------------------------------------
   StepResult r;
-  r.outcome = 0; r.ep_return = 0;
+  r.outcome = 0; r.ep_return = 0; r.ep_disc = 0;
   int len = 0;
   if (mine) { r = tk_agent(c, p, sh, tid, env); len = r.outcome ? (int)sh.env[tid].e.elapsed : 0; }
   const bool done = r.outcome != 0;
@@ -79,6 +75,12 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
         lbase = atomicAdd(&sh.counters[12], __popc(any));
         atomicAdd(&sh.dsum[0], rs);
         if (PREGEN) qbase = atomicAdd(p.regen_count + p.parity, (uint32_t)__popc(any));
+      }
+      if (c.eval_on) {
+        const unsigned neg = __ballot_sync(0xffffffffu, done && r.ep_disc < 0);
+        double ds = r.ep_disc;
+        for (int o = 16; o > 0; o >>= 1) ds += __shfl_down_sync(0xffffffffu, ds, o);
+        if (lane == 0) { atomicAdd(&sh.dsum[1], ds); atomicAdd(&sh.counters[13], __popc(neg)); }
       }
       qbase = __shfl_sync(0xffffffffu, qbase, 0);
       lbase = __shfl_sync(0xffffffffu, lbase, 0);
@@ -137,8 +139,9 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
     double* row = sa.rows + (size_t)blockIdx.x * STATS_STRIDE;
     row[0] += n_done; row[1] += sh.dsum[0]; row[2] += sh.counters[11];
     row[3] += sh.counters[8]; row[4] += sh.counters[9]; row[5] += sh.counters[10];
+    if (c.eval_on) { row[6] += sh.dsum[1]; row[7] += sh.counters[13]; }
   }
-  phase_expand(c, p.obs_map, bs, tid, NT, env0, nvalid);
+  phase_expand(c, p.obs_map, bs, tid, NT, env0, nvalid, p.obs_packed);
 }
 
 }  // namespace pgtg

@@ -26,8 +26,11 @@
 
 namespace pgtg {
 
-constexpr int TK_DESPAWN_CAP = 6;
-constexpr int TK_OCC_MIN = 40;  // fewer cars: "is a car there" scans the env's 16-bit square list instead
+#ifndef PGTG_TK_OCC_SAT
+#define PGTG_TK_OCC_SAT 15  /* tests/emu also builds a variant that saturates at 3 to exercise the exact-count fallback */
+#endif
+constexpr int TK_OCC_SAT = PGTG_TK_OCC_SAT;  // a 4-bit per-square counter is exact below this value; at it, sticky "unknown"
+constexpr int TK_OCC_MIN = 33;  // up to 32 cars the whole list is one warp step and needs no per-square counters
 
 // intent word: kind 0-1 | target square x 2-9, y 10-17 | route 18-22 | delay 23-24 | push 25 | profile 26-28 | moved 31
 enum : uint32_t { IK_STAY = 0, IK_LANE = 1, IK_ENTER = 2, IK_DESPAWN = 3, IK_PUSH = 1u << 25, IK_MOVED = 1u << 31 };
@@ -48,8 +51,7 @@ struct TEnv {
   uint32_t hist[5];              // their routes: 8-bit counter per route id
   int32_t hist_overflow;         // a route counter wrapped: the rule engine falls back to the list scan
   uint64_t bloom;                // 64-bit filter over the squares that hold (or held, this tick) a car: a clear bit = no car there
-  int32_t n_despawn;
-  uint16_t despawn[TK_DESPAWN_CAP];  // list slots of the cars that left the map, ascending
+  int32_t n_despawn;             // cars that leave the map in this tick (counted by the intent phase)
   int32_t done;                  // StepResult.outcome of this tick
   int32_t new_cars, num_positions, perm_h;  // initial traffic of the episode that starts in this tick
   uint32_t perm_keys[4];
@@ -115,24 +117,24 @@ PG_HD MapView tk_map(const DevCfg& c, const TkShared& sh, int g) {
   return m;
 }
 
-// ---- 4-bit occupancy counters (exact below 15; 15 is sticky and means "scan the list") ----------------
+// ---- 4-bit occupancy counters (exact below TK_OCC_SAT; at TK_OCC_SAT sticky = "count the list") ----------------
 PG_HD int occ4_index(const DevCfg& c, unsigned xy) { return (int)(xy & 255u) * c.HS + (int)(xy >> 8); }
 PG_HD int occ4_get(const uint32_t* o, int i) { return (int)((o[i >> 3] >> ((i & 7) * 4)) & 15u); }
 PG_HD void occ4_inc(uint32_t* o, int i) {
   const int sh = (i & 7) * 4;
-  if (((o[i >> 3] >> sh) & 15u) < 15u) o[i >> 3] += 1u << sh;
+  if (((o[i >> 3] >> sh) & 15u) < (uint32_t)TK_OCC_SAT) o[i >> 3] += 1u << sh;
 }
 PG_HD void occ4_dec(uint32_t* o, int i) {
   const int sh = (i & 7) * 4;
   const uint32_t v = (o[i >> 3] >> sh) & 15u;
-  if (v >= 1u && v < 15u) o[i >> 3] -= 1u << sh;
+  if (v >= 1u && v < (uint32_t)TK_OCC_SAT) o[i >> 3] -= 1u << sh;
 }
 PG_HD void occ4_inc_atomic(uint32_t* o, int i) {
   const int sh = (i & 7) * 4;
   uint32_t* w = o + (i >> 3);
   uint32_t old = *(volatile uint32_t*)w;
   for (;;) {
-    if (((old >> sh) & 15u) == 15u) return;
+    if (((old >> sh) & 15u) == (uint32_t)TK_OCC_SAT) return;
     const uint32_t seen = pg_atomic_cas(w, old, old + (1u << sh));
     if (seen == old) return;
     old = seen;
@@ -263,83 +265,127 @@ PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
       if (n == 0) pg_atomic_or(&t.e.err, 16u);
       else route = ld_route(sd, n > 1 ? (int)pg_umulhi(w1[CW_SPAWN_ROUTE & 3], (uint32_t)n) : 0);
       word = intent_pack(IK_DESPAWN, sx, sy, route, 0, false, prof);
+      pg_atomic_add(&t.n_despawn, 1);
     }
   }
   sh.intent[g * sh.MC + r] = word;
 }
 
-// ---- resolve: one env per thread, cars in list order (environment.py:944-965, 1121-1127) -------------------
-PG_HD void tk_resolve(const DevCfg& c, const TkShared& sh, int g) {
+// ---- resolve + commit: one env per WARP, 32 consecutive cars of its list per step --------------------------------
+// Blocking in list order (environment.py:944-965, 1121-1127): car r is blocked iff some other car stands on its target
+// square at ITS turn -- cars before it at their new squares (a replacement of a car that left the map included), cars
+// after it at their old squares. Chunk by chunk (32 cars = 32 lanes):
+//   count(r) = occ[T_r]                                   every car of the env at its current square (earlier chunks
+//                                                         already final, this chunk and later ones still old)
+//            + #{j < r in the chunk, moved: T_j == T_r}   arrived before r's turn
+//            - #{j < r in the chunk, moved: old_j == T_r} left before r's turn
+// Lanes whose target meets no old or target square of another lane of the chunk (a 64-bit filter over the chunk's old
+// squares, match_any over the targets) decide at once from occ; the few others are settled one by one in lane order
+// with three ballots each. Envs with <= 32 cars need no occ array: the chunk is the whole list and occ[T_r] is a ballot.
+// The chunk is then committed: live half -> other half of the car list, order-stable (a despawned car's replacement goes
+// to the end of the list: slot n - n_despawn + rank), counters updated with shared-memory atomics.
+PG_HD void occ4_dec_atomic(uint32_t* o, int i) {
+  const int sh = (i & 7) * 4;
+  uint32_t* w = o + (i >> 3);
+  uint32_t old = *(volatile uint32_t*)w;
+  for (;;) {
+    const uint32_t v = (old >> sh) & 15u;
+    if (v == 0u || v == (uint32_t)TK_OCC_SAT) return;
+    const uint32_t seen = pg_atomic_cas(w, old, old - (1u << sh));
+    if (seen == old) return;
+    old = seen;
+  }
+}
+
+PG_HD void tk_resolve_commit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env) {
+  PG_WARP_LANE
   TEnv& t = sh.env[g];
-  const int n = t.n_cars;
+  const int n = t.n_cars, nd_total = t.n_despawn;
   uint32_t* it = sh.intent + g * sh.MC;
   uint16_t* fx = sh.fxy + g * sh.MC;
   const bool use_occ = tk_use_occ(sh, n);
   uint32_t* occ = use_occ ? sh.occ + g * sh.occ_words : nullptr;
-  int nd = 0;
-  // 64-bit filter over every square that holds a car now or receives one during the pass (bits are never cleared):
-  // most targets hit a clear bit and need neither the list scan nor the counters
-  uint64_t bloom = 0;
-  for (int r = 0; r < n; r++) bloom |= bloom_bit(fx[r]);
-  for (int r = 0; r < n; r++) {
-    const uint32_t w = it[r];
-    const uint32_t kind = w & 3u;
-    if (kind == IK_STAY) continue;
-    const unsigned T = intent_xy(w);
-    if (kind == IK_LANE) {
-      // cars_on_next_position over the live list: earlier cars (and replacements) at their new squares, later
-      // ones at their old squares -- exactly what fx holds at this point
-      bool blocked = false;
-      if (bloom & bloom_bit(T)) {
-        if (use_occ) {
-          const int v = occ4_get(occ, occ4_index(c, T));
-          blocked = v == 15 ? tk_scan(fx, n, T) : v != 0;
-        } else blocked = tk_scan(fx, n, T);
-      }
-      if (blocked && !(w & IK_PUSH)) continue;
-      it[r] = w | IK_MOVED;
-    } else if (kind == IK_DESPAWN) {
-      if (nd < TK_DESPAWN_CAP) t.despawn[nd] = (uint16_t)r;
-      nd++;
+  const int half = misc_half(t.e.misc);
+  const uint64_t* A = car_list(c, p, env, half);
+  uint64_t* B = car_list(c, p, env, half ^ 1);
+  uint32_t bloom_lo = 0, bloom_hi = 0;  // filter over the final squares (the agent's collision test)
+  int nd_before = 0;
+  for (int b = 0; b < n; b += 32) {
+    PG_LV(uint32_t, w); PG_LV(unsigned, T); PG_LV(unsigned, old); PG_LV(int, moved); PG_LV(int, occv); PG_LV(uint32_t, same);
+    uint32_t old_lo, old_hi, inv;
+    PG_FOR_LANES {
+      const bool valid = b + l < n;
+      LV(w) = valid ? it[b + l] : (uint32_t)IK_STAY;
+      LV(T) = intent_xy(LV(w));
+      LV(old) = valid ? (unsigned)fx[b + l] : 0x1FFFFu;
+      const uint32_t kind = LV(w) & 3u;
+      LV(occv) = (use_occ && kind == IK_LANE) ? occ4_get(occ, occ4_index(c, LV(T))) : 0;
+      LV(moved) = kind == IK_ENTER || kind == IK_DESPAWN || (kind == IK_LANE && (LV(occv) == 0 || (LV(w) & IK_PUSH)));
     }
-    if (use_occ) { occ4_dec(occ, occ4_index(c, fx[r])); occ4_inc(occ, occ4_index(c, T)); }
-    fx[r] = (uint16_t)T;
-    bloom |= bloom_bit(T);
+    PG_REDUCE_OR(old_lo, b + l < n ? (uint32_t)bloom_bit(LV(old)) : 0u);
+    PG_REDUCE_OR(old_hi, b + l < n ? (uint32_t)(bloom_bit(LV(old)) >> 32) : 0u);
+    PG_MATCH_ANY(same, (LV(w) & 3u) != IK_STAY ? LV(T) : 0x20000u + (uint32_t)l);
+    const uint64_t old_bloom = (uint64_t)old_hi << 32 | old_lo;
+    PG_BALLOT(inv, (LV(w) & 3u) == IK_LANE && ((old_bloom & bloom_bit(LV(T))) != 0 || (LV(same) & (LV(same) - 1u)) != 0 || LV(occv) == TK_OCC_SAT));
+    while (inv) {  // the lanes whose turn order matters, in list order
+      const int rl = pg_ffs(inv) - 1;
+      inv &= inv - 1;
+      const unsigned Tr = intent_xy(it[b + rl]);
+      uint32_t occm, arrm, leftm;
+      PG_BALLOT(occm, LV(old) == Tr);
+      PG_BALLOT(arrm, l < rl && LV(moved) && LV(T) == Tr);
+      PG_BALLOT(leftm, l < rl && LV(moved) && LV(old) == Tr);
+      int base = (int)pg_popc(occm);
+      if (use_occ) {
+        base = occ4_get(occ, occ4_index(c, Tr));
+        if (base == TK_OCC_SAT) {  // counter saturated: count the list itself (chunks before this one final, the rest old)
+          base = 0;
+          for (int jb = 0; jb < n; jb += 32) { uint32_t m; PG_BALLOT(m, jb + l < n && (unsigned)fx[jb + l] == Tr); base += (int)pg_popc(m); }
+        }
+      }
+      const bool blocked = base + (int)pg_popc(arrm) - (int)pg_popc(leftm) > 0;
+      PG_FOR_LANES { if (l == rl) LV(moved) = !blocked || (LV(w) & IK_PUSH) != 0; }
+    }
+    uint32_t desm, fin_lo, fin_hi;
+    PG_BALLOT(desm, (LV(w) & 3u) == IK_DESPAWN);
+    PG_FOR_LANES {
+      const int r = b + l;
+      if (r < n) {
+        const uint32_t kind = LV(w) & 3u;
+        const unsigned fin = LV(moved) ? LV(T) : LV(old);
+        if (LV(moved)) {
+          fx[r] = (uint16_t)fin;
+          if (use_occ) { occ4_dec_atomic(occ, occ4_index(c, LV(old))); occ4_inc_atomic(occ, occ4_index(c, fin)); }
+        }
+        Car car = car_unpack(A[r]);
+        const int before = nd_before + (int)pg_popc(desm & ((1u << l) - 1u));  // cars ahead of r that left the map
+        int slot;
+        if (kind == IK_DESPAWN) {  // its replacement (_spawn_new_car, :970-1002) goes to the end of the list
+          slot = n - nd_total + before;
+          car.id = t.e.next_car_id + (unsigned)before;
+          car.route = intent_route(LV(w)); car.profile = intent_profile(LV(w)); car.patience = 0; car.delay = 0;
+        } else {
+          slot = r - before;
+          car.delay = intent_delay(LV(w));
+          if (LV(moved)) { car.patience = 0; car.route = intent_route(LV(w)); }
+          else car.patience++;
+        }
+        car.x = (int)(fin & 255u); car.y = (int)(fin >> 8);
+        B[slot] = car_pack(car);
+        if (c.num_rules > 0 && car.x / TILE == t.tile_x && car.y / TILE == t.tile_y) {  // the rule engine's view of the agent's tile
+          pg_atomic_add(&t.in_tile, 1);
+          const uint32_t prev = pg_atomic_add(&t.hist[car.route >> 2], 1u << (8 * (car.route & 3)));
+          if (((prev >> (8 * (car.route & 3))) & 255u) == 255u) t.hist_overflow = 1;  // > 255 cars of one route in one tile
+        }
+      }
+    }
+    PG_REDUCE_OR(fin_lo, b + l < n ? (uint32_t)bloom_bit(LV(moved) ? LV(T) : LV(old)) : 0u);
+    PG_REDUCE_OR(fin_hi, b + l < n ? (uint32_t)(bloom_bit(LV(moved) ? LV(T) : LV(old)) >> 32) : 0u);
+    bloom_lo |= fin_lo; bloom_hi |= fin_hi;
+    nd_before += (int)pg_popc(desm);
+    PG_SYNCWARP();  // the next chunk reads the counters this one updated
   }
-  t.n_despawn = nd;
-  t.bloom = bloom;
-}
-
-// ---- commit: one car per thread; live half -> other half, order-stable ------------------------------------------
-PG_HD void tk_commit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int r, int env) {
-  TEnv& t = sh.env[g];
-  const uint32_t* it = sh.intent + g * sh.MC;
-  const uint32_t w = it[r];
-  const uint32_t kind = w & 3u;
-  const int half = misc_half(t.e.misc), n = t.n_cars, nd = t.n_despawn;
-  Car car = car_unpack(car_list(c, p, env, half)[r]);
-  int before = 0;  // cars ahead of r that left the map
-  if (nd <= TK_DESPAWN_CAP) { for (int k = 0; k < nd; k++) before += t.despawn[k] < r; }
-  else { for (int j = 0; j < r; j++) before += (it[j] & 3u) == IK_DESPAWN; }
-  const unsigned fxy = sh.fxy[g * sh.MC + r];
-  int slot;
-  if (kind == IK_DESPAWN) {
-    slot = n - nd + before;
-    car.id = t.e.next_car_id + (unsigned)before;
-    car.route = intent_route(w); car.profile = intent_profile(w); car.patience = 0; car.delay = 0;
-  } else {
-    slot = r - before;
-    car.delay = intent_delay(w);
-    if (kind == IK_ENTER || (w & IK_MOVED)) { car.patience = 0; car.route = intent_route(w); }
-    else car.patience++;
-  }
-  car.x = (int)(fxy & 255u); car.y = (int)(fxy >> 8);
-  car_list(c, p, env, half ^ 1)[slot] = car_pack(car);
-  if (c.num_rules > 0 && car.x / TILE == t.tile_x && car.y / TILE == t.tile_y) {
-    pg_atomic_add(&t.in_tile, 1);
-    const uint32_t old = pg_atomic_add(&t.hist[car.route >> 2], 1u << (8 * (car.route & 3)));
-    if (((old >> (8 * (car.route & 3))) & 255u) == 255u) t.hist_overflow = 1;  // > 255 cars of one route in one tile
-  }
+  PG_FOR_LANES { if (l == 0) t.bloom = (uint64_t)bloom_hi << 32 | bloom_lo; }
 }
 
 // ---- the agent's part of the tick: one env per thread -----------------------------------------------------
@@ -373,7 +419,7 @@ struct ExtTraffic {
     const uint16_t* fx = sh->fxy + g * sh->MC;
     if (tk_use_occ(*sh, n_cars)) {
       const int v = occ4_get(sh->occ + g * sh->occ_words, occ4_index(c, xy));
-      return v == 15 ? tk_scan(fx, n_cars, xy) : v != 0;
+      return v == TK_OCC_SAT ? tk_scan(fx, n_cars, xy) : v != 0;
     }
     return tk_scan(fx, n_cars, xy);
   }

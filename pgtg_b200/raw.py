@@ -114,6 +114,53 @@ class RawEnv:
         _lib.check(self.lib, self.lib.pgtg_flatten(self._h, order.ctypes.data, stream, C.byref(ptr), C.byref(dim)))
         return ptr.value, dim.value
 
+    # -- checkpoint / clone / evaluation / host-buffer steps ----------------------------------------------
+    def save_state(self) -> np.ndarray:
+        """Everything a tick reads or writes, as one host blob (pgtg_save_state)."""
+        n = int(self.lib.pgtg_state_bytes(self._h))
+        blob = np.empty(n, np.uint8)
+        _lib.check(self.lib, self.lib.pgtg_save_state(self._h, blob.ctypes.data, n))
+        return blob
+
+    def load_state(self, blob: np.ndarray):
+        b = np.ascontiguousarray(blob, np.uint8)
+        _lib.check(self.lib, self.lib.pgtg_load_state(self._h, b.ctypes.data, b.nbytes))
+
+    def copy_state_from(self, other: "RawEnv"):
+        _lib.check(self.lib, self.lib.pgtg_copy_state(self._h, other._h))
+
+    def set_evaluation(self, gamma: float, max_steps: int):
+        _lib.check(self.lib, self.lib.pgtg_set_evaluation(self._h, float(gamma), int(max_steps)))
+
+    def error_summary(self) -> int:
+        v = C.c_uint32()
+        _lib.check(self.lib, self.lib.pgtg_error_summary(self._h, C.byref(v)))
+        return int(v.value)
+
+    def packed_obs_bytes(self) -> int:
+        return int(self.lib.pgtg_packed_obs_bytes(self._h))
+
+    def step_host_packed(self, actions, obs_packed=None, obs_position=None, obs_velocity=None, reward=None, terminated=None,
+                         truncated=None, wait: bool = True, stream: int = 0):
+        a = np.ascontiguousarray(actions, np.int32)
+        assert a.shape == (self.N,)
+        self._keep = [a]  # (the copy of the actions is asynchronous)
+        ptr = lambda x: None if x is None else x.ctypes.data  # noqa: E731
+        _lib.check(self.lib, self.lib.pgtg_step_host_packed(self._h, a.ctypes.data, ptr(obs_packed), ptr(obs_position), ptr(obs_velocity),
+                                                            ptr(reward), ptr(terminated), ptr(truncated), int(bool(wait)), stream))
+
+    def host_sync(self):
+        _lib.check(self.lib, self.lib.pgtg_host_sync(self._h))
+
+    def unpack_obs(self, obs_packed: np.ndarray, out: np.ndarray | None = None, threads: int = 0) -> np.ndarray:
+        """bits -> int8 [N, C, P, P] on the host (multithreaded)."""
+        import os
+
+        if out is None:
+            out = np.empty((self.N, self.C, self.P, self.P), np.int8)
+        _lib.check(self.lib, self.lib.pgtg_unpack_obs(obs_packed.ctypes.data, out.ctypes.data, out.size, threads or (os.cpu_count() or 1)))
+        return out
+
     def set_overlap(self, on: bool):
         _lib.check(self.lib, self.lib.pgtg_set_overlap(self._h, int(bool(on))))
 

@@ -84,6 +84,8 @@ class PGTGVectorEnv:
         self.device = torch.device("cuda", self.device_index)
         if conformance_draws is not None:
             kwargs["rng_mode"] = RNG_TAPE
+        self._ctor = (num_envs, map_path, dict(kwargs))
+        self._shadow = None
         self.hc: HostConfig = make_config(map_path, num_envs=num_envs, **kwargs)
         self.num_envs = num_envs
         with torch.cuda.device(self.device):
@@ -180,6 +182,95 @@ class PGTGVectorEnv:
             self.raw.step_device(ptr, nbytes, self._stream())
         return self._observation(), self._t["reward"], self._terminated, self._truncated, self._info()
 
+    # ---- full-state checkpoint / clone (PGTGEnv.light_step, environment.py:1283-1299) ---------------------
+    def save_state(self) -> np.ndarray:
+        """Everything a tick reads or writes (SoA state, map rings and request queues, car lists with patience /
+        delay, RNG state, light counters, consumed subgoals, episode statistics, outputs) as one host blob.
+        Unlike the reference's `set_to_state` (quirk A.3-10) nothing is left out."""
+        with torch.cuda.device(self.device):
+            return self.raw.save_state()
+
+    def load_state(self, blob: np.ndarray) -> None:
+        with torch.cuda.device(self.device):
+            self.raw.load_state(blob)
+        self._was_reset = True
+
+    def clone(self) -> "PGTGVectorEnv":
+        """A second env in exactly this env's state (device-to-device copy), `copy.deepcopy(env)` of the reference."""
+        if self.hc.pod.rng_mode == RNG_TAPE:
+            raise NotImplementedError("clone() of a conformance-tape env is not supported")
+        num_envs, map_path, kwargs = self._ctor
+        other = PGTGVectorEnv(num_envs, map_path, device=self.device, **kwargs)
+        with torch.cuda.device(self.device):
+            if len(self.hc.rules) != len(other.hc.rules) or any(a is not b and a != b for a, b in zip(self.hc.rules, other.hc.rules)):
+                other.hc.rules = [dict(r) for r in self.hc.rules]
+                other.raw.update_rules(other.hc.rules)
+            other.raw.copy_state_from(self.raw)
+        other._was_reset = self._was_reset
+        return other
+
+    def light_step(self, actions):
+        """PGTGEnv.light_step (environment.py:1283-1299): copy the env and execute one step on the copy; this env
+        stays unchanged. The copy is kept and re-synchronised on every call. Returns the copy's step outputs."""
+        if not self._was_reset:
+            raise RuntimeError("light_step() called before reset()")
+        if self._shadow is None:
+            self._shadow = self.clone()
+        else:
+            with torch.cuda.device(self.device):
+                self._shadow.raw.copy_state_from(self.raw)
+        return self._shadow.step(actions)
+
+    # ---- evaluator (pgtg/evaluator.py:284-339) --------------------------------------------------------------
+    def evaluate(self, policy, number: int, max_steps: int = 100, GAMMA: float = 0.99):
+        """ModularEvaluator.evaluate over the batch: run `policy(observation) -> actions` until at least `number`
+        episodes have finished, at most `max_steps` steps each, discounting rewards with GAMMA ** t on the device.
+        Returns (mean discounted return, (terminated, truncated, over max_steps, negative return)) -- the reference
+        returns the list of returns; here the mean is reduced on the device. PGTGEnv never sets `truncated` itself,
+        so that counter stays 0 and the episode cap shows up as "over max_steps"."""
+        with torch.cuda.device(self.device):
+            self.raw.set_evaluation(GAMMA, max_steps)
+        obs, _ = self.reset()
+        self.episode_stats(reset=True, all_reduce=False)
+        done = 0.0
+        while done < number:
+            for _ in range(max(1, min(max_steps, 8))):
+                obs, _, _, _, _ = self.step(policy(obs))
+            with torch.cuda.device(self.device):
+                _check(self.raw, self.raw.lib.pgtg_reduce_stats(self.raw._h, self._stream()))
+            done = float(self._t["stats"][0].item())
+        st = self.episode_stats(all_reduce=False)
+        with torch.cuda.device(self.device):
+            self.raw.set_evaluation(0.0, 0)
+        n = max(st["episodes"], 1.0)
+        return st["discounted_return_sum"] / n, (int(st["goals"] + st["crashes"]), 0, int(st["truncations"]), int(st["negative_returns"]))
+
+    # ---- host-buffer steps --------------------------------------------------------------------------------
+    def packed_host_buffers(self, pinned: bool = True) -> dict:
+        """Host buffers for `step_host_packed` (pinned by default: the copies are asynchronous)."""
+        N = self.num_envs
+        mk = (lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()) if pinned else (lambda shape, dt: torch.empty(shape, dtype=dt).numpy())
+        return dict(obs_packed=mk((self.raw.packed_obs_bytes() // 4,), torch.int32).view(np.uint32), obs_position=mk((N, 2), torch.int32),
+                    obs_velocity=mk((N, 2), torch.int32), reward=mk((N,), torch.float64), terminated=mk((N,), torch.uint8), truncated=mk((N,), torch.uint8))
+
+    def step_host_packed(self, actions: np.ndarray, out: dict | None = None, wait: bool = False) -> dict:
+        """The tick through HOST buffers with the observation planes as BITS (92 B per env instead of 729 at the
+        defaults) and double-buffered copies: with wait=False the call returns once everything is enqueued and the
+        buffers are complete after `host_sync()`; alternate two buffer sets to overlap tick k + 1 with the copies of
+        tick k. `unpack_obs` turns the bits back into the int8 [N, C, P, P] planes on the host."""
+        if out is None:
+            out = self.packed_host_buffers(pinned=False)
+            wait = True
+        with torch.cuda.device(self.device):
+            self.raw.step_host_packed(actions, stream=self._stream(), wait=wait, **out)
+        return out
+
+    def host_sync(self) -> None:
+        self.raw.host_sync()
+
+    def unpack_obs(self, obs_packed: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        return self.raw.unpack_obs(obs_packed, out)
+
     def step_host(self, actions: np.ndarray, out: dict | None = None) -> dict:
         """The same tick through HOST buffers (`pgtg_step_host`): copies in and out inside the call.
         This is the entry a non-CUDA consumer (the reference-facing plugin boundary) uses."""
@@ -230,6 +321,9 @@ class PGTGVectorEnv:
             json.dump(plan, f, ensure_ascii=False, indent=4)
 
     def close(self):
+        if self._shadow is not None:
+            self._shadow.close()
+            self._shadow = None
         self.raw.close()
 
     # ---- reference extras ------------------------------------------------------------------------
@@ -253,15 +347,35 @@ class PGTGVectorEnv:
         """Host snapshot of every env (the tensors behind PGTGEnv.get_info, environment.py:1538)."""
         return self.raw.get_state()
 
+    def get_info_arrays(self) -> dict:
+        """The computed parts of PGTGEnv.get_info (environment.py:1538-1578) for every env, as arrays:
+        agent_direction (index into AGENT_DIRECTIONS, :185-206), current_tile_type (exits N|E<<1|S<<2|W<<3,
+        :1541-1549), profile_counts [N, 5] (get_driver_profile_stats, :1017-1035). Synchronises."""
+        with torch.cuda.device(self.device):
+            return self.raw.get_info()
+
     def get_info_dicts(self) -> list[dict]:
-        """Per-env dicts shaped like PGTGEnv.get_info() (debugging aid; synchronises)."""
+        """Per-env dicts shaped like PGTGEnv.get_info() (environment.py:1538-1578; debugging aid, synchronises).
+        `traffic_rules.triggered_rules` is not kept per rule: `braking_applied` says whether any rule fired."""
         st = self.raw.get_state()
+        with torch.cuda.device(self.device):
+            extra = self.raw.get_info()
+        flags = self._t["step_flags"].cpu().numpy()
+        configured = {n: float(p) * 100 for n, p in zip(PROFILE_NAMES, np.diff(np.concatenate([[0.0], list(self.hc.pod.profile_cdf)])))}
         out = []
         for i in range(self.num_envs):
             cars = [dict(id=int(c[0]), x=int(c[1]), y=int(c[2]), route=ROUTE_NAMES[c[3]], driver_profile=PROFILE_NAMES[c[4]],
                          patience_counter=int(c[5])) for c in st["cars"][i, : st["num_cars"][i]]]
+            tt = int(extra["current_tile_type"][i])
+            counts = {n: int(v) for n, v in zip(PROFILE_NAMES, extra["profile_counts"][i])}
+            total = int(st["num_cars"][i])
+            stats = dict(counts=counts, percentages={k: (v / total) * 100 if total else 0 for k, v in counts.items()}, total_cars=total,
+                         configured_percentages=configured)
             out.append(dict(x=int(st["agent"][i, 0]), y=int(st["agent"][i, 1]), x_velocity=int(st["agent"][i, 2]),
-                            y_velocity=int(st["agent"][i, 3]), flat_tire=bool(st["flat_tire"][i]), cars=cars))
+                            y_velocity=int(st["agent"][i, 3]), flat_tire=bool(st["flat_tire"][i]),
+                            current_tile_type="".join(str((tt >> k) & 1) for k in range(4)), cars=cars, driver_profile_stats=stats,
+                            traffic_rules=dict(active_rules=[r["name"] for r in self.hc.rules], braking_applied=bool(flags[i] & 2),
+                                               agent_direction=AGENT_DIRECTIONS[int(extra["agent_direction"][i])])))
         return out
 
     def set_to_state(self, agent=None, flat_tire=None, num_cars=None, cars=None):
@@ -283,9 +397,16 @@ class PGTGVectorEnv:
                 torch.distributed.all_reduce(s)
             if reset:
                 _check(self.raw, self.raw.lib.pgtg_reset_stats(self.raw._h, self._stream()))
+            flags = self.raw.error_summary()
+        if flags:
+            names = {1: "conformance tape overrun", 2: "conformance tape tag mismatch", 4: "conformance index out of range", 8: "goal unreachable",
+                     16: "no route at a spawn square", 32: "more cars than max_cars", 64: "no start square",
+                     128: "an action outside 0..8 was replaced by the no-op 4 (the reference raises KeyError)"}
+            raise RuntimeError("env error flags: " + "; ".join(v for k, v in names.items() if flags & k))
         v = s.cpu().tolist()
         n = max(v[0], 1.0)
-        return dict(episodes=v[0], mean_return=v[1] / n, mean_length=v[2] / n, goals=v[3], crashes=v[4], truncations=v[5])
+        return dict(episodes=v[0], mean_return=v[1] / n, mean_length=v[2] / n, goals=v[3], crashes=v[4], truncations=v[5],
+                    discounted_return_sum=v[6], negative_returns=v[7])
 
     def launch_count(self) -> int:
         return self.raw.launch_count()

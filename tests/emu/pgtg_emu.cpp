@@ -17,6 +17,9 @@ static void bk_free(void* p) { free(p); }
 static int bk_set_device(int) { return 0; }
 static int bk_h2d(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
 static int bk_d2h(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
+static int bk_d2d(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
+static void* bk_stream_create() { return malloc(1); }
+static void bk_stream_destroy(void* s) { free(s); }
 static int bk_memset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
 static int bk_memset_async(void* d, int v, size_t n, void*) { memset(d, v, n); return 0; }
 static int bk_sync(void*) { return 0; }
@@ -36,6 +39,7 @@ static int bk_stats_reduce(pgtg_env*, void*);
 static int bk_stats_reset(pgtg_env*, void*);
 static int bk_flatten(pgtg_env*, void*);
 static int bk_info(pgtg_env*, int32_t*);
+static int bk_error_or(pgtg_env*, uint32_t*);
 static int bk_conn_table_max_bits() { return 13; }  // CPU tests: tables up to 8192 entries (e.g. 3x3 maps)
 static int bk_build_conn_table(pgtg_env*, uint32_t*);
 static int bk_build_path_table(pgtg_env*, uint64_t*);
@@ -62,6 +66,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
         sh.done_list[n_done++] = t;
         st[0] += 1; st[1] += r.ep_return; st[2] += sh.regs[t].elapsed;
         st[3] += r.outcome == 2; st[4] += r.outcome == 1; st[5] += r.outcome == 3;
+        if (c.eval_on) { st[6] += r.ep_disc; st[7] += r.ep_disc < 0; }
       }
     }
     if (c.write_final_obs && n_done) {
@@ -76,6 +81,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
       if (!mask || mask[env]) {
         if (seeds) { p.key[env] = (uint64_t)seeds[env]; sh.regs[t].episode = 0; }
         p.ep_return[env] = 0;
+        if (p.ep_disc) p.ep_disc[env] = 0;
         sh.done_list[n_done++] = t;
       }
     }
@@ -100,7 +106,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
     else phase_reset<RNG, TMAX, false>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
   }
   for (int t = 0; t < nvalid; t++) phase_emit<LEAN>(c, p, sh, t, env0 + t, false);
-  for (int t = 0; t < B; t++) phase_expand(c, p.obs_map, sh, t, B, env0, nvalid);
+  for (int t = 0; t < B; t++) phase_expand(c, p.obs_map, sh, t, B, env0, nvalid, p.obs_packed);
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
 }
 
@@ -144,9 +150,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
   const int total = sh.off[G];
   for (int t = 0; t < NT; t++)
     for (int item = t; item < total; item += NT) { int g = sh.item_g[item]; tk_intent(c, p, sh, g, item - sh.off[g], env0 + g); }
-  for (int g = 0; g < nvalid; g++) if (sh.env[g].n_cars > 0) tk_resolve(c, sh, g);
-  for (int t = 0; t < NT; t++)
-    for (int item = t; item < total; item += NT) { int g = sh.item_g[item]; tk_commit(c, p, sh, g, item - sh.off[g], env0 + g); }
+  for (int g = 0; g < nvalid; g++) if (sh.env[g].n_cars > 0) tk_resolve_commit(c, p, sh, g, env0 + g);
   int n_done = 0;
   double st[8] = {0};
   for (int g = 0; g < nvalid; g++) {
@@ -155,6 +159,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
       sh.done_list[n_done++] = g;
       st[0] += 1; st[1] += r.ep_return; st[2] += sh.env[g].e.elapsed;
       st[3] += r.outcome == 2; st[4] += r.outcome == 1; st[5] += r.outcome == 3;
+      if (c.eval_on) { st[6] += r.ep_disc; st[7] += r.ep_disc < 0; }
       if (PREGEN) {
         uint2 q; q.x = (uint32_t)(env0 + g); q.y = sh.env[g].e.episode + 3u;
         p.regen_list[(size_t)p.parity * 2 * c.N + p.regen_count[p.parity]++] = q;
@@ -184,7 +189,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
       for (int item = t; item < total2; item += NT) { int g = sh.item_g[item]; tk_new_car(c, p, sh, g, item - sh.off2[g], env0 + g); }
   }
   for (int g = 0; g < nvalid; g++) tk_emit(c, p, sh, g, env0 + g, false);
-  for (int t = 0; t < NT; t++) phase_expand(c, p.obs_map, bs, t, NT, env0, nvalid);
+  for (int t = 0; t < NT; t++) phase_expand(c, p.obs_map, bs, t, NT, env0, nvalid, p.obs_packed);
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
 }
 
@@ -243,6 +248,7 @@ extern "C" int pgtg_observe(pgtg_env* e, void* stream) {
 static int bk_stats_reduce(pgtg_env*, void*) { return 0; }
 static int bk_stats_reset(pgtg_env* e, void*) { memset(e->dp.stats, 0, 64); return 0; }
 
+static int bk_error_or(pgtg_env* e, uint32_t* out) { uint32_t v = 0; for (int i = 0; i < e->dc.N; i++) v |= e->dp.error[i]; *out = v; return 0; }
 static int bk_info(pgtg_env* e, int32_t* out) {
   Lut lut;
   BlockShared sh;

@@ -32,9 +32,13 @@ class NativeAdapter:
     through torch tensors made from the library's DLPack capsules."""
 
     def __init__(self, backend: str, **kwargs):
+        lib_path = None
+        if backend.startswith("emu"):  # "emu", or "emu_sat3": the variant whose per-square car counters saturate at 3
+            lib_path = build_emu().replace("libpgtg_emu.so", f"libpgtg_{backend}.so")
+            backend = "emu"
         self.backend = backend
         self.hc = make_config(**kwargs)
-        self.raw = RawEnv(self.hc, device=0, lib_path=build_emu() if backend == "emu" else None)
+        self.raw = RawEnv(self.hc, device=0, lib_path=lib_path)
         self.N, self.C, self.P = self.raw.N, self.raw.C, self.raw.P
         self._torch = {}
         if backend == "cuda":

@@ -34,7 +34,7 @@ def test_cuda_library_exports_every_declared_symbol():
     from pgtg_b200 import _lib
 
     assert set(_lib.EXPORTS) == set(declared_functions())
-    assert _lib.load().pgtg_abi_version() == 1
+    assert _lib.load().pgtg_abi_version() == 2
 
 
 def test_config_struct_layout_matches_c(tmp_path):

@@ -35,3 +35,17 @@ def test_traffic_tick_matches_oracle(name, final_obs):
     pc.compare(env, ora, ticks, state_every=10, stay=stay, final_obs=final_obs)
     env.close()
     ora.close()
+
+
+@pytest.mark.parametrize("name", ["crossing_full", "ring_dense_lights", "aggressive_push", "big_8x8_idle"])
+def test_traffic_tick_counter_saturation_fallback(name):
+    """The same against a build whose per-square counters saturate at 3 cars: squares with piled-up cars take the
+    exact-count fallback of the ordered pass and of the agent's collision test."""
+    kw, n, ticks, stay = pc.TRAFFIC_CONFIGS[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = NativeAdapter("emu_sat3", num_envs=n, seed=78, final_observation=True, **kw)
+        ora = OracleVectorEnv(num_envs=n, seed=78, final_observation=True, **kw)
+    pc.compare(env, ora, ticks, state_every=10, stay=stay)
+    env.close()
+    ora.close()

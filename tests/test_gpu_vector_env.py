@@ -169,3 +169,95 @@ def test_conformance_draws_constructor():
         obs, rew, term, trunc, _ = env.step(torch.from_numpy(tr["actions"][t]).cuda())
         assert np.array_equal(rew.cpu().numpy(), tr["reward"][t]) and np.array_equal(obs["map"]["walls"].cpu().numpy(), tr["obs_map"][t + 1][:, 0])
     env.close()
+
+
+@pytest.mark.gpu
+def test_clone_and_light_step_leave_the_env_unchanged():
+    """PGTGEnv.light_step (environment.py:1283-1299): a copy steps, the original does not; a clone is an exact twin."""
+    import torch
+    from pgtg_b200 import PGTGVectorEnv
+
+    n = 2048
+    env = PGTGVectorEnv(n, seed=21, traffic_density=0.1, random_map_obstacle_probability=0.3)
+    env.reset()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    acts = [torch.randint(0, 9, (n,), device="cuda", dtype=torch.int32, generator=g) for _ in range(6)]
+    for a in acts[:3]:
+        env.step(a)
+    before = env.get_state()
+    obs_l, rew_l, term_l, _, _ = env.light_step(acts[3])
+    obs_l = {"position": obs_l["position"].clone(), "walls": obs_l["map"]["walls"].clone(), "traffic": obs_l["map"]["traffic"].clone()}
+    rew_l, term_l = rew_l.clone(), term_l.clone()
+    after = env.get_state()
+    for k in ("agent", "cars", "num_cars", "tiles", "elapsed"):
+        assert (before[k] == after[k]).all(), k  # the original did not move
+    twin = env.clone()
+    obs, rew, term, _, _ = env.step(acts[3])       # now the real step: identical to what light_step predicted
+    assert torch.equal(rew, rew_l) and torch.equal(term, term_l) and torch.equal(obs["position"], obs_l["position"])
+    assert torch.equal(obs["map"]["walls"], obs_l["walls"]) and torch.equal(obs["map"]["traffic"], obs_l["traffic"])
+    obs_t, rew_t, _, _, _ = twin.step(acts[3])
+    assert torch.equal(rew, rew_t) and torch.equal(obs["map"]["traffic"], obs_t["map"]["traffic"])
+    env.close(); twin.close()
+
+
+@pytest.mark.gpu
+def test_evaluate_matches_the_reference_evaluator_bookkeeping():
+    import torch
+    from pgtg_b200 import PGTGVectorEnv
+
+    n = 4096
+    env = PGTGVectorEnv(n, seed=5, random_map_obstacle_probability=0.3)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    policy = lambda obs: torch.randint(3, 6, (n,), device="cuda", dtype=torch.int32, generator=g)  # noqa: E731
+    mean_ret, (terminated, truncated, over, negative) = env.evaluate(policy, number=5000, max_steps=9, GAMMA=0.95)
+    assert terminated + over >= 5000 and truncated == 0 and over > 0 and 0 < negative <= terminated + over
+    assert -100.0 <= mean_ret <= 100.0
+    assert env.episode_stats()["episodes"] >= 5000
+    env.close()
+
+
+@pytest.mark.gpu
+def test_scalar_seed_is_offset_by_the_shard_base():
+    """reset(seed=S) on a shard seeds env i with S + env_id_base + i: two half shards == one full handle."""
+    import torch
+    from pgtg_b200 import PGTGVectorEnv
+
+    kw = dict(rng_mode="numpy", traffic_density=0.05)
+    full = PGTGVectorEnv(256, **kw)
+    lo, hi = PGTGVectorEnv(128, env_id_base=0, **kw), PGTGVectorEnv(128, env_id_base=128, **kw)
+    of, _ = full.reset(seed=77)
+    ol, _ = lo.reset(seed=77)
+    oh, _ = hi.reset(seed=77)
+    a = torch.randint(0, 9, (256,), device="cuda", dtype=torch.int32)
+    for _ in range(5):
+        of, rf, _, _, _ = full.step(a)
+        ol, rl, _, _, _ = lo.step(a[:128])
+        oh, rh, _, _, _ = hi.step(a[128:])
+        assert torch.equal(rf, torch.cat([rl, rh])) and torch.equal(of["map"]["walls"], torch.cat([ol["map"]["walls"], oh["map"]["walls"]]))
+        assert torch.equal(of["map"]["traffic"], torch.cat([ol["map"]["traffic"], oh["map"]["traffic"]]))
+    assert not torch.equal(ol["map"]["walls"], oh["map"]["walls"])
+    full.close(); lo.close(); hi.close()
+
+
+@pytest.mark.gpu
+def test_info_is_a_mapping_and_info_dicts_carry_the_reference_fields():
+    import torch
+    from pgtg_b200 import PGTGVectorEnv
+
+    env = PGTGVectorEnv(64, seed=1, traffic_density=0.2, final_observation=True)
+    env.reset()
+    _, _, _, _, info = env.step(torch.full((64,), 4, device="cuda", dtype=torch.int32))
+    copied = dict(info)
+    assert copied["flat_tire"] is not None and copied["braking_applied"].dtype == torch.bool and copied["_final_observation"] is not None
+    d = env.get_info_dicts()[0]
+    for key in ("x", "y", "x_velocity", "y_velocity", "flat_tire", "current_tile_type", "cars", "driver_profile_stats", "traffic_rules"):
+        assert key in d
+    assert len(d["current_tile_type"]) == 4 and set(d["current_tile_type"]) <= {"0", "1"}
+    assert d["driver_profile_stats"]["total_cars"] == len(d["cars"]) == sum(d["driver_profile_stats"]["counts"].values())
+    assert d["traffic_rules"]["active_rules"] == ["four_way_intersection_brake", "t_intersection_brake"]
+    with pytest.raises(RuntimeError, match="outside 0..8"):
+        env.step(torch.full((64,), 11, device="cuda", dtype=torch.int32))
+        env.episode_stats()
+    env.close()
