@@ -328,6 +328,28 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     bk_h2d(ld, &L, sizeof L, nullptr);
     bk_sync(nullptr);  // (L is a stack object)
     p.lut = ld;
+    // the lane probe of a car inside a tile (environment.py:891-932) as a table: which of the four neighbour squares
+    // that lie in the SAME tile continue the car's route in that direction (tile-crossing moves are looked up live)
+    std::vector<uint8_t> sl((size_t)16 * 81 * PGTG_NUM_ROUTE_IDS, 0);
+    static const int DX[4] = {0, 0, -1, 1}, DY[4] = {-1, 1, 0, 0};
+    for (int ex = 0; ex < 16; ex++)
+      for (int sq = 0; sq < 81; sq++)
+        for (int dd = 0; dd < 4; dd++) {
+          int nx = sq / TILE + DX[dd], ny = sq % TILE + DY[dd];
+          if (nx < 0 || ny < 0 || nx >= TILE || ny >= TILE) continue;
+          uint64_t l = h_lane_desc[ex][nx * TILE + ny];
+          for (int r = 0; r < PGTG_NUM_ROUTE_IDS; r++) {
+            uint8_t& v = sl[((size_t)ex * 81 + sq) * PGTG_NUM_ROUTE_IDS + r];
+            if ((int)(l & 7) == dd + 1) v |= (uint8_t)(16u << dd);
+            for (int i = 0; i < (int)((l >> 3) & 7); i++)
+              if ((int)((l >> (6 + 7 * i)) & 31) == r && (int)((l >> (11 + 7 * i)) & 3) == dd) v |= (uint8_t)(1u << dd);
+          }
+        }
+    uint8_t* sd = dev_alloc<uint8_t>(e, sl.size());
+    if (!sd) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }
+    bk_h2d(sd, sl.data(), sl.size(), nullptr);
+    bk_sync(nullptr);
+    p.step_lut = sd;
   }
   {
     std::vector<uint8_t> lut;

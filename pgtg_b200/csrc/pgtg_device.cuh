@@ -236,6 +236,8 @@ struct DevPtrs {
   const uint8_t* dirlut;        // (2R+1)^2
   const uint32_t* conn_table;   // [2^conn_bits / 32] or null
   const Lut* lut;               // the LUTs with their derived fields, built once per handle
+  const uint8_t* step_lut;      // [16][81][20] per (tile type, local square, route): bit d = the neighbour square in direction d lies in
+                                // the same tile and carries a lane of that route with direction d (bits 4-7: ... carries 'all d')
   const uint64_t* path_table;   // [2^conn_bits] or null: 3-bit subgoal direction of every tile | ns << 48 | unreachable << 63
   const pgtg_rule* rules;
   // outputs

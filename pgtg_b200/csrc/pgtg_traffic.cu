@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
   phase_stage(c, p, bs, tid, NT, env0, nvalid, true, false);
   for (int i = tid; i < G * sh.occ_words; i += NT) sh.occ[i] = 0;
   if (tid < 16) sh.counters[tid] = 0;
+  for (int i = tid; i < 32 * 32; i += NT) sh.wbits[i] = 0;
   if (tid < 2) sh.dsum[tid] = 0.0;
   const bool mine = tid < nvalid;
   const int env = env0 + tid;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
   }
   __syncthreads();
   for (int g = tid >> 5; g < nvalid; g += NT >> 5)  // one env per warp, 32 cars per step
-    if (sh.env[g].n_cars > 0) tk_resolve_commit(c, p, sh, g, env0 + g);
+    if (sh.env[g].n_cars > 0) tk_resolve_commit(c, p, sh, g, env0 + g, tid >> 5);
   __syncthreads();
 
   // ---- the agent --------------------------------------------------------------------------------------

@@ -66,6 +66,7 @@ struct TkShared {
   uint32_t* occ;       // [G][occ_words] 4-bit counters per square, 15 = sticky "unknown" (null when MC < TK_OCC_MIN)
   uint32_t* bits;      // CTA observation bitstring, env g at bit g * obs_bits
   uint16_t* colpre;    // [G][ncolp] lane squares of the tiles before t (new episodes)
+  uint32_t* wbits;     // [32 warps][32] per-warp 1024-bit square filter of the resolve pass (zero between uses)
   uint8_t* item_g;     // [G * MC] item -> env of the CTA (the tick's cars, later the new episodes' cars)
   int* off;            // [G + 1] car items of the tick
   int* off2;           // [G + 1] car items of the episodes that start in this tick
@@ -75,7 +76,7 @@ struct TkShared {
   int bits_words, G, MC, occ_words, ncolp;
 };
 struct TkLayout {
-  uint32_t lut, spread, tiles, env, intent, fxy, occ, bits, colpre, item_g, off, off2, counters, dsum, done_list, total;
+  uint32_t lut, spread, tiles, env, intent, fxy, occ, bits, colpre, wbits, item_g, off, off2, counters, dsum, done_list, total;
   int bits_words, G, MC, occ_words, ncolp;
 };
 PG_HOSTDEV TkLayout tk_layout(const DevCfg& c, int G) {
@@ -94,6 +95,7 @@ PG_HOSTDEV TkLayout tk_layout(const DevCfg& c, int G) {
   L.occ = take(sizeof(uint32_t) * G * L.occ_words);
   L.bits = take(sizeof(uint32_t) * L.bits_words);
   L.colpre = take(sizeof(uint16_t) * G * L.ncolp);
+  L.wbits = take(sizeof(uint32_t) * 32 * 32);
   L.item_g = take((size_t)G * L.MC);
   L.off = take(sizeof(int) * (G + 1)); L.off2 = take(sizeof(int) * (G + 1));
   L.counters = take(sizeof(int) * 16); L.dsum = take(sizeof(double) * 2);
@@ -106,7 +108,7 @@ PG_HOSTDEV TkShared tk_carve(unsigned char* base, const TkLayout& L) {
   s.lut = (Lut*)(base + L.lut); s.spread = (uint2*)(base + L.spread); s.tiles = (uint16_t*)(base + L.tiles);
   s.env = (TEnv*)(base + L.env); s.intent = (uint32_t*)(base + L.intent); s.fxy = (uint16_t*)(base + L.fxy);
   s.occ = L.occ_words ? (uint32_t*)(base + L.occ) : nullptr; s.bits = (uint32_t*)(base + L.bits);
-  s.colpre = (uint16_t*)(base + L.colpre); s.item_g = (uint8_t*)(base + L.item_g); s.off = (int*)(base + L.off); s.off2 = (int*)(base + L.off2);
+  s.colpre = (uint16_t*)(base + L.colpre); s.wbits = (uint32_t*)(base + L.wbits); s.item_g = (uint8_t*)(base + L.item_g); s.off = (int*)(base + L.off); s.off2 = (int*)(base + L.off2);
   s.counters = (int*)(base + L.counters); s.dsum = (double*)(base + L.dsum); s.done_list = (int*)(base + L.done_list);
   s.bits_words = L.bits_words; s.G = L.G; s.MC = L.MC; s.occ_words = L.occ_words; s.ncolp = L.ncolp;
   return s;
@@ -208,28 +210,40 @@ PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
   if (move) {
     bool found = false;
     const int ctx = car.x / TILE, cty = car.y / TILE, clx = car.x - ctx * TILE, cly = car.y - cty * TILE;
-#pragma unroll 1
-    for (int d = 0; d < 4 && !found; d++) {  // up, down, left, right (:891-902)
-      // the neighbour square as (tile, local square): one step from (ctx, cty, clx, cly), no divisions
+    // which neighbour square continues the journey (up, down, left, right, first match wins, :891-932): inside the car's
+    // tile this is a table lookup per (tile type, square, route); only a move across a tile border looks at the other tile
+    const unsigned m0 = pg_ldg(&p.step_lut[((size_t)td_exits(m.tiles[cty * c.W + ctx]) * 81 + clx * TILE + cly) * PGTG_NUM_ROUTE_IDS + car.route]);
+    unsigned lane_mask = m0 & 15u, enter_mask = m0 >> 4;
+    if (clx == 0 || cly == 0 || clx == TILE - 1 || cly == TILE - 1) {
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        const bool cross = d == 0 ? cly == 0 : d == 1 ? cly == TILE - 1 : d == 2 ? clx == 0 : clx == TILE - 1;
+        if (!cross) continue;
+        const int ntx = ctx + (d == 2 ? -1 : d == 3 ? 1 : 0), nty = cty + (d == 0 ? -1 : d == 1 ? 1 : 0);
+        if (ntx < 0 || nty < 0 || ntx >= c.W || nty >= c.H) continue;  // inside_map
+        const int nlx = d == 2 ? TILE - 1 : d == 3 ? 0 : clx, nly = d == 0 ? TILE - 1 : d == 1 ? 0 : cly;
+        const uint64_t ld = lane_desc(td_exits(m.tiles[nty * c.W + ntx]), nlx * TILE + nly);
+        if (ld_all(ld) == d + 1) enter_mask |= 1u << d;
+        else {
+          const int nl = ld_n(ld);
+          for (int i = 0; i < nl; i++)
+            if (ld_route(ld, i) == car.route && ld_dir(ld, i) == d) lane_mask |= 1u << d;
+        }
+      }
+    }
+    if (lane_mask | enter_mask) {
+      found = true;
+      const int d = pg_ffs(lane_mask | enter_mask) - 1;
       int ntx = ctx, nty = cty, nlx = clx + (d == 2 ? -1 : d == 3 ? 1 : 0), nly = cly + (d == 0 ? -1 : d == 1 ? 1 : 0);
       if (nlx < 0) { nlx = TILE - 1; ntx--; } else if (nlx >= TILE) { nlx = 0; ntx++; }
       if (nly < 0) { nly = TILE - 1; nty--; } else if (nly >= TILE) { nly = 0; nty++; }
-      if (ntx < 0 || nty < 0 || ntx >= c.W || nty >= c.H) continue;  // inside_map
       const unsigned td = m.tiles[nty * c.W + ntx];
-      const int ex = td_exits(td), sq = nlx * TILE + nly;
-      const uint64_t ld = lane_desc(ex, sq);
-      if (ld == 0) continue;
-      const int px = ntx * TILE + nlx, py = nty * TILE + nly;
-      if (ld_all(ld) == d + 1) {  // entering a new tile: uniform new route, never blocked (:915-928)
+      const int ex = td_exits(td), sq = nlx * TILE + nly, px = ntx * TILE + nlx, py = nty * TILE + nly;
+      if ((enter_mask >> d) & 1u) {  // entering a new tile: uniform new route, never blocked (:915-928)
+        const uint64_t ld = lane_desc(ex, sq);
         const int n = ld_n(ld);
         word = intent_pack(IK_ENTER, px, py, ld_route(ld, n > 1 ? (int)pg_umulhi(w0[CW_IDX], (uint32_t)n) : 0), delay, false, car.profile);
-        found = true;
-        break;
-      }
-      const int nl = ld_n(ld);
-      for (int i = 0; i < nl; i++) {
-        if (ld_route(ld, i) != car.route || ld_dir(ld, i) != d) continue;  // :932
-        found = true;
+      } else {
         bool stop = false;
         if (td_otype(td) == 4 && bit81(m.L.mask[td_omask(td)], sq) && !bit81(m.L.wall[ex], sq)) {  // a traffic light (:934-942)
           const int phase = light_phase(c, misc_light(e.misc));
@@ -245,7 +259,6 @@ PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
           const bool push = impatient && car_u32_to_uniform(w0[CW_PUSH]) < c.drv_push_probability[car.profile];  // :950-958
           word = intent_pack(IK_LANE, px, py, car.route, delay, push, car.profile);
         }
-        break;
       }
     }
     if (!found) {  // leaves the map; its replacement (_spawn_new_car, :970-1002) is appended to the list
@@ -279,8 +292,8 @@ PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
 //                                                         already final, this chunk and later ones still old)
 //            + #{j < r in the chunk, moved: T_j == T_r}   arrived before r's turn
 //            - #{j < r in the chunk, moved: old_j == T_r} left before r's turn
-// Lanes whose target meets no old or target square of another lane of the chunk (a 64-bit filter over the chunk's old
-// squares, match_any over the targets) decide at once from occ; the few others are settled one by one in lane order
+// Lanes whose target meets no old square of a lane of the chunk that may leave it (a 1024-bit per-warp filter) and no
+// target of another lane (match_any) decide at once from occ; the few others are settled one by one in lane order
 // with three ballots each. Envs with <= 32 cars need no occ array: the chunk is the whole list and occ[T_r] is a ballot.
 // The chunk is then committed: live half -> other half of the car list, order-stable (a despawned car's replacement goes
 // to the end of the list: slot n - n_despawn + rank), counters updated with shared-memory atomics.
@@ -297,7 +310,9 @@ PG_HD void occ4_dec_atomic(uint32_t* o, int i) {
   }
 }
 
-PG_HD void tk_resolve_commit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env) {
+PG_HD unsigned square_hash10(unsigned xy) { return ((xy * 40503u) >> 6) & 1023u; }
+
+PG_HD void tk_resolve_commit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env, int wslot) {
   PG_WARP_LANE
   TEnv& t = sh.env[g];
   const int n = t.n_cars, nd_total = t.n_despawn;
@@ -308,11 +323,12 @@ PG_HD void tk_resolve_commit(const DevCfg& c, const DevPtrs& p, const TkShared& 
   const int half = misc_half(t.e.misc);
   const uint64_t* A = car_list(c, p, env, half);
   uint64_t* B = car_list(c, p, env, half ^ 1);
+  uint32_t* wb = sh.wbits + wslot * 32;
   uint32_t bloom_lo = 0, bloom_hi = 0;  // filter over the final squares (the agent's collision test)
   int nd_before = 0;
   for (int b = 0; b < n; b += 32) {
-    PG_LV(uint32_t, w); PG_LV(unsigned, T); PG_LV(unsigned, old); PG_LV(int, moved); PG_LV(int, occv); PG_LV(uint32_t, same);
-    uint32_t old_lo, old_hi, inv;
+    PG_LV(uint32_t, w); PG_LV(unsigned, T); PG_LV(unsigned, old); PG_LV(int, moved); PG_LV(int, occv); PG_LV(uint32_t, same); PG_LV(uint32_t, hit);
+    uint32_t inv;
     PG_FOR_LANES {
       const bool valid = b + l < n;
       LV(w) = valid ? it[b + l] : (uint32_t)IK_STAY;
@@ -322,11 +338,22 @@ PG_HD void tk_resolve_commit(const DevCfg& c, const DevPtrs& p, const TkShared& 
       LV(occv) = (use_occ && kind == IK_LANE) ? occ4_get(occ, occ4_index(c, LV(T))) : 0;
       LV(moved) = kind == IK_ENTER || kind == IK_DESPAWN || (kind == IK_LANE && (LV(occv) == 0 || (LV(w) & IK_PUSH)));
     }
-    PG_REDUCE_OR(old_lo, b + l < n ? (uint32_t)bloom_bit(LV(old)) : 0u);
-    PG_REDUCE_OR(old_hi, b + l < n ? (uint32_t)(bloom_bit(LV(old)) >> 32) : 0u);
+    // which lanes' turn order matters? Targets that meet the old square of a lane of this chunk that may leave it
+    // (with counters: only movers matter, a staying occupant is in occ already; without: every old square, the filter
+    // doubles as the occupancy test) or the target of another lane. 1024-bit filter per warp, exact on a miss.
+    PG_FOR_LANES {
+      const bool in = b + l < n && (!use_occ || LV(moved) || (LV(w) & 3u) == IK_LANE);
+      if (in) { const unsigned h = square_hash10(LV(old)); pg_atomic_or(&wb[h >> 5], 1u << (h & 31u)); }
+    }
+    PG_SYNCWARP();
     PG_MATCH_ANY(same, (LV(w) & 3u) != IK_STAY ? LV(T) : 0x20000u + (uint32_t)l);
-    const uint64_t old_bloom = (uint64_t)old_hi << 32 | old_lo;
-    PG_BALLOT(inv, (LV(w) & 3u) == IK_LANE && ((old_bloom & bloom_bit(LV(T))) != 0 || (LV(same) & (LV(same) - 1u)) != 0 || LV(occv) == TK_OCC_SAT));
+    PG_FOR_LANES {
+      const unsigned h = square_hash10(LV(T));
+      LV(hit) = (wb[h >> 5] >> (h & 31u)) & 1u;
+    }
+    PG_BALLOT(inv, (LV(w) & 3u) == IK_LANE && ((LV(hit) && (!use_occ || LV(occv) > 0)) || LV(occv) == TK_OCC_SAT || (LV(same) & (LV(same) - 1u)) != 0));
+    PG_SYNCWARP();
+    PG_FOR_LANES { wb[l] = 0; }
     while (inv) {  // the lanes whose turn order matters, in list order
       const int rl = pg_ffs(inv) - 1;
       inv &= inv - 1;

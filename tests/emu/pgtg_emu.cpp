@@ -141,6 +141,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
   bs.lut = sh.lut; bs.spread = sh.spread; bs.tiles = sh.tiles; bs.bits = sh.bits; bs.bits_words = sh.bits_words; bs.done_list = sh.done_list;
   for (int t = 0; t < NT; t++) phase_stage(c, p, bs, t, NT, env0, nvalid, true, false);
   for (int i = 0; i < G * sh.occ_words; i++) sh.occ[i] = 0;
+  for (int i = 0; i < 32 * 32; i++) sh.wbits[i] = 0;
   for (int g = 0; g < nvalid; g++) {
     int env = env0 + g;
     int a = action_bytes == 8 ? (int)((const int64_t*)actions)[env] : ((const int32_t*)actions)[env];
@@ -150,7 +151,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
   const int total = sh.off[G];
   for (int t = 0; t < NT; t++)
     for (int item = t; item < total; item += NT) { int g = sh.item_g[item]; tk_intent(c, p, sh, g, item - sh.off[g], env0 + g); }
-  for (int g = 0; g < nvalid; g++) if (sh.env[g].n_cars > 0) tk_resolve_commit(c, p, sh, g, env0 + g);
+  for (int g = 0; g < nvalid; g++) if (sh.env[g].n_cars > 0) tk_resolve_commit(c, p, sh, g, env0 + g, g & 31);
   int n_done = 0;
   double st[8] = {0};
   for (int g = 0; g < nvalid; g++) {
