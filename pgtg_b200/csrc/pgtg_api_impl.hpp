@@ -128,7 +128,7 @@ static void build_direction_lut(int R, std::vector<uint8_t>& lut) {
 // pgtg_create and again whenever something it depends on changes (pgtg_update_rules, pgtg_set_state).
 static int lean_predicate(const pgtg_config& c, const DevCfg& d) {
   return (d.pregen && !(c.traffic_density > 0) && !d.rules_without_traffic && !c.sliding && d.obs_fast && d.kind_channel[PGTG_CH_CAR_SPAWNER] < 0 &&
-          !d.use_nsd && !d.vis_words && !c.separate_reward_cost && !c.write_final_obs) ? 1 : 0;
+          !d.use_nsd && !d.vis_words && !c.separate_reward_cost) ? 1 : 0;  // (terminal observations: the lean FINAL instantiation)
 }
 
 // The LUT block the kernels stage into shared memory: the generated tables plus everything derived from them.
@@ -345,11 +345,25 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
               if ((int)((l >> (6 + 7 * i)) & 31) == r && (int)((l >> (11 + 7 * i)) & 3) == dd) v |= (uint8_t)(1u << dd);
           }
         }
+    // ... and the same question asked of a square of ANOTHER tile (the move crosses a tile border)
+    std::vector<uint8_t> tl((size_t)16 * 81 * PGTG_NUM_ROUTE_IDS, 0);
+    for (int ex = 0; ex < 16; ex++)
+      for (int sq = 0; sq < 81; sq++) {
+        uint64_t l = h_lane_desc[ex][sq];
+        for (int r = 0; r < PGTG_NUM_ROUTE_IDS; r++) {
+          uint8_t& v = tl[((size_t)ex * 81 + sq) * PGTG_NUM_ROUTE_IDS + r];
+          if ((l & 7) != 0) v |= (uint8_t)(16u << ((l & 7) - 1));
+          for (int i = 0; i < (int)((l >> 3) & 7); i++)
+            if ((int)((l >> (6 + 7 * i)) & 31) == r) v |= (uint8_t)(1u << ((l >> (11 + 7 * i)) & 3));
+        }
+      }
     uint8_t* sd = dev_alloc<uint8_t>(e, sl.size());
-    if (!sd) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }
+    uint8_t* tdv = dev_alloc<uint8_t>(e, tl.size());
+    if (!sd || !tdv) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }
     bk_h2d(sd, sl.data(), sl.size(), nullptr);
+    bk_h2d(tdv, tl.data(), tl.size(), nullptr);
     bk_sync(nullptr);
-    p.step_lut = sd;
+    p.step_lut = sd; p.target_lut = tdv;
   }
   {
     std::vector<uint8_t> lut;
@@ -999,7 +1013,7 @@ extern "C" int pgtg_kernel_info(pgtg_env* e, char* out, int out_bytes) {
   if (!e || !out || out_bytes < 1) return fail(PGTG_ERR_INVALID, "null argument");
   const char* rng = e->cfg.rng_mode == PGTG_RNG_TAPE ? "tape" : e->cfg.rng_mode == PGTG_RNG_NUMPY ? "numpy" : "philox";
   if (e->traffic_G > 0) snprintf(out, (size_t)out_bytes, "tick=traffic(G=%d,NT=%d) mapgen=%s rng=%s", e->traffic_G, e->traffic_NT, e->dc.pregen ? (e->dc.conn_bits && e->dc.path_tab ? "tabled" : "general") : "none", rng);
-  else snprintf(out, (size_t)out_bytes, "tick=%s(B=%d) mapgen=%s rng=%s", e->dc.lean && e->dc.pregen && e->cfg.rng_mode != PGTG_RNG_TAPE ? "lean" : "general", e->block,
+  else snprintf(out, (size_t)out_bytes, "tick=%s(B=%d) mapgen=%s rng=%s", e->dc.lean && e->dc.pregen && e->cfg.rng_mode != PGTG_RNG_TAPE ? (e->dc.write_final_obs ? "lean+final" : "lean") : "general", e->block,
                 e->dc.pregen ? (e->dc.conn_bits && e->dc.path_tab ? "tabled" : "general") : "in-tick", rng);
   return PGTG_OK;
 }

@@ -236,6 +236,8 @@ struct DevPtrs {
   const uint8_t* dirlut;        // (2R+1)^2
   const uint32_t* conn_table;   // [2^conn_bits / 32] or null
   const Lut* lut;               // the LUTs with their derived fields, built once per handle
+  const uint8_t* target_lut;    // [16][81][20] per (tile type, local square, route): bit d = the square carries a lane of that route with
+                                // direction d, bit 4 + d = it carries 'car_lane all d' (a move INTO it from another tile, :915-932)
   const uint8_t* step_lut;      // [16][81][20] per (tile type, local square, route): bit d = the neighbour square in direction d lies in
                                 // the same tile and carries a lane of that route with direction d (bits 4-7: ... carries 'all d')
   const uint64_t* path_table;   // [2^conn_bits] or null: 3-bit subgoal direction of every tile | ns << 48 | unreachable << 63
@@ -634,17 +636,13 @@ struct MapView {
       unsigned lab = (line_labels(t, td) >> (4 * d)) & 15;
       if (lab != 1 && lab != 4) continue;
       int ox = (t % c.W) * TILE, oy = (t / c.W) * TILE;
-      // the 3 squares of exit line d, taken from the LUT (north (3..5,0) east (8,3..5) ...)
+      // the 3 squares of exit line d in ascending order (north (3..5,0) east (8,3..5) ...), from the derived LUT
 #pragma unroll
-      for (int w = 0; w < 3; w++) {
-        uint32_t bits = L.exit_line[d][w];
-        while (bits) {
-          int sq = w * 32 + pg_ffs(bits) - 1;
-          bits &= bits - 1;
-          int X = ox + sq / TILE, Y = oy + sq % TILE;
-          int dist = abs(X - px) + abs(Y - py);
-          if (dist < best || (dist == best && (X < bx || (X == bx && Y < by)))) { best = dist; bx = X; by = Y; }
-        }
+      for (int k = 0; k < 3; k++) {
+        const int sq = L.line_sq[d][k];
+        const int X = ox + sq / TILE, Y = oy + sq % TILE;
+        const int dist = abs(X - px) + abs(Y - py);
+        if (dist < best || (dist == best && (X < bx || (X == bx && Y < by)))) { best = dist; bx = X; by = Y; }
       }
     }
     gx = bx; gy = by;

@@ -40,7 +40,8 @@ __device__ unsigned long long g_phase_clk[16];
 #define PG_CLK(i)
 #endif
 
-template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false>
+// (FINAL: the lean instantiation that also writes the terminal observation of the finished envs, gymnasium's final_observation)
+template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false>
 __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
                                                         const void* __restrict__ actions, int action_bytes, StatsArgs sa,
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
         if (lane == 0) { atomicAdd(&sh.dsum[1], ds); atomicAdd(&sh.counters[13], __popc(neg)); }
       }
     }
-    if (LEAN || (PREGEN && !c.write_final_obs)) {
+    if (LEAN || (PREGEN && !c.write_final_obs)) {  // (LEAN && FINAL is the one lean case with terminal observations)
       // Hot configuration (next maps come from the ring, no terminal-observation output): the
       // reset is a cheap swap, so every finished env is reset by its own thread and the CTA
       // needs one barrier only, the one in front of the byte expansion. Map requests are queued
@@ -103,6 +104,20 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
       uint32_t k = 0, qbase = 0;
       if (any && lane == 0) qbase = atomicAdd(p.regen_count + p.parity, (uint32_t)__popc(any));
       PG_CLK(3)
+      if (LEAN && FINAL) {  // terminal observation first: emit the finished envs' planes, expand their rows, clear the bitstring
+        if (lane == 0) sh.counters[16 + warp] = (int)any;
+        if (done) phase_emit_regs<true>(c, p, sh, tid, env, true, er);
+        __syncthreads();
+        phase_expand_final_vec(c, p.f_obs_map, sh, tid, B, env0, nvalid, sh.counters + 16);
+        __syncthreads();
+        {
+          uint4 z; z.x = z.y = z.z = z.w = 0;
+          uint4* b4 = (uint4*)sh.bits;
+          for (int i = tid; i < sh.bits_words / 4; i += B) b4[i] = z;
+          for (int i = (sh.bits_words / 4) * 4 + tid; i < sh.bits_words; i += B) sh.bits[i] = 0;
+        }
+        __syncthreads();
+      }
       if (done) {
         if (LEAN) { k = er.episode + 1u; phase_reset_regs<RNG, TMAX, true, true>(c, p, sh, tid, env, er); }
         else { k = sh.regs[tid].episode + 1u; phase_reset<RNG, TMAX, true, false>(c, p, sh, tid, env); }  // k: the episode this env is about to start
@@ -224,9 +239,9 @@ __global__ void __launch_bounds__(128, TABLED ? PGTG_MAPGEN_TABLED_MIN_BLOCKS : 
 // launch code: returns the cudaError_t of the launch (0 = ok)
 static inline int lk(cudaError_t e) { return (int)e; }
 
-template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false>
+template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false>
 static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
-  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN, LEAN>;
+  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN, LEAN, FINAL>;
   // same L1/shared carveout as the map-generation kernel: an SM cannot host CTAs of two kernels with
   // different carveouts, which would serialise the two (measured: no overlap at all without this)
   static bool carve_set = false;
@@ -271,8 +286,11 @@ static int launch_mode(pgtg_env* e, int mode, const uint8_t* mask, const int64_t
   switch (mode) {
     case MODE_STEP:
       // plain configuration: the lean instantiation (the ring-fed reset does not depend on the board size)
-      if (RNG != PGTG_RNG_TAPE && e->dc.pregen && e->dc.lean && !getenv("PGTG_NO_LEAN"))
+      if (RNG != PGTG_RNG_TAPE && e->dc.pregen && e->dc.lean && !getenv("PGTG_NO_LEAN")) {
+        if (e->dc.write_final_obs)
+          return launch_one<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, MODE_STEP, 16, RNG != PGTG_RNG_TAPE, RNG != PGTG_RNG_TAPE, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
         return launch_one<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, MODE_STEP, 16, RNG != PGTG_RNG_TAPE, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
+      }
       if (RNG != PGTG_RNG_TAPE && e->dc.pregen) return launch_sized<RNG, MODE_STEP, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
       return launch_sized<RNG, MODE_STEP, false>(e, mask, seeds, actions, action_bytes, st);
     case MODE_RESET:

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
   for (int i = tid; i < G * sh.occ_words; i += NT) sh.occ[i] = 0;
   if (tid < 16) sh.counters[tid] = 0;
   for (int i = tid; i < 32 * 32; i += NT) sh.wbits[i] = 0;
+  for (int i = tid; i < c.T; i += NT) tk_stage_tile(c, sh, i);
   if (tid < 2) sh.dsum[tid] = 0.0;
   const bool mine = tid < nvalid;
   const int env = env0 + tid;
@@ -151,7 +152,9 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
 // observation planes must start 32-byte aligned), threads per CTA and dynamic shared memory; G = 0 when the
 // per-env working set does not fit (very large maps with dense traffic): the sequential tick runs instead.
 int pgtg_traffic_geometry(const pgtg::DevCfg& c, int* G, int* NT, size_t* smem) {
-  const int g = 32;
+  int g = 32;
+  const char* forced_g = getenv("PGTG_TRAFFIC_G");  // experiment knob: 32 / 64 / 128 envs per CTA
+  if (forced_g && (atoi(forced_g) == 32 || atoi(forced_g) == 64 || atoi(forced_g) == 128)) g = atoi(forced_g);
   const pgtg::TkLayout L = pgtg::tk_layout(c, g);
   *G = 0; *NT = 0; *smem = 0;
   if (L.total > 220u * 1024u || c.max_cars > 0xFFFF) return 0;
@@ -160,6 +163,7 @@ int pgtg_traffic_geometry(const pgtg::DevCfg& c, int* G, int* NT, size_t* smem) 
   *NT = L.total > 72u * 1024u ? 1024 : (L.total > 28u * 1024u ? 256 : 128);
   const char* forced = getenv("PGTG_TRAFFIC_NT");  // experiment knob
   if (forced && (atoi(forced) == 64 || atoi(forced) == 128 || atoi(forced) == 256 || atoi(forced) == 1024)) *NT = atoi(forced);
+  if (*NT < g) *NT = g;  // one env per thread in the per-env phases
   return 1;
 }
 

@@ -66,6 +66,8 @@ struct TkShared {
   uint32_t* occ;       // [G][occ_words] 4-bit counters per square, 15 = sticky "unknown" (null when MC < TK_OCC_MIN)
   uint32_t* bits;      // CTA observation bitstring, env g at bit g * obs_bits
   uint16_t* colpre;    // [G][ncolp] lane squares of the tiles before t (new episodes)
+  uint16_t* torg;      // [T] origin square of tile t (x | y << 8); [T] bytes after it: which map borders the tile touches (N 1, E 2, S 4, W 8)
+  uint8_t* tborder;
   uint32_t* wbits;     // [32 warps][32] per-warp 1024-bit square filter of the resolve pass (zero between uses)
   uint8_t* item_g;     // [G * MC] item -> env of the CTA (the tick's cars, later the new episodes' cars)
   int* off;            // [G + 1] car items of the tick
@@ -76,7 +78,7 @@ struct TkShared {
   int bits_words, G, MC, occ_words, ncolp;
 };
 struct TkLayout {
-  uint32_t lut, spread, tiles, env, intent, fxy, occ, bits, colpre, wbits, item_g, off, off2, counters, dsum, done_list, total;
+  uint32_t lut, spread, tiles, env, intent, fxy, occ, bits, colpre, torg, tborder, wbits, item_g, off, off2, counters, dsum, done_list, total;
   int bits_words, G, MC, occ_words, ncolp;
 };
 PG_HOSTDEV TkLayout tk_layout(const DevCfg& c, int G) {
@@ -95,6 +97,7 @@ PG_HOSTDEV TkLayout tk_layout(const DevCfg& c, int G) {
   L.occ = take(sizeof(uint32_t) * G * L.occ_words);
   L.bits = take(sizeof(uint32_t) * L.bits_words);
   L.colpre = take(sizeof(uint16_t) * G * L.ncolp);
+  L.torg = take(sizeof(uint16_t) * c.T); L.tborder = take((size_t)c.T);
   L.wbits = take(sizeof(uint32_t) * 32 * 32);
   L.item_g = take((size_t)G * L.MC);
   L.off = take(sizeof(int) * (G + 1)); L.off2 = take(sizeof(int) * (G + 1));
@@ -108,7 +111,7 @@ PG_HOSTDEV TkShared tk_carve(unsigned char* base, const TkLayout& L) {
   s.lut = (Lut*)(base + L.lut); s.spread = (uint2*)(base + L.spread); s.tiles = (uint16_t*)(base + L.tiles);
   s.env = (TEnv*)(base + L.env); s.intent = (uint32_t*)(base + L.intent); s.fxy = (uint16_t*)(base + L.fxy);
   s.occ = L.occ_words ? (uint32_t*)(base + L.occ) : nullptr; s.bits = (uint32_t*)(base + L.bits);
-  s.colpre = (uint16_t*)(base + L.colpre); s.wbits = (uint32_t*)(base + L.wbits); s.item_g = (uint8_t*)(base + L.item_g); s.off = (int*)(base + L.off); s.off2 = (int*)(base + L.off2);
+  s.colpre = (uint16_t*)(base + L.colpre); s.torg = (uint16_t*)(base + L.torg); s.tborder = (uint8_t*)(base + L.tborder); s.wbits = (uint32_t*)(base + L.wbits); s.item_g = (uint8_t*)(base + L.item_g); s.off = (int*)(base + L.off); s.off2 = (int*)(base + L.off2);
   s.counters = (int*)(base + L.counters); s.dsum = (double*)(base + L.dsum); s.done_list = (int*)(base + L.done_list);
   s.bits_words = L.bits_words; s.G = L.G; s.MC = L.MC; s.occ_words = L.occ_words; s.ncolp = L.ncolp;
   return s;
@@ -148,6 +151,31 @@ PG_HD bool tk_scan(const uint16_t* fx, int n, unsigned xy) {
   for (int j = 0; j < n; j++)
     if (fx[j] == xy) return true;
   return false;
+}
+
+// per-CTA tile tables (stage, one tile per thread)
+PG_HD void tk_stage_tile(const DevCfg& c, const TkShared& sh, int t) {
+  const int tx = t % c.W, ty = t / c.W;
+  sh.torg[t] = (uint16_t)(tx * TILE | (ty * TILE) << 8);
+  sh.tborder[t] = (uint8_t)((ty == 0 ? 1u : 0u) | (tx == c.W - 1 ? 2u : 0u) | (ty == c.H - 1 ? 4u : 0u) | (tx == 0 ? 8u : 0u));
+}
+// build_spawner_list_tile_major (pgtg_logic.cuh) on the per-CTA tile tables: no divisions by the map width
+PG_HD void tk_spawner_list(const DevCfg& c, const DevPtrs& p, const TkShared& sh, const MapView& m, int env) {
+  int n = 0;
+  uint16_t* list = p.spawners + (size_t)env * c.spawner_cap;
+  for (int t = 0; t < c.T; t++) {
+    const int ex = td_exits(m.tiles[t]);
+    if (ex == 0) continue;  // no lanes on wall-only tiles (parser.py:113-118)
+    unsigned slots = (m.L.native_spawner[ex] != 255 ? 1u : 0u) | (unsigned)(m.L.entry_ok[ex] & sh.tborder[t]) << 1;
+    const unsigned org = sh.torg[t];
+    while (slots) {
+      const int k = pg_ffs(slots) - 1, sq = spawner_slot_square(m.L, ex, k);
+      slots &= slots - 1;
+      if (n < c.spawner_cap) list[n] = (uint16_t)(((org & 255u) + (unsigned)(sq / TILE)) | ((org >> 8) + (unsigned)(sq % TILE)) << 8);
+      n++;
+    }
+  }
+  p.spawner_count[env] = (uint16_t)(n < c.spawner_cap ? n : c.spawner_cap);
 }
 
 // ---- stage: one env per thread ----------------------------------------------------------------------
@@ -222,13 +250,9 @@ PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
         const int ntx = ctx + (d == 2 ? -1 : d == 3 ? 1 : 0), nty = cty + (d == 0 ? -1 : d == 1 ? 1 : 0);
         if (ntx < 0 || nty < 0 || ntx >= c.W || nty >= c.H) continue;  // inside_map
         const int nlx = d == 2 ? TILE - 1 : d == 3 ? 0 : clx, nly = d == 0 ? TILE - 1 : d == 1 ? 0 : cly;
-        const uint64_t ld = lane_desc(td_exits(m.tiles[nty * c.W + ntx]), nlx * TILE + nly);
-        if (ld_all(ld) == d + 1) enter_mask |= 1u << d;
-        else {
-          const int nl = ld_n(ld);
-          for (int i = 0; i < nl; i++)
-            if (ld_route(ld, i) == car.route && ld_dir(ld, i) == d) lane_mask |= 1u << d;
-        }
+        const unsigned tm = pg_ldg(&p.target_lut[((size_t)td_exits(m.tiles[nty * c.W + ntx]) * 81 + nlx * TILE + nly) * PGTG_NUM_ROUTE_IDS + car.route]);
+        if ((tm >> (4 + d)) & 1u) enter_mask |= 1u << d;  // 'car_lane all d' wins over a lane of the same square (:915)
+        else if ((tm >> d) & 1u) lane_mask |= 1u << d;
       }
     }
     if (lane_mask | enter_mask) {
@@ -506,7 +530,7 @@ PG_HD void tk_reset(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g
   if (PREGEN) env_reset_pregenerated<PGTG_RNG_PHILOX, false, true>(c, p, m, e, env);
   else env_reset<PGTG_RNG_PHILOX, TMAX, true>(c, p, m, e, env);
   m.plan = e.plan;
-  build_spawner_list_tile_major(c, p, m, env);
+  tk_spawner_list(c, p, sh, m, env);
   uint16_t* colpre = sh.colpre + g * sh.ncolp;
   const int np = lane_tile_prefix(c, m, colpre);
   int nc = initial_car_count(c, np);

@@ -71,6 +71,11 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
     }
     if (c.write_final_obs && n_done) {
       for (int k = 0; k < n_done; k++) phase_emit(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true);
+      if (LEAN) {  // the lean FINAL instantiation expands the finished envs' rows 32 bytes at a time
+        int words[8] = {0};
+        for (int k = 0; k < n_done; k++) words[sh.done_list[k] >> 5] |= (int)(1u << (sh.done_list[k] & 31));
+        for (int t = 0; t < B; t++) phase_expand_final_vec(c, p.f_obs_map, sh, t, B, env0, nvalid, words);
+      } else
       for (int t = 0; t < B; t++) phase_expand_final(c, p.f_obs_map, sh, t, B, env0, n_done);
       for (int i = 0; i < sh.bits_words; i++) sh.bits[i] = 0;
     }
@@ -142,6 +147,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
   for (int t = 0; t < NT; t++) phase_stage(c, p, bs, t, NT, env0, nvalid, true, false);
   for (int i = 0; i < G * sh.occ_words; i++) sh.occ[i] = 0;
   for (int i = 0; i < 32 * 32; i++) sh.wbits[i] = 0;
+  for (int i = 0; i < c.T; i++) tk_stage_tile(c, sh, i);
   for (int g = 0; g < nvalid; g++) {
     int env = env0 + g;
     int a = action_bytes == 8 ? (int)((const int64_t*)actions)[env] : ((const int32_t*)actions)[env];

@@ -131,3 +131,41 @@ def test_specialised_kernels_match_general(kw, monkeypatch):
     assert fast_stats.keys() == slow_stats.keys()
     for k in fast_stats:
         assert fast_stats[k] == pytest.approx(slow_stats[k], rel=1e-12), k
+
+
+@pytest.mark.gpu
+def test_lean_final_observation_matches_general(monkeypatch):
+    """final_observation=True on the plain configuration runs the lean FINAL instantiation: terminal observations (rows of the
+    finished envs), the observation after the reset and every other output equal the general tick's, bit for bit."""
+    import torch
+
+    from pgtg_b200 import PGTGVectorEnv
+
+    n, ticks = 20000, 30
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(3)
+    actions = [torch.randint(0, 9, (n,), device="cuda:0", dtype=torch.int32, generator=g) for _ in range(ticks)]
+
+    def run():
+        env = PGTGVectorEnv(n, device="cuda:0", seed=8, final_observation=True, random_map_obstacle_probability=0.5, max_episode_steps=6)
+        info = env.raw.kernel_info()
+        env.reset()
+        out = []
+        for a in actions:
+            obs, rew, term, trunc, inf = env.step(a)
+            done = term | trunc
+            fo = inf["final_observation"]
+            out.append((env._t["obs_map"].clone(), rew.clone(), done.clone(), env._t["final_obs_map"][done].clone(), fo["position"][done].clone(), fo["velocity"][done].clone()))
+        env.close()
+        return out, info
+
+    fast, info_fast = run()
+    monkeypatch.setenv("PGTG_NO_LEAN", "1")
+    slow, info_slow = run()
+    assert "lean+final" in info_fast and "general" in info_slow
+    finished = 0
+    for t, (a, b) in enumerate(zip(fast, slow)):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), f"tick {t}"
+        finished += int(a[2].sum())
+    assert finished > 100000
