@@ -218,34 +218,31 @@ class HostConfig:
 
 
 def _validate_generate_map_args(width, height, start_position, goal_position, min_dist):
-    """The argument checks of generate_map (map_generator.py:92-154), same messages."""
-    for position, name in [(start_position, "start_position"), (goal_position, "goal_position")]:
-        if isinstance(position, str) and position != "random":
-            raise ValueError(f"{name} must be a tuple or the string 'random'.")
-        if isinstance(position, tuple) and not (
-            position[0] == 0 or position[0] == -1 or position[0] == width - 1
-            or position[1] == 0 or position[1] == -1 or position[1] == height - 1
-        ):
+    """Reject what generate_map rejects (map_generator.py:92-154), with its messages. A position is "random", a border
+    tile (x, y) or a border tile with the side it opens to (x, y, side); -1 counts from the far edge."""
+    for name, pos in (("start_position", start_position), ("goal_position", goal_position)):
+        if isinstance(pos, str):
+            if pos != "random":
+                raise ValueError(f"{name} must be a tuple or the string 'random'.")
+            continue
+        if not isinstance(pos, tuple):
+            continue
+        # the map borders this tile lies on: coordinate 0 / -1 or the last index of its axis
+        on = {"west": pos[0] == 0, "east": pos[0] in (-1, width - 1), "north": pos[1] == 0, "south": pos[1] in (-1, height - 1)}
+        if not any(on.values()):
             raise ValueError(f"{name} must specify a tile on the map border.")
-        if isinstance(position, tuple) and len(position) == 3 and not (
-            ((not position[2] == "north") or (position[1] == 0))
-            and ((not position[2] == "east") or (position[0] == -1 or position[0] == width - 1))
-            and ((not position[2] == "south") or (position[1] == -1 or position[1] == height - 1))
-            and ((not position[2] == "west") or (position[0] == 0))
-        ):
+        if len(pos) == 3 and pos[2] in on and not on[pos[2]]:
             raise ValueError(f"The direction in {name} is not a map border.")
-    if (
-        isinstance(start_position, tuple) and len(start_position) == 3
-        and isinstance(goal_position, tuple) and len(goal_position) == 3
-        and start_position == goal_position
-    ):
+    both_exact = all(isinstance(p, tuple) and len(p) == 3 for p in (start_position, goal_position))
+    if both_exact and start_position == goal_position:
         raise ValueError("start_position and goal_position can't be the same tile and direction.")
-    if min_dist is not None and start_position != "random" and goal_position != "random":
-        raise ValueError(
-            "minimum_distance_between_start_and_goal can only be used if start_position and goal_position are 'random'."
-        )
-    if min_dist is not None and min_dist > width + height - 2:
-        raise ValueError("minimum_distance_between_start_and_goal can't be larger than width + height - 2.")
+    if min_dist is not None:
+        if "random" not in (start_position, goal_position):  # (the reference lets one fixed end pass)
+            raise ValueError(
+                "minimum_distance_between_start_and_goal can only be used if start_position and goal_position are 'random'."
+            )
+        if min_dist > width + height - 2:
+            raise ValueError("minimum_distance_between_start_and_goal can't be larger than width + height - 2.")
 
 
 def _position_fields(position, width, height):

@@ -1013,7 +1013,7 @@ extern "C" int pgtg_kernel_info(pgtg_env* e, char* out, int out_bytes) {
   if (!e || !out || out_bytes < 1) return fail(PGTG_ERR_INVALID, "null argument");
   const char* rng = e->cfg.rng_mode == PGTG_RNG_TAPE ? "tape" : e->cfg.rng_mode == PGTG_RNG_NUMPY ? "numpy" : "philox";
   if (e->traffic_G > 0) snprintf(out, (size_t)out_bytes, "tick=traffic(G=%d,NT=%d) mapgen=%s rng=%s", e->traffic_G, e->traffic_NT, e->dc.pregen ? (e->dc.conn_bits && e->dc.path_tab ? "tabled" : "general") : "none", rng);
-  else snprintf(out, (size_t)out_bytes, "tick=%s(B=%d) mapgen=%s rng=%s", e->dc.lean && e->dc.pregen && e->cfg.rng_mode != PGTG_RNG_TAPE ? (e->dc.write_final_obs ? "lean+final" : "lean") : "general", e->block,
+  else snprintf(out, (size_t)out_bytes, "tick=%s(B=%d) mapgen=%s rng=%s", e->dc.lean && e->dc.pregen && e->cfg.rng_mode != PGTG_RNG_TAPE && !getenv("PGTG_NO_LEAN") ? (e->dc.write_final_obs ? "lean+final" : "lean") : "general", e->block,
                 e->dc.pregen ? (e->dc.conn_bits && e->dc.path_tab ? "tabled" : "general") : "in-tick", rng);
   return PGTG_OK;
 }

@@ -35,6 +35,7 @@
 #define pg_atomic_or(p, v) atomicOr((p), (v))
 #define pg_atomic_add(p, v) atomicAdd((p), (v))
 #define pg_atomic_cas(p, o, n) atomicCAS((p), (o), (n))
+#define pg_atomic_min(p, v) atomicMin((p), (v))
 #define pg_store_streaming(ptr, v) __stcs((ptr), (v))  /* written once, never re-read by the kernel: evict-first */
 #define pg_prefetch_l2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))  /* fire-and-forget */
 /* 32 bytes with one 256-bit streaming store (sm_100: STG.256); ptr 32-byte aligned */
@@ -61,6 +62,7 @@ static inline uint32_t pg_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((u
 #define pg_atomic_or(p, v) (*(p) |= (v))
 static inline uint32_t pg_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline int pg_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline uint32_t pg_atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 static inline uint32_t pg_atomic_cas(uint32_t* p, uint32_t o, uint32_t n) { uint32_t c = *p; if (c == o) *p = n; return c; }
 #define pg_store_streaming(ptr, v) (*(ptr) = (v))
 #define pg_prefetch_l2(ptr) ((void)(ptr))
@@ -574,6 +576,8 @@ struct MapView {
   const uint16_t* border_slots;
   uint32_t graph;      // connectivity-table index of the generated map's edge set (valid when graph_valid)
   bool graph_valid;
+  uint32_t ng_key = 0xFFFFFFFFu;  // nearest_goal's answer computed beforehand (when ng_pre)
+  bool ng_pre = false;
   PG_MEMBER bool inside(int x, int y) const { return !(x < 0 || y < 0 || x >= c.WS || y >= c.HS); }  // map.py:44-47
   PG_MEMBER int start_tile() const { return plan_sy(plan) * c.W + plan_sx(plan); }
   PG_MEMBER int goal_tile() const { return plan_gy(plan) * c.W + plan_gx(plan); }
@@ -621,32 +625,37 @@ struct MapView {
   PG_MEMBER void consume_subgoal(int x, int y) { tiles[(y / TILE) * c.W + x / TILE] |= TD_USED; }
 
   // nearest remaining subgoal / final-goal square: first strict minimum of the Manhattan distance
-  // in the x-major scan (environment.py:1047-1053, 1474-1480) == lexicographic min of (d, x, y)
-  PG_MEMBER bool nearest_goal(int px, int py, int& gx, int& gy) const {
-    int best = 0x7fffffff, bx = 0, by = 0;
-    int gt = goal_tile();
-    for (int t = 0; t < c.T; t++) {
-      unsigned td = tiles[t];
-      int sg = td_sg(td);
-      if (!sg) continue;
-      int d;
-      if (t == gt) { d = plan_gd(plan); if (!((td_exits(td) >> d) & 1)) continue; }
-      else { if (td & TD_USED) continue; d = sg - 1; }
-      // claimed earlier by start? (only possible on degenerate fixed maps) -- labels decide
-      unsigned lab = (line_labels(t, td) >> (4 * d)) & 15;
-      if (lab != 1 && lab != 4) continue;
-      int ox = (t % c.W) * TILE, oy = (t / c.W) * TILE;
-      // the 3 squares of exit line d in ascending order (north (3..5,0) east (8,3..5) ...), from the derived LUT
+  // in the x-major scan (environment.py:1047-1053, 1474-1480) == lexicographic min of (d, x, y), i.e. the minimum of the
+  // key d << 16 | x << 8 | y. tile_goal_key = the best key among the goal-line squares of tile t (0xFFFFFFFF: none).
+  PG_MEMBER uint32_t tile_goal_key(int t, int px, int py) const {
+    const unsigned td = tiles[t];
+    const int sg = td_sg(td);
+    if (!sg) return 0xFFFFFFFFu;
+    int d;
+    if (t == goal_tile()) { d = plan_gd(plan); if (!((td_exits(td) >> d) & 1)) return 0xFFFFFFFFu; }
+    else { if (td & TD_USED) return 0xFFFFFFFFu; d = sg - 1; }
+    // claimed earlier by start? (only possible on degenerate fixed maps) -- labels decide
+    const unsigned lab = (line_labels(t, td) >> (4 * d)) & 15;
+    if (lab != 1 && lab != 4) return 0xFFFFFFFFu;
+    const int ox = (t % c.W) * TILE, oy = (t / c.W) * TILE;
+    uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int sq = L.line_sq[d][k];
-        const int X = ox + sq / TILE, Y = oy + sq % TILE;
-        const int dist = abs(X - px) + abs(Y - py);
-        if (dist < best || (dist == best && (X < bx || (X == bx && Y < by)))) { best = dist; bx = X; by = Y; }
-      }
+    for (int k = 0; k < 3; k++) {  // the 3 squares of exit line d (north (3..5,0) east (8,3..5) ...), from the derived LUT
+      const int sq = L.line_sq[d][k];
+      const int X = ox + sq / TILE, Y = oy + sq % TILE;
+      const uint32_t key = (uint32_t)(abs(X - px) + abs(Y - py)) << 16 | (uint32_t)X << 8 | (uint32_t)Y;
+      best = key < best ? key : best;
     }
-    gx = bx; gy = by;
-    return best != 0x7fffffff;
+    return best;
+  }
+  PG_MEMBER bool nearest_goal(int px, int py, int& gx, int& gy) const {
+    uint32_t best = ng_key;  // (the traffic tick computes the key beforehand, one tile per thread)
+    if (!ng_pre) {
+      best = 0xFFFFFFFFu;
+      for (int t = 0; t < c.T; t++) { const uint32_t k = tile_goal_key(t, px, py); best = k < best ? k : best; }
+    }
+    gx = (int)((best >> 8) & 255u); gy = (int)(best & 255u);
+    return best != 0xFFFFFFFFu;
   }
 };
 

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
   }
   __syncthreads();
   if (mine) tk_prefix(sh, sh.off, tid, nvalid, false);
+  if (c.num_rules > 0)  // the rule engine's heading needs the nearest goal-line square of the position before the move
+    for (int i = tid; i < nvalid * c.T; i += NT) tk_goal_key(c, sh, i / c.T, i % c.T, false);
   __syncthreads();
   const int total = sh.off[G];
 
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
   StepResult r;
   r.outcome = 0; r.ep_return = 0; r.ep_disc = 0;
   int len = 0;
-  if (mine) { r = tk_agent(c, p, sh, tid, env); len = r.outcome ? (int)sh.env[tid].e.elapsed : 0; }
+  if (mine) { r = tk_agent(c, p, sh, tid, env); len = r.outcome ? (int)sh.env[tid].e.elapsed : 0; sh.env[tid].ng_key = 0xFFFFFFFFu; }
   const bool done = r.outcome != 0;
   if (tid < ((G + 31) & ~31)) {  // warps that hold envs: episode statistics and the map requests of the finished ones
     const unsigned any = __ballot_sync(0xffffffffu, done);
@@ -101,12 +103,16 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
 
   // ---- terminal observation of the finished envs (optional output) ------------------------------------------
   if (c.write_final_obs && n_done) {  // CTA-uniform
+    if (c.use_nsd) {  // next_subgoal_direction of the terminal observation
+      for (int i = tid; i < nvalid * c.T; i += NT) if (sh.env[i / c.T].done) tk_goal_key(c, sh, i / c.T, i % c.T, true);
+      __syncthreads();
+    }
     for (int item = tid; item < total; item += NT) {
       const int g = sh.item_g[item];
       const TEnv& t = sh.env[g];
       if (t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
     }
-    if (done) tk_emit(c, p, sh, tid, env, true);
+    if (done) { tk_emit(c, p, sh, tid, env, true); sh.env[tid].ng_key = 0xFFFFFFFFu; }
     __syncthreads();
     phase_expand_final(c, p.f_obs_map, bs, tid, NT, env0, n_done);
     __syncthreads();
@@ -135,6 +141,10 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
   }
 
   // ---- map planes + scalars + state (per env) ---------------------------------------------------------------------
+  if (c.use_nsd) {  // next_subgoal_direction: nearest goal-line square of the observed position, one tile per thread
+    for (int i = tid; i < nvalid * c.T; i += NT) tk_goal_key(c, sh, i / c.T, i % c.T, true);
+    __syncthreads();
+  }
   if (mine) tk_emit(c, p, sh, tid, env, false);
   __syncthreads();
   if (tid == 0 && n_done) {

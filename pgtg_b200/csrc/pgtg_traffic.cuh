@@ -50,6 +50,7 @@ struct TEnv {
   int32_t in_tile;               // cars in that tile after the traffic advance
   uint32_t hist[5];              // their routes: 8-bit counter per route id
   int32_t hist_overflow;         // a route counter wrapped: the rule engine falls back to the list scan
+  uint32_t ng_key;               // nearest remaining goal-line square of the position the next per-env phase asks about (d << 16 | x << 8 | y)
   uint64_t bloom;                // 64-bit filter over the squares that hold (or held, this tick) a car: a clear bit = no car there
   int32_t n_despawn;             // cars that leave the map in this tick (counted by the intent phase)
   int32_t done;                  // StepResult.outcome of this tick
@@ -117,9 +118,22 @@ PG_HOSTDEV TkShared tk_carve(unsigned char* base, const TkLayout& L) {
   return s;
 }
 
-PG_HD MapView tk_map(const DevCfg& c, const TkShared& sh, int g) {
+PG_HD MapView tk_map(const DevCfg& c, const TkShared& sh, int g, bool with_goal_key = false) {
   MapView m = {c, *sh.lut, sh.tiles + g * c.tile_stride, sh.env[g].e.plan, nullptr, nullptr, nullptr, 0u, false};
+  if (with_goal_key) { m.ng_key = sh.env[g].ng_key; m.ng_pre = true; }
   return m;
+}
+// nearest_goal (rule engine's heading, next_subgoal_direction) one TILE per thread: min over the tile's goal-line squares
+// of the key, folded into the env's ng_key with a shared-memory atomicMin. The position asked about: the agent's.
+PG_HD void tk_goal_key(const DevCfg& c, const TkShared& sh, int g, int tile, bool clamp) {
+  TEnv& t = sh.env[g];
+  const MapView m = tk_map(c, sh, g);
+  int px = t.e.x, py = t.e.y;
+  if (clamp) {  // get_observation clamps the position into the map first (:1352-1353)
+    px = px < 0 ? 0 : (px > c.WS - 1 ? c.WS - 1 : px); py = py < 0 ? 0 : (py > c.HS - 1 ? c.HS - 1 : py);
+  }
+  const uint32_t k = m.tile_goal_key(tile, px, py);
+  if (k != 0xFFFFFFFFu) pg_atomic_min(&t.ng_key, k);
 }
 
 // ---- 4-bit occupancy counters (exact below TK_OCC_SAT; at TK_OCC_SAT sticky = "count the list") ----------------
@@ -196,7 +210,7 @@ PG_HD void tk_stage_env(const DevCfg& c, const DevPtrs& p, const TkShared& sh, i
   int tx = floordiv9(e.x), ty = floordiv9(e.y);
   t.tile_x = tx < 0 ? 0 : (tx > c.W - 1 ? c.W - 1 : tx);
   t.tile_y = ty < 0 ? 0 : (ty > c.H - 1 ? c.H - 1 : ty);
-  t.in_tile = 0; t.n_despawn = 0; t.done = 0; t.new_cars = 0; t.num_positions = 0; t.perm_h = 2; t.hist_overflow = 0; t.bloom = 0;
+  t.in_tile = 0; t.n_despawn = 0; t.done = 0; t.new_cars = 0; t.num_positions = 0; t.perm_h = 2; t.hist_overflow = 0; t.bloom = 0; t.ng_key = 0xFFFFFFFFu;
 #pragma unroll
   for (int i = 0; i < 5; i++) t.hist[i] = 0;
 }
@@ -481,7 +495,7 @@ PG_HD StepResult tk_agent(const DevCfg& c, const DevPtrs& p, const TkShared& sh,
   EnvRegs& e = t.e;
   e.next_car_id += (uint32_t)t.n_despawn;
   e.misc ^= 1u << 15;  // the commit phase wrote the other half: it is the live list now
-  MapView m = tk_map(c, sh, g);
+  MapView m = tk_map(c, sh, g, true);  // (ng_key: nearest goal-line square of the position before the move)
   ExtTraffic tr = {&sh, g};
   StepResult r = env_step<PGTG_RNG_PHILOX, false, ExtTraffic>(c, p, m, e, env, t.action, tr);
   write_step_outputs<false>(c, p, env, e, r);
@@ -509,7 +523,7 @@ PG_HD void tk_emit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g,
   const TEnv& t = sh.env[g];
   EnvRegs e = t.e;
   e.misc &= 0xFFFFu;  // no cars for env_observe's own traffic loop
-  const MapView m = tk_map(c, sh, g);
+  const MapView m = tk_map(c, sh, g, c.use_nsd != 0);  // (ng_key: ... of the position observed)
   int32_t pos[2], vel[2], nsd;
   env_observe<false>(c, p, m, e, env, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, pos, vel, &nsd);
   if (final_obs) {

@@ -154,6 +154,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
     tk_stage_env(c, p, sh, g, env, a);
   }
   for (int g = 0; g < nvalid; g++) tk_prefix(sh, sh.off, g, nvalid, false);
+  if (c.num_rules > 0) for (int i = 0; i < nvalid * c.T; i++) tk_goal_key(c, sh, i / c.T, i % c.T, false);
   const int total = sh.off[G];
   for (int t = 0; t < NT; t++)
     for (int item = t; item < total; item += NT) { int g = sh.item_g[item]; tk_intent(c, p, sh, g, item - sh.off[g], env0 + g); }
@@ -162,6 +163,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
   double st[8] = {0};
   for (int g = 0; g < nvalid; g++) {
     StepResult r = tk_agent(c, p, sh, g, env0 + g);
+    sh.env[g].ng_key = 0xFFFFFFFFu;
     if (r.outcome) {
       sh.done_list[n_done++] = g;
       st[0] += 1; st[1] += r.ep_return; st[2] += sh.env[g].e.elapsed;
@@ -179,7 +181,8 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
       const TEnv& t = sh.env[g];
       if (t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
     }
-    for (int k = 0; k < n_done; k++) tk_emit(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true);
+    if (c.use_nsd) for (int i = 0; i < nvalid * c.T; i++) if (sh.env[i / c.T].done) tk_goal_key(c, sh, i / c.T, i % c.T, true);
+    for (int k = 0; k < n_done; k++) { tk_emit(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true); sh.env[sh.done_list[k]].ng_key = 0xFFFFFFFFu; }
     for (int t = 0; t < NT; t++) phase_expand_final(c, p.f_obs_map, bs, t, NT, env0, n_done);
     for (int i = 0; i < sh.bits_words; i++) sh.bits[i] = 0;
   }
@@ -195,6 +198,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
     for (int t = 0; t < NT; t++)
       for (int item = t; item < total2; item += NT) { int g = sh.item_g[item]; tk_new_car(c, p, sh, g, item - sh.off2[g], env0 + g); }
   }
+  if (c.use_nsd) for (int i = 0; i < nvalid * c.T; i++) tk_goal_key(c, sh, i / c.T, i % c.T, true);
   for (int g = 0; g < nvalid; g++) tk_emit(c, p, sh, g, env0 + g, false);
   for (int t = 0; t < NT; t++) phase_expand(c, p.obs_map, bs, t, NT, env0, nvalid, p.obs_packed);
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
