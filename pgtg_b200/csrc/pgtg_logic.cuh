@@ -1038,10 +1038,32 @@ PG_HD void emit_bits(uint32_t* bits, uint32_t off, uint32_t v) {
   if (s && (v >> (32 - s))) pg_atomic_or(&bits[(off >> 5) + 1], v >> (32 - s));
 }
 
+// one column of a sliding-window plane (environment.py:1369-1385, map.py:80-118): bit iy = the square (X, y0 + iy) carries
+// `kind`; squares outside the map are walls and nothing else (fill {"wall"}, :1384)
+PG_HD uint32_t sliding_column_bits(const DevCfg& c, const MapView& m, int kind, int phase, int X, int y0) {
+  uint32_t col = 0;
+  if (X < 0 || X >= c.WS) return kind == PGTG_CH_WALLS ? (c.P >= 32 ? 0xFFFFFFFFu : ((1u << c.P) - 1u)) : 0u;
+  const int ttx = X / TILE, lx = X - ttx * TILE;
+  for (int iy = 0; iy < c.P;) {
+    const int Y = y0 + iy;
+    if (Y < 0 || Y >= c.HS) { if (kind == PGTG_CH_WALLS) col |= 1u << iy; iy++; continue; }
+    const int tty = Y / TILE, ly = Y - tty * TILE;
+    uint32_t w[3];
+    tile_plane(c, m, kind, tty * c.W + ttx, phase, w);
+    const uint32_t c9 = col9(w, lx) >> ly;  // rows ly.. of this tile column
+    int cnt = TILE - ly;
+    if (cnt > c.P - iy) cnt = c.P - iy;
+    col |= (c9 & ((1u << cnt) - 1u)) << iy;
+    iy += cnt;
+  }
+  return col;
+}
+
 // writes env's C*P*P observation bits at bit offset `base` of `bits`, plus position/velocity/nsd
+// (planes = false: only the scalars -- the caller writes the planes itself, e.g. one window column per thread)
 template <bool LEAN = false>
 PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, uint32_t* bits,
-                        uint32_t base, int32_t* pos, int32_t* vel, int32_t* nsd) {
+                        uint32_t base, int32_t* pos, int32_t* vel, int32_t* nsd, bool planes = true) {
   int pix = e.x < 0 ? 0 : (e.x > c.WS - 1 ? c.WS - 1 : e.x);  // :1352-1356
   int piy = e.y < 0 ? 0 : (e.y > c.HS - 1 ? c.HS - 1 : e.y);
   int tx = pix / TILE, ty = piy / TILE;
@@ -1049,7 +1071,9 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
   const int ncars = LEAN ? 0 : misc_ncars(e.misc);
   const uint64_t* live = LEAN ? nullptr : car_list(c, p, env, misc_half(e.misc));
   int PP = c.P * c.P;
-  if (LEAN || (!c.sliding && c.obs_fast)) {
+  if (!LEAN && !planes && !c.sliding) {
+    pos[0] = pix - tx * TILE; pos[1] = piy - ty * TILE;
+  } else if (LEAN || (!c.sliding && c.obs_fast)) {
     // Fixed window, kind by kind: a tile has walls, at most ONE obstacle / light plane, goal-ish
     // lines only on path tiles; everything else stays zero and costs nothing (same bits as the
     // channel loop below, which remains for feature lists that name a kind twice).
@@ -1117,7 +1141,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
     pos[0] = pix - tx * TILE; pos[1] = piy - ty * TILE;  // :1448-1461
   } else {
     int k = c.window_k, x0 = e.x - k, y0 = e.y - k;  // window around the UNCLAMPED position (:1370-1377)
-    for (int ch = 0; ch < c.C; ch++) {
+    for (int ch = 0; planes && ch < c.C; ch++) {
       int kind = c.channel_kind[ch];
       if (kind == PGTG_CH_ZERO) continue;
       uint32_t off = base + ch * PP;
@@ -1129,28 +1153,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
         }
         continue;
       }
-      for (int ix = 0; ix < c.P; ix++) {
-        int X = x0 + ix;
-        uint32_t col = 0;
-        uint32_t full = c.P >= 32 ? 0xFFFFFFFFu : ((1u << c.P) - 1u);
-        if (X < 0 || X >= c.WS) { if (kind == PGTG_CH_WALLS) col = full; }  // fill {"wall"} (:1384)
-        else {
-          int ttx = X / TILE, lx = X - ttx * TILE;
-          for (int iy = 0; iy < c.P;) {
-            int Y = y0 + iy;
-            if (Y < 0 || Y >= c.HS) { if (kind == PGTG_CH_WALLS) col |= 1u << iy; iy++; continue; }
-            int tty = Y / TILE, ly = Y - tty * TILE;
-            uint32_t w[3];
-            tile_plane(c, m, kind, tty * c.W + ttx, phase, w);
-            uint32_t c9 = col9(w, lx) >> ly;  // rows ly.. of this tile column
-            int cnt = TILE - ly;
-            if (cnt > c.P - iy) cnt = c.P - iy;
-            col |= (c9 & ((1u << cnt) - 1u)) << iy;
-            iy += cnt;
-          }
-        }
-        emit_bits(bits, off + ix * c.P, col);
-      }
+      for (int ix = 0; ix < c.P; ix++) emit_bits(bits, off + ix * c.P, sliding_column_bits(c, m, kind, phase, x0 + ix, y0));
     }
     pos[0] = k; pos[1] = k;  // quirk A.3-4
   }

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
       const TEnv& t = sh.env[g];
       if (t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
     }
+    if (c.sliding)
+      for (int i = tid; i < nvalid * c.C * c.P; i += NT) if (sh.env[i / (c.C * c.P)].done) tk_sliding_column(c, sh, i / (c.C * c.P), i % (c.C * c.P));
     if (done) { tk_emit(c, p, sh, tid, env, true); sh.env[tid].ng_key = 0xFFFFFFFFu; }
     __syncthreads();
     phase_expand_final(c, p.f_obs_map, bs, tid, NT, env0, n_done);
@@ -129,7 +131,12 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
 
   // ---- same-step auto-reset: the map (per env), then the new episode's cars (flat) ------------------------------
   if (n_done) {
-    if (done) tk_reset<TMAX, PREGEN>(c, p, sh, tid, env);
+    if (done) tk_reset_map<TMAX, PREGEN>(c, p, sh, tid, env);
+    __syncthreads();
+    if (NT >= 3 * G) {  // lane squares, spawner list and placement keys of the new maps: three groups of warps side by side
+      const int part = tid / G, g = tid - part * G;
+      if (part < 3 && g < nvalid && sh.env[g].done) tk_reset_traffic(c, p, sh, g, env0 + g, 1 << part);
+    } else if (done) tk_reset_traffic(c, p, sh, tid, env, 7);
     __syncthreads();
     if (mine) tk_prefix(sh, sh.off2, tid, nvalid, true);  // (rewrites the item table: the tick's items are done with)
     __syncthreads();
@@ -145,6 +152,8 @@ __global__ void __launch_bounds__(NT, MINB) pgtg_traffic_tick_kernel(const __gri
     for (int i = tid; i < nvalid * c.T; i += NT) tk_goal_key(c, sh, i / c.T, i % c.T, true);
     __syncthreads();
   }
+  if (c.sliding)  // sliding-window planes, one (plane, column) per thread
+    for (int i = tid; i < nvalid * c.C * c.P; i += NT) tk_sliding_column(c, sh, i / (c.C * c.P), i % (c.C * c.P));
   if (mine) tk_emit(c, p, sh, tid, env, false);
   __syncthreads();
   if (tid == 0 && n_done) {

@@ -518,6 +518,15 @@ PG_HD void tk_car_bit(const DevCfg& c, uint32_t* bits, uint32_t base, int ex, in
     if (ix >= 0 && ix < c.P && iy >= 0 && iy < c.P) emit_bits(bits, base + (uint32_t)(ch * c.P * c.P + ix * c.P + iy), 1u);
   }
 }
+// sliding window: one (plane, window column) per thread
+PG_HD void tk_sliding_column(const DevCfg& c, const TkShared& sh, int g, int item) {
+  const int ch = item / c.P, ix = item - ch * c.P, kind = c.channel_kind[ch];
+  if (kind == PGTG_CH_ZERO || kind == PGTG_CH_TRAFFIC) return;  // (the traffic plane comes from the car threads)
+  const EnvRegs& e = sh.env[g].e;
+  const MapView m = tk_map(c, sh, g);
+  const uint32_t col = sliding_column_bits(c, m, kind, light_phase(c, misc_light(e.misc)), e.x - c.window_k + ix, e.y - c.window_k);
+  emit_bits(sh.bits, (uint32_t)g * (uint32_t)c.obs_bits + (uint32_t)(ch * c.P * c.P + ix * c.P), col);
+}
 // map planes + scalars of env g (the traffic plane comes from the car threads); final = terminal observation
 PG_HD void tk_emit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env, bool final_obs) {
   const TEnv& t = sh.env[g];
@@ -525,7 +534,7 @@ PG_HD void tk_emit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g,
   e.misc &= 0xFFFFu;  // no cars for env_observe's own traffic loop
   const MapView m = tk_map(c, sh, g, c.use_nsd != 0);  // (ng_key: ... of the position observed)
   int32_t pos[2], vel[2], nsd;
-  env_observe<false>(c, p, m, e, env, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, pos, vel, &nsd);
+  env_observe<false>(c, p, m, e, env, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, pos, vel, &nsd, !c.sliding);  // (sliding planes: tk_sliding_column)
   if (final_obs) {
     p.f_obs_position[2 * env] = pos[0]; p.f_obs_position[2 * env + 1] = pos[1];
     p.f_obs_velocity[2 * env] = vel[0]; p.f_obs_velocity[2 * env + 1] = vel[1];
@@ -536,26 +545,31 @@ PG_HD void tk_emit(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g,
 }
 
 // ---- reset of a finished env: one env per thread (PGTGEnv.reset, environment.py:581-656, minus the cars) ------
+// part A: the map and the agent
 template <int TMAX, bool PREGEN>
-PG_HD void tk_reset(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env) {
+PG_HD void tk_reset_map(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env) {
   TEnv& t = sh.env[g];
   EnvRegs& e = t.e;
   MapView m = tk_map(c, sh, g);
   if (PREGEN) env_reset_pregenerated<PGTG_RNG_PHILOX, false, true>(c, p, m, e, env);
   else env_reset<PGTG_RNG_PHILOX, TMAX, true>(c, p, m, e, env);
-  m.plan = e.plan;
-  tk_spawner_list(c, p, sh, m, env);
-  uint16_t* colpre = sh.colpre + g * sh.ncolp;
-  const int np = lane_tile_prefix(c, m, colpre);
-  int nc = initial_car_count(c, np);
-  if (nc > c.max_cars) { e.err |= 32; nc = c.max_cars; }
-  t.num_positions = np; t.new_cars = nc;
-  if (nc > 0) {
-    philox_car_block(t.key, e.elapsed, e.episode, -1, 0, t.perm_keys);
-    t.perm_h = feistel_bits(np);
+}
+// part B, three independent pieces that different warps run side by side on the new map:
+// 1 the lane squares (how many cars, _create_initial_traffic :833-834), 2 the car_spawners list, 4 the placement keys
+PG_HD void tk_reset_traffic(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int env, int parts) {
+  TEnv& t = sh.env[g];
+  EnvRegs& e = t.e;
+  const MapView m = tk_map(c, sh, g);
+  if (parts & 2) tk_spawner_list(c, p, sh, m, env);
+  if (parts & 4) philox_car_block(t.key, e.elapsed, e.episode, -1, 0, t.perm_keys);
+  if (parts & 1) {
+    const int np = lane_tile_prefix(c, m, sh.colpre + g * sh.ncolp);
+    int nc = initial_car_count(c, np);
+    if (nc > c.max_cars) { e.err |= 32; nc = c.max_cars; }
+    t.num_positions = np; t.new_cars = nc; t.perm_h = feistel_bits(np);
+    e.misc = misc_pack(0, 0, nc, 0);
+    e.next_car_id = (uint32_t)nc;  // ids follow the slots (_create_initial_traffic, :830-879)
   }
-  e.misc = misc_pack(0, 0, nc, 0);
-  e.next_car_id = (uint32_t)nc;  // ids follow the slots (_create_initial_traffic, :830-879)
 }
 // one car of the new episode per thread
 PG_HD void tk_new_car(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int g, int j, int env) {

@@ -182,6 +182,7 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
       if (t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
     }
     if (c.use_nsd) for (int i = 0; i < nvalid * c.T; i++) if (sh.env[i / c.T].done) tk_goal_key(c, sh, i / c.T, i % c.T, true);
+    if (c.sliding) for (int i = 0; i < nvalid * c.C * c.P; i++) if (sh.env[i / (c.C * c.P)].done) tk_sliding_column(c, sh, i / (c.C * c.P), i % (c.C * c.P));
     for (int k = 0; k < n_done; k++) { tk_emit(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true); sh.env[sh.done_list[k]].ng_key = 0xFFFFFFFFu; }
     for (int t = 0; t < NT; t++) phase_expand_final(c, p.f_obs_map, bs, t, NT, env0, n_done);
     for (int i = 0; i < sh.bits_words; i++) sh.bits[i] = 0;
@@ -192,13 +193,16 @@ static void run_traffic_block(pgtg_env* h, const void* actions, int action_bytes
     if (!t.done) tk_car_bit(c, sh.bits, (uint32_t)g * (uint32_t)c.obs_bits, t.e.x, t.e.y, sh.fxy[g * sh.MC + item - sh.off[g]]);
   }
   if (n_done) {
-    for (int k = 0; k < n_done; k++) tk_reset<TMAX, PREGEN>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+    for (int k = 0; k < n_done; k++) tk_reset_map<TMAX, PREGEN>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
+    for (int part = 0; part < 3; part++)
+      for (int k = 0; k < n_done; k++) tk_reset_traffic(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], 1 << part);
     for (int g = 0; g < nvalid; g++) tk_prefix(sh, sh.off2, g, nvalid, true);
     const int total2 = sh.off2[G];
     for (int t = 0; t < NT; t++)
       for (int item = t; item < total2; item += NT) { int g = sh.item_g[item]; tk_new_car(c, p, sh, g, item - sh.off2[g], env0 + g); }
   }
   if (c.use_nsd) for (int i = 0; i < nvalid * c.T; i++) tk_goal_key(c, sh, i / c.T, i % c.T, true);
+  if (c.sliding) for (int i = 0; i < nvalid * c.C * c.P; i++) tk_sliding_column(c, sh, i / (c.C * c.P), i % (c.C * c.P));
   for (int g = 0; g < nvalid; g++) tk_emit(c, p, sh, g, env0 + g, false);
   for (int t = 0; t < NT; t++) phase_expand(c, p.obs_map, bs, t, NT, env0, nvalid, p.obs_packed);
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
