@@ -283,6 +283,20 @@ static int rng_car_choice_cdf(rctx* r, int slot, int pos, const double* cdf, int
   return i;
 }
 
+/* Index draws of the edge-removal and border-connection phases. Philox mode (product specification, pgtg_logic.cuh
+ * map_index): a 32-bit word serves successive draws -- draw = hi32(word * n), the low half of the product is the next
+ * draw's word -- while the product of the served ranges, the new one included, stays <= 2^16. */
+typedef struct { uint32_t rem, used; } map_draw;
+static int map_index(rctx* r, map_draw* md, int n) {
+  if (r->b->cfg.rng_mode != PGTG_RNG_PHILOX) return rng_index(r, PGTG_STREAM_MAP, n);
+  if (n <= 1) return 0;
+  uint32_t w = md->rem;
+  if (md->used == 0 || md->used * (uint32_t)n > 65536u) { w = philox_word(r, PGTG_STREAM_MAP); md->used = 1; }
+  uint64_t prod = (uint64_t)w * (uint32_t)n;
+  md->rem = (uint32_t)prod; md->used *= (uint32_t)n;
+  return (int)(prod >> 32);
+}
+
 /* Generator.choice(n, size=k, replace=False): k distinct indices in returned order.
  * Philox mode: the keyed Feistel permutation of the car-stream specification above. */
 static void rng_distinct(rctx* r, int stream, int n, int k, int* out) {
@@ -447,8 +461,17 @@ static void generate_map(rctx* r, ora_env* e) {
   int keep = c->edges_to_keep;
   int path[GMAXN];
   int plen = g_bfs(&g, S, E, path);
+  map_draw md = {0, 0};
+  if (c->rng_mode == PGTG_RNG_PHILOX) {
+    /* Philox specification: the draw is over the grid edges not tried yet (what the reference's draw over removable_edges
+     * amounts to: both directions of an edge are listed and leave the list together), enumerated in the order of the
+     * product's connectivity bits: horizontal edges row by row, then vertical edges by tile index y * W + x. */
+    n_rem = 0;
+    for (int y = 0; y < H; y++) for (int x = 0; x + 1 < W; x++) { rem[n_rem][0] = x * H + y; rem[n_rem][1] = (x + 1) * H + y; n_rem++; }
+    for (int y = 0; y + 1 < H; y++) for (int x = 0; x < W; x++) { rem[n_rem][0] = x * H + y; rem[n_rem][1] = x * H + y + 1; n_rem++; }
+  }
   while (g_edge_count(&g) - 4 > keep && n_rem > 0) { /* :245 */
-    int idx = rng_index(r, PGTG_STREAM_MAP, n_rem); /* :249 */
+    int idx = map_index(r, &md, n_rem); /* :249 */
     int a = rem[idx][0], b = rem[idx][1];
     /* removable_edges.remove(chosen); .remove(reverse) (:252-253) */
     int w = 0;
@@ -501,7 +524,7 @@ static void generate_map(rctx* r, ora_env* e) {
     }
   }
   for (int k = 0; k < c->border_connections; k++) {
-    int idx = rng_index(r, PGTG_STREAM_MAP, nb); /* :367 */
+    int idx = map_index(r, &md, nb); /* :367 */
     e->exits[bc[idx][0] * W + bc[idx][1]] |= (unsigned char)(1 << bc[idx][2]);
     for (int j = idx; j + 1 < nb; j++) memcpy(bc[j], bc[j + 1], sizeof bc[0]);
     nb--;

@@ -115,26 +115,25 @@ __global__ void __launch_bounds__(128) pgtg_build_path_table_kernel(const __grid
     table[g] = path_table_entry(c, *sh.lut, g, sh.tiles + threadIdx.x * c.tile_stride);
 }
 
-// FlattenObservation view: one thread per output float, coalesced float32 stores; reads the int8
-// planes through L2 (they were just written by the tick).
-__global__ void pgtg_flatten_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, FlatOrder order,
-                                    float* __restrict__ out, int dim) {
-  const int PP = c.P * c.P, map_dim = c.C * PP, nsd_dim = c.use_nsd ? 9 : 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)c.N * dim; i += (size_t)gridDim.x * blockDim.x) {
-    int env = (int)(i / dim), j = (int)(i - (size_t)env * dim);
-    float v;
-    if (j < map_dim) {
-      int k = j / PP, cell = j - k * PP;
-      v = (float)p.obs_map[((size_t)env * c.C + order.plane[k]) * PP + cell];
-    } else if (j < map_dim + nsd_dim) {
-      v = (p.obs_nsd[env] + 1 == j - map_dim) ? 1.0f : 0.0f;  // Discrete(9, start=-1) one-hot
-    } else if (j < map_dim + nsd_dim + 18) {
-      int q = j - map_dim - nsd_dim;  // MultiDiscrete([9, 9]) -> two one-hots
-      v = (p.obs_position[2 * env + (q >= 9)] == (q >= 9 ? q - 9 : q)) ? 1.0f : 0.0f;
-    } else {
-      v = (float)p.obs_velocity[2 * env + (j - map_dim - nsd_dim - 18)];
+// FlattenObservation view: one warp per env, plane by plane (no per-element divisions), coalesced float32 stores;
+// reads the int8 planes through L2 (they were just written by the tick).
+__global__ void __launch_bounds__(256) pgtg_flatten_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, FlatOrder order,
+                                                          float* __restrict__ out, int dim) {
+  const int PP = c.P * c.P, lane = threadIdx.x & 31;
+  for (int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); env < c.N; env += gridDim.x * (blockDim.x >> 5)) {
+    float* o = out + (size_t)env * dim;
+    const int8_t* m = p.obs_map + (size_t)env * c.C * PP;
+    for (int k = 0; k < c.C; k++) {
+      const int8_t* src = m + order.plane[k] * PP;
+      for (int cell = lane; cell < PP; cell += 32) o[k * PP + cell] = (float)src[cell];
     }
-    out[i] = v;
+    o += c.C * PP;
+    if (c.use_nsd) {  // Discrete(9, start=-1) one-hot
+      if (lane < 9) o[lane] = (p.obs_nsd[env] + 1 == lane) ? 1.0f : 0.0f;
+      o += 9;
+    }
+    if (lane < 18) o[lane] = (p.obs_position[2 * env + (lane >= 9)] == (lane >= 9 ? lane - 9 : lane)) ? 1.0f : 0.0f;  // MultiDiscrete([9, 9]) -> two one-hots
+    else if (lane < 20) o[lane] = (float)p.obs_velocity[2 * env + (lane - 18)];
   }
 }
 
@@ -221,9 +220,9 @@ static int bk_info(pgtg_env* e, int32_t* out_dev) {
 static int bk_flatten(pgtg_env* e, void* stream) {
   pgtg::FlatOrder order;
   for (int i = 0; i < PGTG_MAX_CHANNELS; i++) order.plane[i] = e->flat_order[i];
-  size_t total = (size_t)e->dc.N * e->flat_dim;
-  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  pgtg::pgtg_flatten_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(e->dc, e->dp, order, e->flat, e->flat_dim);
+  const int warps = 8, want = (e->dc.N + warps - 1) / warps;
+  const int blocks = want < 148 * 32 ? want : 148 * 32;
+  pgtg::pgtg_flatten_kernel<<<blocks, 32 * warps, 0, (cudaStream_t)stream>>>(e->dc, e->dp, order, e->flat, e->flat_dim);
   return ck(cudaGetLastError());
 }
 static int bk_stats_reset(pgtg_env* e, void* stream) {

@@ -678,6 +678,22 @@ PG_HD void graph_to_boards(const DevCfg& c, uint32_t graph, uint32_t& E, uint32_
   E = e; S = graph >> c.conn_ne;
 }
 
+// Philox specification of the index draws of the edge-removal and border-connection phases: a 32-bit word serves successive
+// draws -- draw = hi32(word * n), the low half of the product becomes the word of the next draw -- while the product of the
+// ranges it has served, the new one included, stays <= 2^16 (so every draw still sees >= 16 fresh bits beyond its own range:
+// bias below 2^-16). Tape / numpy modes draw exactly as the reference does.
+struct MapDraw { uint32_t rem, used; };
+template <int RNG>
+PG_HD int map_index(Rng<RNG>& rng, MapDraw& md, int n) {
+  if (RNG != PGTG_RNG_PHILOX) return rng.index(PGTG_STREAM_MAP, n);
+  if (n <= 1) return 0;
+  uint32_t w = md.rem;
+  if (md.used == 0 || md.used * (uint32_t)n > 65536u) { w = rng.word(PGTG_STREAM_MAP); md.used = 1; }
+  const uint64_t prod = (uint64_t)w * (uint32_t)n;
+  md.rem = (uint32_t)prod; md.used *= (uint32_t)n;
+  return (int)(prod >> 32);
+}
+
 // TABLED = compile-time promise that both per-handle tables exist (fixed start/goal, <= 16 tiles,
 // <= 24 inner edges): the flood fill, the BFS and the start/goal draws are not emitted.
 template <int RNG, int TMAX, bool TABLED = false>
@@ -694,14 +710,52 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
   Board<TMAX> E, S;
 #pragma unroll
   for (int k = 0; k < Board<TMAX>::NW; k++) { E.w[k] = c.full_e[k]; S.w[k] = c.full_s[k]; }
+  // with the connectivity table the graph is kept as the table index itself (one bit per grid edge)
+  const bool tabled = TABLED || (TMAX <= 32 && c.conn_bits != 0);
+  uint32_t graph = tabled ? ((c.conn_bits >= 32 ? 0u : (1u << c.conn_bits)) - 1u) : 0u;
+  MapDraw md = {0u, 0u};
+  if (RNG == PGTG_RNG_PHILOX) {
+    // Philox specification: each trip picks uniformly among the grid edges not tried yet -- exactly what the reference's
+    // draw over removable_edges amounts to (both directions of an edge are listed and leave the list together, :249-253) --
+    // enumerated in the order of the connectivity-table bits: horizontal edges row by row, then vertical edges by tile.
+    constexpr int UW = (2 * TMAX + 31) / 32;
+    uint32_t untried[UW];
+    const int n_he = c.H * (W - 1), n_und = n_he + W * (c.H - 1);
+    int n_untried = n_und, cur = 2 * n_und;
+#pragma unroll
+    for (int i = 0; i < UW; i++) untried[i] = (i * 32 + 32 <= n_und) ? 0xFFFFFFFFu : (i * 32 < n_und ? ((1u << (n_und & 31)) - 1u) : 0u);
+    while (cur > c.edges_to_keep && n_untried > 0) {  // :245
+      int idx = map_index<RNG>(rng, md, n_untried);  // :249
+      int pos;
+      if (UW == 1) { pos = select32(untried[0], idx); untried[0] &= ~(1u << pos); }
+      else {
+        int wi = 0;
+        for (;; wi++) { int pc = pg_popc(untried[wi]); if (idx < pc) break; idx -= pc; }
+        const int bpos = select32(untried[wi], idx);
+        untried[wi] &= ~(1u << bpos);
+        pos = wi * 32 + bpos;
+      }
+      n_untried--;
+      if (tabled) {
+        const uint32_t g2 = graph & ~(1u << pos);
+        const bool keep = (pg_ldg(&p.conn_table[g2 >> 5]) >> (g2 & 31)) & 1u;
+        graph = keep ? g2 : graph;
+        cur -= keep ? 2 : 0;
+        continue;
+      }
+      const bool horiz = pos < n_he;
+      const int lo = horiz ? (pos / (W - 1)) * W + pos % (W - 1) : pos - n_he;
+      const int a = lo, b = horiz ? lo + 1 : lo + W;
+      if (horiz) bclr(E, lo); else bclr(S, lo);
+      if (still_connected<TMAX>(c, p, E, S, a, b, st, gt)) cur -= 2;
+      else { if (horiz) bset(E, lo); else bset(S, lo); }
+    }
+  } else {
   constexpr int AW = (4 * TMAX + 31) / 32;
   uint32_t alive[AW];
   int n_tab = c.n_edge_tab, n_alive = n_tab, cur = n_tab;
 #pragma unroll
   for (int i = 0; i < AW; i++) alive[i] = (i * 32 + 32 <= n_tab) ? 0xFFFFFFFFu : (i * 32 < n_tab ? ((1u << (n_tab & 31)) - 1u) : 0u);
-  // with the connectivity table the graph is kept as the table index itself (one bit per grid edge)
-  const bool tabled = TABLED || (TMAX <= 32 && c.conn_bits != 0);
-  uint32_t graph = tabled ? ((c.conn_bits >= 32 ? 0u : (1u << c.conn_bits)) - 1u) : 0u;
   while (cur > c.edges_to_keep && n_alive > 0) {  // :245
     int idx = rng.index(PGTG_STREAM_MAP, n_alive);  // :249
     int i;
@@ -741,6 +795,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     if (still_connected<TMAX>(c, p, E, S, a, b, st, gt)) cur -= 2;
     else { if (horiz) bset(E, lo); else bset(S, lo); }
   }
+  }
   if (tabled) {  // back to the boards: E has a hole after every row, S is contiguous
     graph_to_boards(c, graph, E.w[0], S.w[0]);
     m.graph = graph; m.graph_valid = true;
@@ -760,7 +815,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
   uint64_t slots = c.n_border_slots >= 64 ? ~0ull : ((1ull << c.n_border_slots) - 1ull);
   int n_slots = c.n_border_slots;
   for (int k = 0; k < c.border_connections && n_slots > 0; k++) {
-    int idx = rng.index(PGTG_STREAM_MAP, n_slots);  // :367
+    int idx = map_index<RNG>(rng, md, n_slots);  // :367
     uint32_t lo32 = (uint32_t)slots, hi32 = (uint32_t)(slots >> 32);
     int pc0 = pg_popc(lo32);
     bool hi = idx >= pc0;
