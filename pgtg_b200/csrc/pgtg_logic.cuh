@@ -576,6 +576,14 @@ PG_HD int select32(uint32_t v, int n) {
   return pos;
 }
 
+// the same through a 2 KB table (position of the k-th set bit of every byte): a dozen instructions and one shared-memory byte
+PG_HD int select32_lut(const uint8_t* sel8, uint32_t v, int n) {
+  const int c0 = pg_popc(v & 0xFFu), c1 = c0 + pg_popc(v & 0xFF00u), c2 = c1 + pg_popc(v & 0xFF0000u);
+  const int k = (n >= c0) + (n >= c1) + (n >= c2);
+  const int base = k == 0 ? 0 : k == 1 ? c0 : k == 2 ? c1 : c2;
+  return 8 * k + sel8[((v >> (8 * k)) & 255u) * 8 + (n - base)];
+}
+
 // Does removing edge (a, b) keep start and goal connected? E bit i: edge i<->i+1, S bit i: edge
 // i<->i+W (the edge is already cleared). Flood from a: reaching b means nothing changed (early
 // exit, typically after going round one grid face); otherwise the flood ends on a's whole
@@ -727,7 +735,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     while (cur > c.edges_to_keep && n_untried > 0) {  // :245
       int idx = map_index<RNG>(rng, md, n_untried);  // :249
       int pos;
-      if (UW == 1) { pos = select32(untried[0], idx); untried[0] &= ~(1u << pos); }
+      if (UW == 1) { pos = m.sel8 ? select32_lut(m.sel8, untried[0], idx) : select32(untried[0], idx); untried[0] &= ~(1u << pos); }
       else {
         int wi = 0;
         for (;; wi++) { int pc = pg_popc(untried[wi]); if (idx < pc) break; idx -= pc; }
@@ -819,7 +827,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     uint32_t lo32 = (uint32_t)slots, hi32 = (uint32_t)(slots >> 32);
     int pc0 = pg_popc(lo32);
     bool hi = idx >= pc0;
-    int i = select32(hi ? hi32 : lo32, hi ? idx - pc0 : idx) + (hi ? 32 : 0);
+    int i = (m.sel8 ? select32_lut(m.sel8, hi ? hi32 : lo32, hi ? idx - pc0 : idx) : select32(hi ? hi32 : lo32, hi ? idx - pc0 : idx)) + (hi ? 32 : 0);
     slots &= ~(1ull << i);
     n_slots--;
     unsigned v = m.border_slots[i];

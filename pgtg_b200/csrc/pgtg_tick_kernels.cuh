@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(128, TABLED ? PGTG_MAPGEN_TABLED_MIN_BLOCKS : 
   if (blockIdx.x * blockDim.x >= count) return;
   BlockShared sh = carve_layout(smem, layout);
   stage_tables(c, p, sh, threadIdx.x, blockDim.x);
+  for (int i = threadIdx.x; i < 2048 / 16; i += blockDim.x) ((uint4*)sh.sel8)[i] = __ldg((const uint4*)p.sel8 + i);  // k-th-set-bit table
   __syncthreads();
   const uint2* list = p.regen_list + (size_t)parity * 2 * c.N;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {

@@ -128,6 +128,7 @@ static void run_mapgen(pgtg_env* h) {
     memset(smem, 0xA5, bytes);
     BlockShared sh = carve_mapgen(smem, c, B);
     for (int t = 0; t < B; t++) stage_tables(c, p, sh, t, B);
+    memcpy(sh.sel8, p.sel8, 2048);
     for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<RNG, TMAX, TABLED>(c, p, sh, t, (int)list[i0 + t].x, list[i0 + t].y);
   }
   free(smem);
