@@ -238,7 +238,8 @@ PG_HDN TrafficIO advance_cars(const DevCfg& c, const DevPtrs& p, const MapView m
     } else {  // _spawn_new_car (:970-1002)
       if (use_occ) occ_sub(c, p, env, ox, oy);
       int sx = 0, sy = 0;
-      int ns = p.spawner_count[env];
+      int ns = p.spawner_count ? p.spawner_count[env] : 0;  // (no list on a handle created without traffic: cars injected by set_state)
+      if (!p.spawner_count) e.err |= 16;
       if (ns > 0) {
         unsigned v = p.spawners[(size_t)env * c.spawner_cap + rng.car_index(r, CW_SPAWNER, ns)];
         sx = (int)(v & 255); sy = (int)(v >> 8);

@@ -302,7 +302,7 @@ PG_HD void tk_intent(const DevCfg& c, const DevPtrs& p, const TkShared& sh, int 
     if (!found) {  // leaves the map; its replacement (_spawn_new_car, :970-1002) is appended to the list
       if (!have1) philox_car_block(t.key, e.elapsed, e.episode, r, 1, w1);
       int sx = 0, sy = 0;
-      const int ns = p.spawner_count[env];
+      const int ns = p.spawner_count ? p.spawner_count[env] : 0;  // (no list on a handle created without traffic)
       if (ns > 0) {
         const unsigned v = p.spawners[(size_t)env * c.spawner_cap + (ns > 1 ? (int)pg_umulhi(w1[CW_SPAWNER & 3], (uint32_t)ns) : 0)];
         sx = (int)(v & 255u); sy = (int)(v >> 8);
@@ -560,6 +560,10 @@ PG_HD void tk_reset_traffic(const DevCfg& c, const DevPtrs& p, const TkShared& s
   TEnv& t = sh.env[g];
   EnvRegs& e = t.e;
   const MapView m = tk_map(c, sh, g);
+  if (!(c.traffic_density > 0)) {  // a car-free configuration on this tick (sliding window / next_subgoal_direction): nothing to prepare
+    if (parts & 1) { t.num_positions = 0; t.new_cars = 0; e.misc = misc_pack(0, 0, 0, 0); e.next_car_id = 0; }
+    return;
+  }
   if (parts & 2) tk_spawner_list(c, p, sh, m, env);
   if (parts & 4) philox_car_block(t.key, e.elapsed, e.episode, -1, 0, t.perm_keys);
   if (parts & 1) {

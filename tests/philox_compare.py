@@ -76,6 +76,11 @@ CONFIGS = {
     "wide_16x16": (dict(random_map_width=16, random_map_height=16, random_map_percentage_of_connections=0.6, traffic_density=0.01,
                         random_map_obstacle_probability=0.3, use_next_subgoal_direction=True), 4, 12),
     "tiny_1x1": (dict(random_map_width=1, random_map_height=1, traffic_density=0.5, ignore_traffic_collisions=True), 130, 30),
+    # car-free configurations outside the lean tick's promise (they run the traffic tick's parallel observation phases)
+    "carfree_sliding_nsd": (dict(use_sliding_observation_window=True, sliding_observation_window_size=5, use_next_subgoal_direction=True,
+                                 random_map_obstacle_probability=0.5), 200, 40),
+    "carfree_nsd_penalties": (dict(use_next_subgoal_direction=True, standing_still_penalty=1, already_visited_position_penalty=2,
+                                   random_map_width=3, random_map_height=5, max_episode_steps=9), 200, 40),
 }
 
 # long-lived episodes (the agent mostly idles) for the traffic dynamics: blocking chains, patience, push-through,
