@@ -53,7 +53,7 @@ WORKLOADS = {
     "train-py": (TRAIN_PY, 262144, 1024, dict(max_episode_steps=100, flat=True)),
     # gymnasium's vector contract: terminal observations of auto-reset envs are written too
     "default-2M+final_observation": (dict(), 2 * 1024 * 1024, 16384, dict(final_observation=True)),
-    # a car-free configuration outside the lean tick's promise: sliding window + next_subgoal_direction
+    # a car-free configuration outside the lean tick's promise (general tick): sliding window + next_subgoal_direction
     "sliding-nsd-1M": (dict(use_sliding_observation_window=True, sliding_observation_window_size=5, use_next_subgoal_direction=True), 1024 * 1024, 8192, {}),
     # small smoke-sized run
     "default-64k": (dict(), 65536, 8192, {}),

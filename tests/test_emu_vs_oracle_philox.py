@@ -49,3 +49,19 @@ def test_traffic_tick_counter_saturation_fallback(name):
     pc.compare(env, ora, ticks, state_every=10, stay=stay)
     env.close()
     ora.close()
+
+
+@pytest.mark.parametrize("name", ["carfree_sliding_nsd", "carfree_nsd_penalties"])
+def test_carfree_configurations_on_the_traffic_tick(name, monkeypatch):
+    """Car-free sliding-window / next_subgoal_direction configurations normally run the general tick; the traffic tick's
+    parallel observation phases must give the same bits when forced onto them."""
+    monkeypatch.setenv("PGTG_TRAFFIC_KERNEL_CARFREE", "1")
+    kw, n, ticks = pc.CONFIGS[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = NativeAdapter("emu", num_envs=n, seed=4242, final_observation=True, **kw)
+        ora = OracleVectorEnv(num_envs=n, seed=4242, final_observation=True, **kw)
+    assert "tick=traffic" in env.raw.kernel_info()
+    assert pc.compare(env, ora, ticks, state_every=10) > 0
+    env.close()
+    ora.close()
