@@ -283,20 +283,6 @@ static int rng_car_choice_cdf(rctx* r, int slot, int pos, const double* cdf, int
   return i;
 }
 
-/* Index draws of the edge-removal and border-connection phases. Philox mode (product specification, pgtg_logic.cuh
- * map_index): a 32-bit word serves successive draws -- draw = hi32(word * n), the low half of the product is the next
- * draw's word -- while the product of the served ranges, the new one included, stays <= 2^16. */
-typedef struct { uint32_t rem, used; } map_draw;
-static int map_index(rctx* r, map_draw* md, int n) {
-  if (r->b->cfg.rng_mode != PGTG_RNG_PHILOX) return rng_index(r, PGTG_STREAM_MAP, n);
-  if (n <= 1) return 0;
-  uint32_t w = md->rem;
-  if (md->used == 0 || md->used * (uint32_t)n > 65536u) { w = philox_word(r, PGTG_STREAM_MAP); md->used = 1; }
-  uint64_t prod = (uint64_t)w * (uint32_t)n;
-  md->rem = (uint32_t)prod; md->used *= (uint32_t)n;
-  return (int)(prod >> 32);
-}
-
 /* Generator.choice(n, size=k, replace=False): k distinct indices in returned order.
  * Philox mode: the keyed Feistel permutation of the car-stream specification above. */
 static void rng_distinct(rctx* r, int stream, int n, int k, int* out) {
@@ -461,25 +447,43 @@ static void generate_map(rctx* r, ora_env* e) {
   int keep = c->edges_to_keep;
   int path[GMAXN];
   int plen = g_bfs(&g, S, E, path);
-  map_draw md = {0, 0};
+  static __thread unsigned char tried[4 * PGTG_MAX_TILES];
+  int cbits = 1, per_word = 32, cleft = 0, n_und = 0;
+  uint32_t cw = 0;
   if (c->rng_mode == PGTG_RNG_PHILOX) {
-    /* Philox specification: the draw is over the grid edges not tried yet (what the reference's draw over removable_edges
-     * amounts to: both directions of an edge are listed and leave the list together), enumerated in the order of the
-     * product's connectivity bits: horizontal edges row by row, then vertical edges by tile index y * W + x. */
+    /* Philox specification (pgtg_logic.cuh generate_map): the pick is over the grid edges not tried yet (what the
+     * reference's draw over removable_edges amounts to: both directions of an edge are listed and leave the list
+     * together), numbered in the order of the product's connectivity bits -- horizontal edges row by row, then vertical
+     * edges by tile index y * W + x -- and made by rejection: the map stream's words are cut into chunks of
+     * ceil(log2(n_edges)) bits, lowest first, floor(32 / bits) per word; a chunk naming no edge or a tried one is skipped. */
     n_rem = 0;
     for (int y = 0; y < H; y++) for (int x = 0; x + 1 < W; x++) { rem[n_rem][0] = x * H + y; rem[n_rem][1] = (x + 1) * H + y; n_rem++; }
     for (int y = 0; y + 1 < H; y++) for (int x = 0; x < W; x++) { rem[n_rem][0] = x * H + y; rem[n_rem][1] = x * H + y + 1; n_rem++; }
+    n_und = n_rem;
+    memset(tried, 0, (size_t)n_und);
+    while (cbits < 32 && (1 << cbits) < n_und) cbits++;
+    per_word = 32 / cbits;
   }
   while (g_edge_count(&g) - 4 > keep && n_rem > 0) { /* :245 */
-    int idx = map_index(r, &md, n_rem); /* :249 */
-    int a = rem[idx][0], b = rem[idx][1];
-    /* removable_edges.remove(chosen); .remove(reverse) (:252-253) */
-    int w = 0;
-    for (int i = 0; i < n_rem; i++) {
-      if ((rem[i][0] == a && rem[i][1] == b) || (rem[i][0] == b && rem[i][1] == a)) continue;
-      rem[w][0] = rem[i][0]; rem[w][1] = rem[i][1]; w++;
+    int a, b;
+    if (c->rng_mode == PGTG_RNG_PHILOX) {
+      if (cleft == 0) { cw = philox_word(r, PGTG_STREAM_MAP); cleft = per_word; }
+      int pos = (int)(cw & ((1u << cbits) - 1u));
+      cw >>= cbits; cleft--;
+      if (pos >= n_und || tried[pos]) continue;
+      tried[pos] = 1; n_rem--;
+      a = rem[pos][0]; b = rem[pos][1];
+    } else {
+      int idx = rng_index(r, PGTG_STREAM_MAP, n_rem); /* :249 */
+      a = rem[idx][0]; b = rem[idx][1];
+      /* removable_edges.remove(chosen); .remove(reverse) (:252-253) */
+      int w = 0;
+      for (int i = 0; i < n_rem; i++) {
+        if ((rem[i][0] == a && rem[i][1] == b) || (rem[i][0] == b && rem[i][1] == a)) continue;
+        rem[w][0] = rem[i][0]; rem[w][1] = rem[i][1]; w++;
+      }
+      n_rem = w;
     }
-    n_rem = w;
     g_del_edge(&g, a, b); g_del_edge(&g, b, a);
     int ina = 0, inb = 0;
     for (int i = 0; i < plen; i++) { if (path[i] == a) ina = 1; if (path[i] == b) inb = 1; }
@@ -523,8 +527,25 @@ static void generate_map(rctx* r, ora_env* e) {
       nb--; break;
     }
   }
+  if (c->rng_mode == PGTG_RNG_PHILOX) {
+    /* Philox specification (pgtg_logic.cuh choose_border_slots): the picks are a uniformly random subset of the slots,
+     * drawn by the same rejection scheme as the edges: a fresh word, chunks of ceil(log2 n) bits, a chunk >= n or naming a
+     * chosen slot is skipped. */
+    int left = c->border_connections < nb ? c->border_connections : nb, bbits = 1, bleft = 0;
+    unsigned char chosen[4 * 64] = {0};
+    uint32_t bw = 0;
+    while (bbits < 31 && (1 << bbits) < nb) bbits++;
+    while (left > 0) {
+      if (bleft == 0) { bw = philox_word(r, PGTG_STREAM_MAP); bleft = 32 / bbits; }
+      int v = (int)(bw & ((1u << bbits) - 1u)); /* :367 */
+      bw >>= bbits; bleft--;
+      if (v >= nb || chosen[v]) continue;
+      chosen[v] = 1; left--;
+      e->exits[bc[v][0] * W + bc[v][1]] |= (unsigned char)(1 << bc[v][2]);
+    }
+  } else
   for (int k = 0; k < c->border_connections; k++) {
-    int idx = map_index(r, &md, nb); /* :367 */
+    int idx = rng_index(r, PGTG_STREAM_MAP, nb); /* :367 */
     e->exits[bc[idx][0] * W + bc[idx][1]] |= (unsigned char)(1 << bc[idx][2]);
     for (int j = idx; j + 1 < nb; j++) memcpy(bc[j], bc[j + 1], sizeof bc[0]);
     nb--;

@@ -361,12 +361,6 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
             if ((int)((l >> (6 + 7 * i)) & 31) == r) v |= (uint8_t)(1u << ((l >> (11 + 7 * i)) & 3));
         }
       }
-    std::vector<uint8_t> s8(2048, 0);  // position of the k-th set bit of a byte
-    for (int b = 0; b < 256; b++) { int k = 0; for (int bit = 0; bit < 8; bit++) if ((b >> bit) & 1) s8[b * 8 + k++] = (uint8_t)bit; }
-    uint8_t* s8d = dev_alloc<uint8_t>(e, s8.size());
-    if (!s8d) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }
-    bk_h2d(s8d, s8.data(), s8.size(), nullptr);
-    p.sel8 = s8d;
     uint8_t* sd = dev_alloc<uint8_t>(e, sl.size());
     uint8_t* tdv = dev_alloc<uint8_t>(e, tl.size());
     if (!sd || !tdv) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }

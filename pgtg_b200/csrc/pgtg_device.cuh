@@ -27,6 +27,7 @@
 #define pg_umulhi(a, b) __umulhi((a), (b))
 #define pg_ffs(v) __ffs((int)(v))
 #define pg_popc(v) __popc((unsigned)(v))
+#define pg_clz(v) __clz((int)(v))
 #define pg_popcll(v) __popcll((unsigned long long)(v))
 #define pg_ldg(p) __ldg(p)
 #define pg_dmul(a, b) __dmul_rn((a), (b))
@@ -53,6 +54,7 @@ __device__ __forceinline__ void pg_store_streaming32(void* ptr, uint2 a, uint2 b
 static inline uint32_t pg_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 #define pg_ffs(v) __builtin_ffs((int)(v))
 #define pg_popc(v) __builtin_popcount((unsigned)(v))
+#define pg_clz(v) ((v) ? __builtin_clz((unsigned)(v)) : 32)
 #define pg_popcll(v) __builtin_popcountll((unsigned long long)(v))
 #define pg_ldg(p) (*(p))
 // the emulation build uses -ffp-contract=off, so plain operators are correctly rounded, unfused
@@ -238,7 +240,6 @@ struct DevPtrs {
   const uint8_t* dirlut;        // (2R+1)^2
   const uint32_t* conn_table;   // [2^conn_bits / 32] or null
   const Lut* lut;               // the LUTs with their derived fields, built once per handle
-  const uint8_t* sel8;          // [256][8] position of the k-th set bit of a byte
   const uint8_t* target_lut;    // [16][81][20] per (tile type, local square, route): bit d = the square carries a lane of that route with
                                 // direction d, bit 4 + d = it carries 'car_lane all d' (a move INTO it from another tile, :915-932)
   const uint8_t* step_lut;      // [16][81][20] per (tile type, local square, route): bit d = the neighbour square in direction d lies in
@@ -579,7 +580,6 @@ struct MapView {
   bool graph_valid;
   uint32_t ng_key = 0xFFFFFFFFu;  // nearest_goal's answer computed beforehand (when ng_pre)
   bool ng_pre = false;
-  const uint8_t* sel8 = nullptr;  // [256][8] position of the k-th set bit of a byte (shared-memory copy; map generation)
   PG_MEMBER bool inside(int x, int y) const { return !(x < 0 || y < 0 || x >= c.WS || y >= c.HS); }  // map.py:44-47
   PG_MEMBER int start_tile() const { return plan_sy(plan) * c.W + plan_sx(plan); }
   PG_MEMBER int goal_tile() const { return plan_gy(plan) * c.W + plan_gx(plan); }

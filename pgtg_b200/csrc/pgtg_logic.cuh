@@ -577,14 +577,6 @@ PG_HD int select32(uint32_t v, int n) {
   return pos;
 }
 
-// the same through a 2 KB table (position of the k-th set bit of every byte): a dozen instructions and one shared-memory byte
-PG_HD int select32_lut(const uint8_t* sel8, uint32_t v, int n) {
-  const int c0 = pg_popc(v & 0xFFu), c1 = c0 + pg_popc(v & 0xFF00u), c2 = c1 + pg_popc(v & 0xFF0000u);
-  const int k = (n >= c0) + (n >= c1) + (n >= c2);
-  const int base = k == 0 ? 0 : k == 1 ? c0 : k == 2 ? c1 : c2;
-  return 8 * k + sel8[((v >> (8 * k)) & 255u) * 8 + (n - base)];
-}
-
 // Does removing edge (a, b) keep start and goal connected? E bit i: edge i<->i+1, S bit i: edge
 // i<->i+W (the edge is already cleared). Flood from a: reaching b means nothing changed (early
 // exit, typically after going round one grid face); otherwise the flood ends on a's whole
@@ -687,20 +679,73 @@ PG_HD void graph_to_boards(const DevCfg& c, uint32_t graph, uint32_t& E, uint32_
   E = e; S = graph >> c.conn_ne;
 }
 
-// Philox specification of the index draws of the edge-removal and border-connection phases: a 32-bit word serves successive
-// draws -- draw = hi32(word * n), the low half of the product becomes the word of the next draw -- while the product of the
-// ranges it has served, the new one included, stays <= 2^16 (so every draw still sees >= 16 fresh bits beyond its own range:
-// bias below 2^-16). Tape / numpy modes draw exactly as the reference does.
-struct MapDraw { uint32_t rem, used; };
+// Philox specification of the edge removal (generate_map_graph, map_generator.py:245-264). Each trip picks uniformly among
+// the grid edges not tried yet -- exactly what the reference's draw over removable_edges amounts to (both directions of an
+// edge are listed and leave the list together, :249-253). The edges are numbered in the order of the connectivity-table
+// bits (horizontal edges row by row, then vertical edges by tile) and the pick is by REJECTION: the map stream's 32-bit
+// words are cut into chunks of b = ceil(log2(n_edges)) bits, lowest bits first, floor(32 / b) chunks per word, the rest
+// of the word dropped; a chunk that names no edge, or an edge already tried, is skipped. Exactly uniform over the untried
+// edges, and one mask test per chunk instead of a k-th-set-bit select per trip (map generation is issue-bound).
+PG_HOSTDEV int edge_chunk_bits(int n_edges) { int b = 1; while (b < 31 && (1 << b) < n_edges) b++; return b; }
+
+// the loop for grids of <= 32 edges with the connectivity table: the edge set is the table index itself
+PG_HD void edge_trial(const DevCfg& c, const DevPtrs& p, uint32_t pbit, uint32_t& graph, uint32_t& untried, int& go) {
+  if (go > 0 && (untried & pbit)) {  // (a chunk >= n_edges names a bit `untried` never had)
+    untried ^= pbit;
+    // "start and goal still connected?" is a pure function of the edge set: one lookup in the 2^E-bit table built once
+    // per handle (2 MB for the 4x4 grid, L2-resident)
+    const uint32_t g2 = graph & ~pbit;
+    const bool keep = (pg_ldg(&p.conn_table[g2 >> 5]) >> (g2 & 31)) & 1u;
+    graph = keep ? g2 : graph;
+    go = untried != 0u ? 2 * pg_popc(graph) - c.edges_to_keep : 0;  // :245 (both directions of an edge are counted): > 0 = carry on
+  }
+}
 template <int RNG>
-PG_HD int map_index(Rng<RNG>& rng, MapDraw& md, int n) {
-  if (RNG != PGTG_RNG_PHILOX) return rng.index(PGTG_STREAM_MAP, n);
-  if (n <= 1) return 0;
-  uint32_t w = md.rem;
-  if (md.used == 0 || md.used * (uint32_t)n > 65536u) { w = rng.word(PGTG_STREAM_MAP); md.used = 1; }
-  const uint64_t prod = (uint64_t)w * (uint32_t)n;
-  md.rem = (uint32_t)prod; md.used *= (uint32_t)n;
-  return (int)(prod >> 32);
+PG_HD uint32_t remove_edges_tabled(const DevCfg& c, const DevPtrs& p, Rng<RNG>& rng) {
+  const int n_und = c.H * (c.W - 1) + c.W * (c.H - 1);
+  uint32_t graph = (c.conn_bits >= 32 ? 0u : (1u << c.conn_bits)) - 1u;
+  uint32_t untried = n_und >= 32 ? 0xFFFFFFFFu : (1u << n_und) - 1u;
+  int go = untried != 0u ? 2 * n_und - c.edges_to_keep : 0;
+  const int cbits = edge_chunk_bits(n_und);
+  if (cbits == 5) {  // 17..32 edges (the 4x4 grid has 24): the six chunks of a word unrolled
+    while (go > 0) {
+      const uint32_t cw = rng.word(PGTG_STREAM_MAP);
+#pragma unroll
+      for (int k = 0; k < 6; k++) edge_trial(c, p, 1u << ((cw >> (5 * k)) & 31u), graph, untried, go);  // :249
+    }
+  } else {
+    const int per_word = 32 / cbits;
+    const uint32_t cmask = (1u << cbits) - 1u;
+    while (go > 0) {
+      uint32_t cw = rng.word(PGTG_STREAM_MAP);
+      for (int k = 0; k < per_word && go > 0; k++) { edge_trial(c, p, 1u << (cw & cmask), graph, untried, go); cw >>= cbits; }
+    }
+  }
+  return graph;
+}
+
+// Philox specification of add_connections_to_borders (map_generator.py:337-371): `border_connections` distinct slots out of
+// n (host-table order, default start / goal slots removed), which is a uniformly random subset -- drawn by the same
+// rejection scheme: a fresh word, chunks of ceil(log2 n) bits, a chunk >= n or naming a chosen slot is skipped. Returns
+// the chosen slots as a bit set (the order of the picks does not matter: each sets one exit bit).
+template <int RNG, typename MASK = uint64_t>
+PG_HD MASK choose_border_slots(const DevCfg& c, Rng<RNG>& rng) {
+  const int n = c.n_border_slots;
+  int left = c.border_connections < n ? c.border_connections : n;
+  MASK chosen = 0;
+  if (left <= 0) return chosen;
+  const int cbits = edge_chunk_bits(n), per_word = 32 / cbits;
+  const uint32_t cmask = (1u << cbits) - 1u;
+  const MASK valid = n >= (int)(8 * sizeof(MASK)) ? ~(MASK)0 : (((MASK)1 << n) - 1);
+  while (left > 0) {
+    uint32_t cw = rng.word(PGTG_STREAM_MAP);
+    for (int k = 0; k < per_word && left > 0; k++) {
+      const MASK bit = (MASK)1 << (cw & cmask);  // :367 (callers with a 32-bit mask have <= 32 slots, so cbits <= 5)
+      cw >>= cbits;
+      if (bit & valid & ~chosen) { chosen |= bit; left--; }
+    }
+  }
+  return chosen;
 }
 
 // TABLED = compile-time promise that both per-handle tables exist (fixed start/goal, <= 16 tiles,
@@ -722,31 +767,33 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
   // with the connectivity table the graph is kept as the table index itself (one bit per grid edge)
   const bool tabled = TABLED || (TMAX <= 32 && c.conn_bits != 0);
   uint32_t graph = tabled ? ((c.conn_bits >= 32 ? 0u : (1u << c.conn_bits)) - 1u) : 0u;
-  MapDraw md = {0u, 0u};
   if (RNG == PGTG_RNG_PHILOX) {
-    // Philox specification: each trip picks uniformly among the grid edges not tried yet -- exactly what the reference's
-    // draw over removable_edges amounts to (both directions of an edge are listed and leave the list together, :249-253) --
-    // enumerated in the order of the connectivity-table bits: horizontal edges row by row, then vertical edges by tile.
+    // Philox specification: see remove_edges_tabled above (rejection over fixed-width chunks of the stream's words)
     constexpr int UW = (2 * TMAX + 31) / 32;
+    if (UW == 1 && tabled) graph = remove_edges_tabled<RNG>(c, p, rng);
+    else {
     uint32_t untried[UW];
     const int n_he = c.H * (W - 1), n_und = n_he + W * (c.H - 1);
     int n_untried = n_und, cur = 2 * n_und;
 #pragma unroll
     for (int i = 0; i < UW; i++) untried[i] = (i * 32 + 32 <= n_und) ? 0xFFFFFFFFu : (i * 32 < n_und ? ((1u << (n_und & 31)) - 1u) : 0u);
+    const int cbits = edge_chunk_bits(n_und), per_word = 32 / cbits;
+    const uint32_t cmask = (1u << cbits) - 1u;
+    uint32_t cw = 0;
+    int cleft = 0;
     while (cur > c.edges_to_keep && n_untried > 0) {  // :245
-      int idx = map_index<RNG>(rng, md, n_untried);  // :249
-      int pos;
-      if (UW == 1) { pos = m.sel8 ? select32_lut(m.sel8, untried[0], idx) : select32(untried[0], idx); untried[0] &= ~(1u << pos); }
-      else {
-        int wi = 0;
-        for (;; wi++) { int pc = pg_popc(untried[wi]); if (idx < pc) break; idx -= pc; }
-        const int bpos = select32(untried[wi], idx);
-        untried[wi] &= ~(1u << bpos);
-        pos = wi * 32 + bpos;
-      }
+      if (cleft == 0) { cw = rng.word(PGTG_STREAM_MAP); cleft = per_word; }
+      const int pos = (int)(cw & cmask);  // :249
+      cw >>= cbits; cleft--;
+      const uint32_t pbit = 1u << (pos & 31);
+      bool hit = false;
+#pragma unroll
+      for (int i = 0; i < UW; i++)
+        if (i == (pos >> 5) && (untried[i] & pbit)) { untried[i] ^= pbit; hit = true; }
+      if (!hit) continue;
       n_untried--;
       if (tabled) {
-        const uint32_t g2 = graph & ~(1u << pos);
+        const uint32_t g2 = graph & ~pbit;
         const bool keep = (pg_ldg(&p.conn_table[g2 >> 5]) >> (g2 & 31)) & 1u;
         graph = keep ? g2 : graph;
         cur -= keep ? 2 : 0;
@@ -758,6 +805,7 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
       if (horiz) bclr(E, lo); else bclr(S, lo);
       if (still_connected<TMAX>(c, p, E, S, a, b, st, gt)) cur -= 2;
       else { if (horiz) bset(E, lo); else bset(S, lo); }
+    }
     }
   } else {
   constexpr int AW = (4 * TMAX + 31) / 32;
@@ -821,18 +869,24 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
   m.tiles[st] |= (uint16_t)(1 << sd);
   m.tiles[gt] |= (uint16_t)(1 << gd);
   // add_connections_to_borders (:337-371): slots in host-table order, default start/goal removed
-  uint64_t slots = c.n_border_slots >= 64 ? ~0ull : ((1ull << c.n_border_slots) - 1ull);
-  int n_slots = c.n_border_slots;
-  for (int k = 0; k < c.border_connections && n_slots > 0; k++) {
-    int idx = map_index<RNG>(rng, md, n_slots);  // :367
-    uint32_t lo32 = (uint32_t)slots, hi32 = (uint32_t)(slots >> 32);
-    int pc0 = pg_popc(lo32);
-    bool hi = idx >= pc0;
-    int i = (m.sel8 ? select32_lut(m.sel8, hi ? hi32 : lo32, hi ? idx - pc0 : idx) : select32(hi ? hi32 : lo32, hi ? idx - pc0 : idx)) + (hi ? 32 : 0);
-    slots &= ~(1ull << i);
-    n_slots--;
-    unsigned v = m.border_slots[i];
-    m.tiles[v & 255] |= (uint16_t)(1 << (v >> 8));
+  if (RNG == PGTG_RNG_PHILOX) {
+    const uint64_t chosen = choose_border_slots<RNG, uint64_t>(c, rng);
+    for (int i = 0; i < c.n_border_slots; i++)
+      if ((chosen >> i) & 1ull) { const unsigned v = m.border_slots[i]; m.tiles[v & 255] |= (uint16_t)(1 << (v >> 8)); }
+  } else {
+    uint64_t slots = c.n_border_slots >= 64 ? ~0ull : ((1ull << c.n_border_slots) - 1ull);
+    int n_slots = c.n_border_slots;
+    for (int k = 0; k < c.border_connections && n_slots > 0; k++) {
+      int idx = rng.index(PGTG_STREAM_MAP, n_slots);  // :367
+      uint32_t lo32 = (uint32_t)slots, hi32 = (uint32_t)(slots >> 32);
+      int pc0 = pg_popc(lo32);
+      bool hi = idx >= pc0;
+      int i = select32(hi ? hi32 : lo32, hi ? idx - pc0 : idx) + (hi ? 32 : 0);
+      slots &= ~(1ull << i);
+      n_slots--;
+      unsigned v = m.border_slots[i];
+      m.tiles[v & 255] |= (uint16_t)(1 << (v >> 8));
+    }
   }
   // add_obstacles_to_map (:374-472), row-major, one random() per tile whatever the outcome
   if (c.obstacle_probability > 0) {
@@ -994,6 +1048,50 @@ PG_HD void build_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
   if (lab == 3) e.plan |= (unsigned)rng.index(PGTG_STREAM_MAP, 3) << 29;
   else e.err |= 64;
   m.plan = e.plan;
+}
+
+// build_map for the configuration the headline runs (Philox, both tables, fixed start / goal, 8 or 16 tiles, no obstacles): the map is a pure function of the surviving edge set and one start-square draw, so the
+// descriptors are assembled in registers, two per word, from the edge boards and the path-table entry -- no per-tile
+// loops over shared memory, no staged tables. Same bits as build_map (tests/test_gpu_properties.py forces both).
+PG_HOSTDEV bool map_in_registers(const DevCfg& c) {
+  return c.conn_bits != 0 && c.path_tab && (c.T == 8 || c.T == 16) && !(c.obstacle_probability > 0) && c.start_mode == 0 && c.goal_mode == 0 && !c.fixed_map;
+}
+template <int RNG>
+PG_HD void build_map_in_registers(const DevCfg& c, const DevPtrs& p, EnvRegs& e, Rng<RNG>& rng, uint32_t (&out)[8]) {
+  const uint32_t graph = remove_edges_tabled<RNG>(c, p, rng);
+  const uint64_t v = pg_ldg(&p.path_table[graph]);  // 3-bit subgoal direction per tile | ns << 48 | unreachable << 63
+  uint32_t E, S;
+  graph_to_boards(c, graph, E, S);
+  const uint32_t Sn = S << c.W, Ew = E << 1;  // map_graph_to_tile_map_object (:269-334): exits N E S W
+  const int st = c.start_y * c.W + c.start_x, gt = c.goal_y * c.W + c.goal_x;
+  uint64_t border = (uint64_t)(1u << c.start_dir) << (4 * st) | (uint64_t)(1u << c.goal_dir) << (4 * gt);
+  for (uint32_t chosen = choose_border_slots<RNG, uint32_t>(c, rng); chosen != 0u; chosen &= chosen - 1u) {  // <= 32 slots with <= 16 tiles
+    const unsigned s = pg_ldg(&p.border_slots[pg_ffs(chosen) - 1]);  // tile | direction << 8
+    border |= (uint64_t)(1u << (s >> 8)) << (4 * (s & 255u));
+  }
+  const uint32_t sg_lo = (uint32_t)v, sg_hi = (uint32_t)(v >> 24);  // tiles 0-7 in bits 0-23, tiles 8-15 in bits 24-47
+  const uint32_t bd_lo = (uint32_t)border, bd_hi = (uint32_t)(border >> 32);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int t = 2 * k + h;
+      const uint32_t ex = ((Sn >> t) & 1u) | ((E >> t) & 1u) << 1 | ((S >> t) & 1u) << 2 | ((Ew >> t) & 1u) << 3 | (((t < 8 ? bd_lo : bd_hi) >> (4 * (t & 7))) & 15u);
+      const uint32_t sg = ((t < 8 ? sg_lo : sg_hi) >> (3 * (t & 7))) & 7u;
+      w |= (ex | sg << 11) << (16 * h);
+    }
+    out[k] = w;
+  }
+  if (v >> 63) e.err |= 8;
+  e.plan = plan_pack(c.start_x, c.start_y, c.start_dir, c.goal_x, c.goal_y, c.goal_dir, 0) | (unsigned)((v >> 48) & 0x1FFu) << 20;
+  // self.position = map_rng.choice(self.map.starters) (:635): drawn iff the start line is still labelled "start"
+  // (MapView::line_labels: a subgoal label on the same line comes first)
+  const uint32_t ex_st = ((Sn >> st) & 1u) | ((E >> st) & 1u) << 1 | ((S >> st) & 1u) << 2 | ((Ew >> st) & 1u) << 3 | (1u << c.start_dir);
+  const int sg_st = (int)((v >> (3 * st)) & 7u);
+  const bool start_labelled = !(sg_st && st != gt && sg_st - 1 == c.start_dir && ((ex_st >> (sg_st - 1)) & 1u));
+  if (start_labelled) e.plan |= (unsigned)rng.index(PGTG_STREAM_MAP, 3) << 29;
+  else e.err |= 64;
 }
 
 // the rest of PGTGEnv.reset (environment.py:635-656) on a finished map

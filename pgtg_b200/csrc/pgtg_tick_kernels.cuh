@@ -220,15 +220,21 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
 // (PGTG_MAPGEN_CTAS_PER_SM); the default is one request per thread. TABLED: see generate_map.
 template <int RNG, int TMAX, bool TABLED = false>
 __global__ void __launch_bounds__(128, TABLED ? PGTG_MAPGEN_TABLED_MIN_BLOCKS : PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity,
-                                                                                const __grid_constant__ SharedLayout layout) {
+                                                                                const __grid_constant__ SharedLayout layout, bool in_registers) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t count = p.regen_count[parity];
   if (blockIdx.x * blockDim.x >= count) return;
+  const uint2* list = p.regen_list + (size_t)parity * 2 * c.N;
+  if (RNG == PGTG_RNG_PHILOX && TABLED && in_registers) {  // the headline configuration: no tables, no shared memory, no barrier
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+      const uint2 r = list[i];
+      phase_pregenerate_in_registers<RNG>(c, p, (int)r.x, r.y);
+    }
+    return;
+  }
   BlockShared sh = carve_layout(smem, layout);
   stage_tables(c, p, sh, threadIdx.x, blockDim.x);
-  for (int i = threadIdx.x; i < 2048 / 16; i += blockDim.x) ((uint4*)sh.sel8)[i] = __ldg((const uint4*)p.sel8 + i);  // k-th-set-bit table
   __syncthreads();
-  const uint2* list = p.regen_list + (size_t)parity * 2 * c.N;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     uint2 r = list[i];
     phase_pregenerate<RNG, TMAX, TABLED>(c, p, sh, threadIdx.x, (int)r.x, r.y);
@@ -271,14 +277,20 @@ static int launch_mapgen(pgtg_env* e, cudaStream_t st) {
   const int B = 128;
   size_t smem = pgtg::mapgen_shared_bytes(e->dc, B);
   auto kern = pgtg::pgtg_mapgen_kernel<RNG, TMAX, TABLED>;
+  const bool in_registers = TABLED && pgtg::map_in_registers(e->dc) && !getenv("PGTG_NO_MAP_IN_REGISTERS");
+  if (in_registers) smem = 0;
   static bool carve_set = false;
-  if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve_set = true; }
+  if (!carve_set) {
+    const char* cv = getenv("PGTG_MAPGEN_CARVEOUT");  // experiment: L1-sized carveout for the connectivity-table lookups
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : cudaSharedmemCarveoutMaxShared);
+    carve_set = true;
+  }
   if (smem > 48 * 1024) { int rc = lk(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); if (rc) return rc; }
   int full = (2 * e->dc.N + B - 1) / B;
   int grid = e->mapgen_grid > 0 && e->mapgen_grid < full ? e->mapgen_grid : full;
   unsigned char* const origin = (unsigned char*)4096;
   const pgtg::SharedLayout layout = pgtg::layout_of(pgtg::carve_mapgen(origin, e->dc, B), origin);
-  kern<<<grid, B, smem, st>>>(e->dc, e->dp, e->dp.parity, layout);
+  kern<<<grid, B, smem, st>>>(e->dc, e->dp, e->dp.parity, layout, in_registers);
   return lk(cudaGetLastError());
 }
 

@@ -124,11 +124,15 @@ static void run_mapgen(pgtg_env* h) {
   unsigned char* smem = (unsigned char*)bk_alloc(bytes);
   uint32_t count = p.regen_count[p.parity];
   const uint2* list = p.regen_list + (size_t)p.parity * 2 * c.N;
+  if (RNG == PGTG_RNG_PHILOX && TABLED && map_in_registers(c) && !getenv("PGTG_NO_MAP_IN_REGISTERS")) {  // as the kernel dispatches
+    for (uint32_t i = 0; i < count; i++) phase_pregenerate_in_registers<RNG>(c, p, (int)list[i].x, list[i].y);
+    free(smem);
+    return;
+  }
   for (uint32_t i0 = 0; i0 < count; i0 += B) {
     memset(smem, 0xA5, bytes);
     BlockShared sh = carve_mapgen(smem, c, B);
     for (int t = 0; t < B; t++) stage_tables(c, p, sh, t, B);
-    memcpy(sh.sel8, p.sel8, 2048);
     for (int t = 0; t < B && i0 + t < count; t++) phase_pregenerate<RNG, TMAX, TABLED>(c, p, sh, t, (int)list[i0 + t].x, list[i0 + t].y);
   }
   free(smem);

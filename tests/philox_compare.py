@@ -76,6 +76,12 @@ CONFIGS = {
     "wide_16x16": (dict(random_map_width=16, random_map_height=16, random_map_percentage_of_connections=0.6, traffic_density=0.01,
                         random_map_obstacle_probability=0.3, use_next_subgoal_direction=True), 4, 12),
     "tiny_1x1": (dict(random_map_width=1, random_map_height=1, traffic_density=0.5, ignore_traffic_collisions=True), 130, 30),
+    # 8-tile grids: the emulation build has the connectivity / path tables up to 13 edges, so these run the tabled edge
+    # removal and the register-resident map assembly the headline configuration uses on the device (map_in_registers)
+    "tabled_2x4_registers": (dict(random_map_width=2, random_map_height=4), 300, 40),
+    "tabled_4x2_registers_sparse": (dict(random_map_width=4, random_map_height=2, random_map_percentage_of_connections=0.2,
+                                         max_episode_steps=12), 300, 40),
+    "tabled_3x3_shared": (dict(random_map_width=3, random_map_height=3, random_map_obstacle_probability=0.3), 200, 40),
     # car-free configurations outside the lean tick's promise (they run the traffic tick's parallel observation phases)
     "carfree_sliding_nsd": (dict(use_sliding_observation_window=True, sliding_observation_window_size=5, use_next_subgoal_direction=True,
                                  random_map_obstacle_probability=0.5), 200, 40),

@@ -1,5 +1,5 @@
 """Philox mode is distribution-exact, not draw-exact: its draw specification (per-car blocks, Feistel placement, tile-major index
-spaces, edge draws over untried grid edges with shared words -- DESIGN.md section 5) must leave every distribution of the
+spaces, edge draws over untried grid edges by rejection -- DESIGN.md section 5) must leave every distribution of the
 reference untouched. Checked here on the oracle by comparing Philox-mode statistics with the numpy-exact mode (which is the
 reference draw for draw) over many independent envs: tile-type frequencies per tile, obstacle frequencies, initial car
 counts and car-position occupancy, spawner choice after many ticks."""
@@ -50,11 +50,17 @@ def test_map_and_traffic_distributions_match_the_reference_exact_mode():
     _close(pa, pb, min(na, nb), "driver profiles")
     (ra, _), (rb, _) = car_hist(sa, 3, 20), car_hist(sb, 3, 20)
     _close(ra, rb, min(na, nb), "routes")
-    def tile_of_car(s):
+    def cars_per_tile(s):
+        """[env, tile] counts: the envs are the independent trials (the cars of one env share its map)"""
         m = np.arange(s["cars"].shape[1])[None, :] < s["num_cars"][:, None]
         t = (s["cars"][:, :, 2] // 9) * 4 + s["cars"][:, :, 1] // 9
-        return np.bincount(t[m], minlength=T)[:T] / m.sum()
-    _close(tile_of_car(sa), tile_of_car(sb), min(na, nb), "car tiles")
+        out = np.zeros((m.shape[0], T))
+        for k in range(T):
+            out[:, k] = ((t == k) & m).sum(axis=1)
+        return out
+    ta, tb = cars_per_tile(sa), cars_per_tile(sb)
+    z = np.abs(ta.mean(axis=0) - tb.mean(axis=0)) / np.sqrt((ta.var(axis=0) + tb.var(axis=0)) / n + 1e-12)
+    assert z.max() < 5.0, f"cars per tile: largest deviation {z.max():.1f} sigma at tile {int(z.argmax())}"
     a.close(); b.close()
 
 
@@ -73,4 +79,32 @@ def test_traffic_dynamics_statistics_match():
     (xa, na), (xb, nb) = stat(sa), stat(sb)
     # mean patience, share of cars that just moved, share in a reaction delay, share of respawned cars
     assert np.all(np.abs(xa - xb) < np.array([0.12, 0.01, 0.01, 0.01])), (xa, xb)
+    a.close(); b.close()
+
+
+def test_edge_removal_pair_statistics_match():
+    """The edge draws of the Philox map stream are by rejection over fixed-width chunks of its words (pgtg_logic.cuh
+    generate_map); the removal process must keep the reference's joint law of the surviving edges: every pair
+    P(edge i kept and edge j kept) on the default 4x4 grid, and the number of kept edges."""
+    n = 40000
+    a, b = _envs(n)
+    ta, tb = a.get_state()["tiles"], b.get_state()["tiles"]
+    def edges(t):
+        ex = (t & 15).astype(np.uint8)
+        east = ((ex >> 1) & 1)[:, [i for i in range(16) if i % 4 != 3]]   # start / goal border exits are west / east of column 0 / 3
+        south = ((ex >> 2) & 1)[:, :12]
+        return np.concatenate([east, south], axis=1).astype(np.float64)
+    ea, eb = edges(ta), edges(tb)
+    assert ea.shape[1] == 24
+    _close(ea.T @ ea / n, eb.T @ eb / n, n, "edge pairs")
+    ka, kb = ea.sum(axis=1), eb.sum(axis=1)
+    _close(np.bincount(ka.astype(int), minlength=25) / n, np.bincount(kb.astype(int), minlength=25) / n, n, "kept edges")
+    # add_connections_to_borders: a uniformly random 7-subset of the 14 border slots (rejection draws in Philox mode)
+    def borders(t):
+        ex = (t & 15).astype(np.uint8)
+        cols = [(k, 0) for k in range(4)] + [(k, 1) for k in (7, 11, 15)] + [(k, 2) for k in range(12, 16)] + [(k, 3) for k in (0, 4, 8)]
+        return np.stack([(ex[:, k] >> d) & 1 for k, d in cols], axis=1).astype(np.float64)
+    ba, bb = borders(ta), borders(tb)
+    assert (ba.sum(axis=1) == 7).all() and (bb.sum(axis=1) == 7).all()
+    _close(ba.T @ ba / n, bb.T @ bb / n, n, "border slot pairs")
     a.close(); b.close()

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/r02_pytest_m.log
+B="--cpu-seconds 0 --python-seconds 0 --e2e-steps 0 --no-extra"
+python bench.py --steps 30 --warmup 5 $B > gpurun_out/r02_bench_m_default.json 2> gpurun_out/r02_bench_m_default.err
+PGTG_NO_MAP_IN_REGISTERS=1 python bench.py --steps 30 --warmup 5 $B > gpurun_out/r02_bench_m_default_shared_maps.json 2> /dev/null
+python bench.py --workload traffic-64k --steps 30 --warmup 5 $B > gpurun_out/r02_bench_m_traffic.json 2> /dev/null
+python bench.py --workload default-2M+final_observation --steps 30 --warmup 5 $B > gpurun_out/r02_bench_m_final.json 2> /dev/null
+bash tools/ncu_capture.sh r02_mapgen_m pgtg_mapgen_kernel 6 --steps 3 --warmup 3 $B
+tail -3 gpurun_out/r02_pytest_m.log
