@@ -250,7 +250,7 @@ def time_kernels_alone(env, pool, steps, flat):
             env.flat_observation()
     alone = env.raw.timing()
     env.raw.enable_timing(0)
-    env.raw.set_overlap(True)
+    env.raw.set_overlap(not os.environ.get("PGTG_NO_OVERLAP"))
     return alone
 
 

@@ -447,32 +447,23 @@ static void generate_map(rctx* r, ora_env* e) {
   int keep = c->edges_to_keep;
   int path[GMAXN];
   int plen = g_bfs(&g, S, E, path);
-  static __thread unsigned char tried[4 * PGTG_MAX_TILES];
-  int cbits = 1, per_word = 32, cleft = 0, n_und = 0;
-  uint32_t cw = 0;
   if (c->rng_mode == PGTG_RNG_PHILOX) {
-    /* Philox specification (pgtg_logic.cuh generate_map): the pick is over the grid edges not tried yet (what the
+    /* Philox specification (pgtg_logic.cuh remove_edges_tabled): the pick is over the grid edges not tried yet (what the
      * reference's draw over removable_edges amounts to: both directions of an edge are listed and leave the list
-     * together), numbered in the order of the product's connectivity bits -- horizontal edges row by row, then vertical
-     * edges by tile index y * W + x -- and made by rejection: the map stream's words are cut into chunks of
-     * ceil(log2(n_edges)) bits, lowest first, floor(32 / bits) per word; a chunk naming no edge or a tried one is skipped. */
+     * together), kept in an array that starts in the order of the product's connectivity bits -- horizontal edges row by
+     * row, then vertical edges by tile index y * W + x. A trip takes one word of the map stream (also when one edge is
+     * left), i = (word * n) >> 32, tries edge a[i] and closes the gap with the last one: a[i] = a[n-1], n -= 1. */
     n_rem = 0;
     for (int y = 0; y < H; y++) for (int x = 0; x + 1 < W; x++) { rem[n_rem][0] = x * H + y; rem[n_rem][1] = (x + 1) * H + y; n_rem++; }
     for (int y = 0; y + 1 < H; y++) for (int x = 0; x < W; x++) { rem[n_rem][0] = x * H + y; rem[n_rem][1] = x * H + y + 1; n_rem++; }
-    n_und = n_rem;
-    memset(tried, 0, (size_t)n_und);
-    while (cbits < 32 && (1 << cbits) < n_und) cbits++;
-    per_word = 32 / cbits;
   }
   while (g_edge_count(&g) - 4 > keep && n_rem > 0) { /* :245 */
     int a, b;
     if (c->rng_mode == PGTG_RNG_PHILOX) {
-      if (cleft == 0) { cw = philox_word(r, PGTG_STREAM_MAP); cleft = per_word; }
-      int pos = (int)(cw & ((1u << cbits) - 1u));
-      cw >>= cbits; cleft--;
-      if (pos >= n_und || tried[pos]) continue;
-      tried[pos] = 1; n_rem--;
-      a = rem[pos][0]; b = rem[pos][1];
+      int idx = (int)(((uint64_t)philox_word(r, PGTG_STREAM_MAP) * (uint32_t)n_rem) >> 32); /* :249 */
+      a = rem[idx][0]; b = rem[idx][1];
+      rem[idx][0] = rem[n_rem - 1][0]; rem[idx][1] = rem[n_rem - 1][1];
+      n_rem--;
     } else {
       int idx = rng_index(r, PGTG_STREAM_MAP, n_rem); /* :249 */
       a = rem[idx][0]; b = rem[idx][1];
@@ -529,8 +520,8 @@ static void generate_map(rctx* r, ora_env* e) {
   }
   if (c->rng_mode == PGTG_RNG_PHILOX) {
     /* Philox specification (pgtg_logic.cuh choose_border_slots): the picks are a uniformly random subset of the slots,
-     * drawn by the same rejection scheme as the edges: a fresh word, chunks of ceil(log2 n) bits, a chunk >= n or naming a
-     * chosen slot is skipped. */
+     * drawn by rejection: the stream's next words are cut into chunks of ceil(log2 n) bits, lowest first, floor(32 / bits)
+     * per word, the rest of a word dropped; a chunk >= n or naming a chosen slot is skipped. */
     int left = c->border_connections < nb ? c->border_connections : nb, bbits = 1, bleft = 0;
     unsigned char chosen[4 * 64] = {0};
     uint32_t bw = 0;

@@ -388,13 +388,29 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     const char* env_ctas = getenv("PGTG_MAPGEN_CTAS_PER_SM");
     int per_sm = env_ctas ? atoi(env_ctas) : 0;  // 0 = full grid (best with the connectivity table)
     e->mapgen_grid = per_sm > 0 ? sms * per_sm : 0;
-    e->mapgen_grid_overlap = e->mapgen_grid; e->overlap = true;
+    e->mapgen_grid_overlap = e->mapgen_grid; e->overlap = !getenv("PGTG_NO_OVERLAP");
   }
   if (e->dc.conn_bits) {
     size_t words = ((size_t)1 << e->dc.conn_bits) / 32 + 1;
     uint32_t* t = dev_alloc<uint32_t>(e, words, false);
     if (!t || bk_build_conn_table(e, t)) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, std::string("connectivity table: ") + bk_error()); }
     p.conn_table = t;
+    // the grid faces next to every edge (remove_edges_tabled: an edge whose face is otherwise intact cannot disconnect anything)
+    const int W = e->dc.W, H = e->dc.H, n_he = H * (W - 1);
+    std::vector<uint2> ft((size_t)e->dc.conn_bits);
+    for (auto& m : ft) m.x = m.y = 0x80000000u;
+    auto add = [&](int edge, uint32_t others) { uint2& m = ft[(size_t)edge]; if (m.x == 0x80000000u) m.x = others; else m.y = others; };
+    for (int r = 0; r + 1 < H; r++)
+      for (int x = 0; x + 1 < W; x++) {
+        const int f[4] = {r * (W - 1) + x, (r + 1) * (W - 1) + x, n_he + r * W + x, n_he + r * W + x + 1};  // top, bottom, left, right
+        uint32_t all = 0;
+        for (int k = 0; k < 4; k++) all |= 1u << f[k];
+        for (int k = 0; k < 4; k++) add(f[k], all & ~(1u << f[k]));
+      }
+    uint2* fd = dev_alloc<uint2>(e, ft.size());
+    if (!fd) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, "device allocation failed"); }
+    bk_h2d(fd, ft.data(), ft.size() * sizeof(uint2), nullptr);
+    p.face_tab = fd;
   }
   if (e->dc.path_tab) {
     uint64_t* t = dev_alloc<uint64_t>(e, (size_t)1 << e->dc.conn_bits, false);

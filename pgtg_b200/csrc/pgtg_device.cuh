@@ -245,6 +245,7 @@ struct DevPtrs {
   const uint8_t* step_lut;      // [16][81][20] per (tile type, local square, route): bit d = the neighbour square in direction d lies in
                                 // the same tile and carries a lane of that route with direction d (bits 4-7: ... carries 'all d')
   const uint64_t* path_table;   // [2^conn_bits] or null: 3-bit subgoal direction of every tile | ns << 48 | unreachable << 63
+  const uint2* face_tab;        // [conn_bits] or null: per grid edge, the other three edges of its two grid faces as edge-set masks (bit 31 = no such face)
   const pgtg_rule* rules;
   // outputs
   uint32_t* obs_packed;  // [ceil(N * obs_bits / 32)] the observation planes as bits (env i at bit i * obs_bits), or null
@@ -488,6 +489,15 @@ struct Rng {
     uint32_t j = pos & 3u;
     return j == 0 ? b0 : j == 1 ? b1 : j == 2 ? b2 : b3;
   }
+  // block `b` of a stream (words 4b .. 4b+3), for callers that walk a stream a block at a time and account for the
+  // words themselves (set_position afterwards)
+  PG_MEMBER void block(int stream, uint32_t b, uint32_t (&w)[4]) {
+    const uint64_t key = p.key[env];
+    w[0] = b; w[1] = e.elapsed; w[2] = e.episode; w[3] = (uint32_t)stream;
+    philox4x32_10(w[0], w[1], w[2], w[3], (uint32_t)key, (uint32_t)(key >> 32));
+  }
+  PG_MEMBER uint32_t position(int stream) const { return kcount[stream]; }
+  PG_MEMBER void set_position(int stream, uint32_t pos) { kcount[stream] = pos; if (cur_stream == stream) cur_stream = -1; }
   // ---- car stream (see the CW_* specification above); tape / numpy modes keep the reference's sequential order
   PG_MEMBER uint32_t car_word(int slot, int pos) {
     const int tag = 0x100 + slot;

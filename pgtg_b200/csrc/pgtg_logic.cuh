@@ -682,51 +682,55 @@ PG_HD void graph_to_boards(const DevCfg& c, uint32_t graph, uint32_t& E, uint32_
 // Philox specification of the edge removal (generate_map_graph, map_generator.py:245-264). Each trip picks uniformly among
 // the grid edges not tried yet -- exactly what the reference's draw over removable_edges amounts to (both directions of an
 // edge are listed and leave the list together, :249-253). The edges are numbered in the order of the connectivity-table
-// bits (horizontal edges row by row, then vertical edges by tile) and the pick is by REJECTION: the map stream's 32-bit
-// words are cut into chunks of b = ceil(log2(n_edges)) bits, lowest bits first, floor(32 / b) chunks per word, the rest
-// of the word dropped; a chunk that names no edge, or an edge already tried, is skipped. Exactly uniform over the untried
-// edges, and one mask test per chunk instead of a k-th-set-bit select per trip (map generation is issue-bound).
+// bits (horizontal edges row by row, then vertical edges by tile) and kept in an array, a[i] = i at the start; a trip
+// takes ONE word of the map stream (also when a single edge is left), i = (word * n) >> 32 over the n edges still in the
+// array, tries edge a[i] and closes the gap with the last one (a[i] = a[n-1], n -= 1): a Fisher-Yates walk, every trip
+// productive, no k-th-set-bit select and no rejected draws (map generation is bound by its chain of dependent lookups).
 PG_HOSTDEV int edge_chunk_bits(int n_edges) { int b = 1; while (b < 31 && (1 << b) < n_edges) b++; return b; }
 
-// the loop for grids of <= 32 edges with the connectivity table: the edge set is the table index itself
-PG_HD void edge_trial(const DevCfg& c, const DevPtrs& p, uint32_t pbit, uint32_t& graph, uint32_t& untried, int& go) {
-  if (go > 0 && (untried & pbit)) {  // (a chunk >= n_edges names a bit `untried` never had)
-    untried ^= pbit;
-    // "start and goal still connected?" is a pure function of the edge set: one lookup in the 2^E-bit table built once
-    // per handle (2 MB for the 4x4 grid, L2-resident)
-    const uint32_t g2 = graph & ~pbit;
-    const bool keep = (pg_ldg(&p.conn_table[g2 >> 5]) >> (g2 & 31)) & 1u;
-    graph = keep ? g2 : graph;
-    go = untried != 0u ? 2 * pg_popc(graph) - c.edges_to_keep : 0;  // :245 (both directions of an edge are counted): > 0 = carry on
-  }
-}
+// the loop for grids of <= 32 edges with the connectivity table: the edge set is the table index itself. `arr`: n_edges
+// bytes (rounded up to a word) of this thread's scratch. The stream must stand at a block boundary (it does: TABLED maps have a fixed start and
+// goal, nothing was drawn before); four trips per Philox block, unrolled.
 template <int RNG>
-PG_HD uint32_t remove_edges_tabled(const DevCfg& c, const DevPtrs& p, Rng<RNG>& rng) {
+PG_HD uint32_t remove_edges_tabled(const DevCfg& c, const DevPtrs& p, Rng<RNG>& rng, uint8_t* arr) {
   const int n_und = c.H * (c.W - 1) + c.W * (c.H - 1);
   uint32_t graph = (c.conn_bits >= 32 ? 0u : (1u << c.conn_bits)) - 1u;
-  uint32_t untried = n_und >= 32 ? 0xFFFFFFFFu : (1u << n_und) - 1u;
-  int go = untried != 0u ? 2 * n_und - c.edges_to_keep : 0;
-  const int cbits = edge_chunk_bits(n_und);
-  if (cbits == 5) {  // 17..32 edges (the 4x4 grid has 24): the six chunks of a word unrolled
-    while (go > 0) {
-      const uint32_t cw = rng.word(PGTG_STREAM_MAP);
+  for (int i = 0; 4 * i < n_und; i++) ((uint32_t*)arr)[i] = 0x03020100u + 0x04040404u * (uint32_t)i;  // a[i] = i (arr is word-aligned, room for 4 * ceil(n / 4))
+  int n = n_und;
+  int go = n > 0 ? 2 * n_und - c.edges_to_keep : 0;  // :245 (both directions of an edge are counted): > 0 = carry on
+  uint32_t pos = rng.position(PGTG_STREAM_MAP);
+  while (go > 0) {
+    uint32_t w[4];
+    rng.block(PGTG_STREAM_MAP, pos >> 2, w);
 #pragma unroll
-      for (int k = 0; k < 6; k++) edge_trial(c, p, 1u << ((cw >> (5 * k)) & 31u), graph, untried, go);  // :249
-    }
-  } else {
-    const int per_word = 32 / cbits;
-    const uint32_t cmask = (1u << cbits) - 1u;
-    while (go > 0) {
-      uint32_t cw = rng.word(PGTG_STREAM_MAP);
-      for (int k = 0; k < per_word && go > 0; k++) { edge_trial(c, p, 1u << (cw & cmask), graph, untried, go); cw >>= cbits; }
+    for (int k = 0; k < 4; k++) {
+      if (go > 0) {
+        const int i = (int)pg_umulhi(w[k], (uint32_t)n);  // :249
+        const int edge = arr[i];
+        const uint32_t pbit = 1u << edge;
+        arr[i] = arr[n - 1];
+        n--; pos++;
+        // "start and goal still connected?" is a pure function of the edge set: one lookup in the 2^E-bit table built
+        // once per handle (2 MB for the 4x4 grid, L2-resident) -- unless one of the two grid faces next to the edge is
+        // otherwise intact: then its end points stay connected round that face and nothing can change (half of the
+        // trips; the generation is bound by the L2's rate of scattered sector requests, so this halves its time)
+        const uint32_t g2 = graph & ~pbit;
+        const uint2 face = pg_ldg(&p.face_tab[edge]);
+        bool keep = (graph & face.x) == face.x || (graph & face.y) == face.y;
+        if (!keep) keep = (pg_ldg(&p.conn_table[g2 >> 5]) >> (g2 & 31)) & 1u;
+        graph = keep ? g2 : graph;
+        go = n > 0 ? 2 * pg_popc(graph) - c.edges_to_keep : 0;
+      }
     }
   }
+  rng.set_position(PGTG_STREAM_MAP, pos);
   return graph;
 }
 
 // Philox specification of add_connections_to_borders (map_generator.py:337-371): `border_connections` distinct slots out of
-// n (host-table order, default start / goal slots removed), which is a uniformly random subset -- drawn by the same
-// rejection scheme: a fresh word, chunks of ceil(log2 n) bits, a chunk >= n or naming a chosen slot is skipped. Returns
+// n (host-table order, default start / goal slots removed), which is a uniformly random subset -- drawn by rejection:
+// the stream's next words are cut into chunks of ceil(log2 n) bits, lowest first, floor(32 / bits) per word, the rest of
+// a word dropped; a chunk >= n or naming a chosen slot is skipped. Returns
 // the chosen slots as a bit set (the order of the picks does not matter: each sets one exit bit).
 template <int RNG, typename MASK = uint64_t>
 PG_HD MASK choose_border_slots(const DevCfg& c, Rng<RNG>& rng) {
@@ -746,6 +750,28 @@ PG_HD MASK choose_border_slots(const DevCfg& c, Rng<RNG>& rng) {
     }
   }
   return chosen;
+}
+
+// add_obstacles_to_map (map_generator.py:374-472) for one tile with exits `ex`: one random() whatever the outcome (:415),
+// then the obstacle type (:418) and its mask (:430, :470). Returns the descriptor bits type << 4 | mask << 7 (0 = none).
+template <int RNG>
+PG_HD unsigned obstacle_draw(const DevCfg& c, Rng<RNG>& rng, int ex) {
+  const double u = rng.uniform(PGTG_STREAM_MAP);  // :415
+  if (!(u < c.obstacle_probability) || ex == 0) return 0u;
+  const int type = 1 + rng.choice_cdf(PGTG_STREAM_MAP, c.obstacle_cdf, 4);  // :418
+  int mask;
+  if (type != 4) mask = rng.index(PGTG_STREAM_MAP, 8);  // :430
+  else {
+    // candidate masks 8..13 as a bit set (no indexed local array: that would live in local memory)
+    const int cnt = pg_popc(ex);
+    unsigned cand = (unsigned)(ex & 15);                          // 8..11: one light per exit
+    if ((ex & 1) && (ex & 4) && cnt >= 3) cand |= 16u;            // 12: north-south pair
+    if ((ex & 2) && (ex & 8) && cnt >= 3) cand |= 32u;            // 13: east-west pair
+    int k = rng.index(PGTG_STREAM_MAP, pg_popc(cand));  // :470
+    while (k-- > 0) cand &= cand - 1;                             // drop the k lowest candidates
+    mask = 8 + pg_ffs(cand) - 1;
+  }
+  return (unsigned)(type << 4 | mask << 7);
 }
 
 // TABLED = compile-time promise that both per-handle tables exist (fixed start/goal, <= 16 tiles,
@@ -768,32 +794,23 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
   const bool tabled = TABLED || (TMAX <= 32 && c.conn_bits != 0);
   uint32_t graph = tabled ? ((c.conn_bits >= 32 ? 0u : (1u << c.conn_bits)) - 1u) : 0u;
   if (RNG == PGTG_RNG_PHILOX) {
-    // Philox specification: see remove_edges_tabled above (rejection over fixed-width chunks of the stream's words)
+    // Philox specification: see remove_edges_tabled above (one word per trip, Fisher-Yates walk over the edge array)
     constexpr int UW = (2 * TMAX + 31) / 32;
-    if (UW == 1 && tabled) graph = remove_edges_tabled<RNG>(c, p, rng);
-    else {
-    uint32_t untried[UW];
+    if (UW == 1 && tabled && (rng.position(PGTG_STREAM_MAP) & 3u) == 0u) {
+      alignas(4) uint8_t arr8[32];
+      graph = remove_edges_tabled<RNG>(c, p, rng, arr8);
+    } else {
+    uint16_t arr[2 * TMAX];  // (the slow path: big maps, random start / goal -- a local-memory array is fine here)
     const int n_he = c.H * (W - 1), n_und = n_he + W * (c.H - 1);
-    int n_untried = n_und, cur = 2 * n_und;
-#pragma unroll
-    for (int i = 0; i < UW; i++) untried[i] = (i * 32 + 32 <= n_und) ? 0xFFFFFFFFu : (i * 32 < n_und ? ((1u << (n_und & 31)) - 1u) : 0u);
-    const int cbits = edge_chunk_bits(n_und), per_word = 32 / cbits;
-    const uint32_t cmask = (1u << cbits) - 1u;
-    uint32_t cw = 0;
-    int cleft = 0;
-    while (cur > c.edges_to_keep && n_untried > 0) {  // :245
-      if (cleft == 0) { cw = rng.word(PGTG_STREAM_MAP); cleft = per_word; }
-      const int pos = (int)(cw & cmask);  // :249
-      cw >>= cbits; cleft--;
-      const uint32_t pbit = 1u << (pos & 31);
-      bool hit = false;
-#pragma unroll
-      for (int i = 0; i < UW; i++)
-        if (i == (pos >> 5) && (untried[i] & pbit)) { untried[i] ^= pbit; hit = true; }
-      if (!hit) continue;
-      n_untried--;
+    for (int i = 0; i < n_und; i++) arr[i] = (uint16_t)i;
+    int n = n_und, cur = 2 * n_und;
+    while (cur > c.edges_to_keep && n > 0) {  // :245
+      const int i = (int)pg_umulhi(rng.word(PGTG_STREAM_MAP), (uint32_t)n);  // :249
+      const int pos = arr[i];
+      arr[i] = arr[n - 1];
+      n--;
       if (tabled) {
-        const uint32_t g2 = graph & ~pbit;
+        const uint32_t g2 = graph & ~(1u << pos);
         const bool keep = (pg_ldg(&p.conn_table[g2 >> 5]) >> (g2 & 31)) & 1u;
         graph = keep ? g2 : graph;
         cur -= keep ? 2 : 0;
@@ -889,27 +906,8 @@ PG_HD void generate_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& 
     }
   }
   // add_obstacles_to_map (:374-472), row-major, one random() per tile whatever the outcome
-  if (c.obstacle_probability > 0) {
-    for (int t = 0; t < T; t++) {
-      double u = rng.uniform(PGTG_STREAM_MAP);  // :415
-      int ex = td_exits(m.tiles[t]);
-      if (!(u < c.obstacle_probability) || ex == 0) continue;
-      int type = 1 + rng.choice_cdf(PGTG_STREAM_MAP, c.obstacle_cdf, 4);  // :418
-      int mask;
-      if (type != 4) mask = rng.index(PGTG_STREAM_MAP, 8);  // :430
-      else {
-        // candidate masks 8..13 as a bit set (no indexed local array: that would live in local memory)
-        int cnt = pg_popc(ex);
-        unsigned cand = (unsigned)(ex & 15);                          // 8..11: one light per exit
-        if ((ex & 1) && (ex & 4) && cnt >= 3) cand |= 16u;            // 12: north-south pair
-        if ((ex & 2) && (ex & 8) && cnt >= 3) cand |= 32u;            // 13: east-west pair
-        int k = rng.index(PGTG_STREAM_MAP, pg_popc(cand));  // :470
-        while (k-- > 0) cand &= cand - 1;                             // drop the k lowest candidates
-        mask = 8 + pg_ffs(cand) - 1;
-      }
-      m.tiles[t] = (uint16_t)(ex | type << 4 | mask << 7);
-    }
-  }
+  if (c.obstacle_probability > 0)
+    for (int t = 0; t < T; t++) m.tiles[t] = (uint16_t)(m.tiles[t] | obstacle_draw<RNG>(c, rng, td_exits(m.tiles[t])));
   e.plan = plan_pack(sx, sy, sd, gx, gy, gd, 0);
 }
 
@@ -1050,15 +1048,16 @@ PG_HD void build_map(const DevCfg& c, const DevPtrs& p, MapView& m, EnvRegs& e, 
   m.plan = e.plan;
 }
 
-// build_map for the configuration the headline runs (Philox, both tables, fixed start / goal, 8 or 16 tiles, no obstacles): the map is a pure function of the surviving edge set and one start-square draw, so the
-// descriptors are assembled in registers, two per word, from the edge boards and the path-table entry -- no per-tile
-// loops over shared memory, no staged tables. Same bits as build_map (tests/test_gpu_properties.py forces both).
+// build_map for maps that are a function of the surviving edge set and a few draws (Philox, both tables, fixed start / goal,
+// 8 or 16 tiles -- the headline configuration and every BASELINE configuration on the default 4x4 grid): the descriptors are
+// assembled in registers, two per word, from the edge boards, the border picks and the path-table entry, and stored straight
+// to the ring -- no per-tile loops over shared memory, no staged tables. Same bits as build_map (both are tested).
 PG_HOSTDEV bool map_in_registers(const DevCfg& c) {
-  return c.conn_bits != 0 && c.path_tab && (c.T == 8 || c.T == 16) && !(c.obstacle_probability > 0) && c.start_mode == 0 && c.goal_mode == 0 && !c.fixed_map;
+  return c.conn_bits != 0 && c.path_tab && (c.T == 8 || c.T == 16) && c.start_mode == 0 && c.goal_mode == 0 && !c.fixed_map;
 }
 template <int RNG>
-PG_HD void build_map_in_registers(const DevCfg& c, const DevPtrs& p, EnvRegs& e, Rng<RNG>& rng, uint32_t (&out)[8]) {
-  const uint32_t graph = remove_edges_tabled<RNG>(c, p, rng);
+PG_HD void build_map_in_registers(const DevCfg& c, const DevPtrs& p, EnvRegs& e, Rng<RNG>& rng, uint8_t* arr, uint32_t* dst /* T / 2 words, 16-byte aligned */) {
+  const uint32_t graph = remove_edges_tabled<RNG>(c, p, rng, arr);
   const uint64_t v = pg_ldg(&p.path_table[graph]);  // 3-bit subgoal direction per tile | ns << 48 | unreachable << 63
   uint32_t E, S;
   graph_to_boards(c, graph, E, S);
@@ -1069,19 +1068,36 @@ PG_HD void build_map_in_registers(const DevCfg& c, const DevPtrs& p, EnvRegs& e,
     const unsigned s = pg_ldg(&p.border_slots[pg_ffs(chosen) - 1]);  // tile | direction << 8
     border |= (uint64_t)(1u << (s >> 8)) << (4 * (s & 255u));
   }
-  const uint32_t sg_lo = (uint32_t)v, sg_hi = (uint32_t)(v >> 24);  // tiles 0-7 in bits 0-23, tiles 8-15 in bits 24-47
-  const uint32_t bd_lo = (uint32_t)border, bd_hi = (uint32_t)(border >> 32);
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    uint32_t w = 0;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int t = 2 * k + h;
-      const uint32_t ex = ((Sn >> t) & 1u) | ((E >> t) & 1u) << 1 | ((S >> t) & 1u) << 2 | ((Ew >> t) & 1u) << 3 | (((t < 8 ? bd_lo : bd_hi) >> (4 * (t & 7))) & 15u);
-      const uint32_t sg = ((t < 8 ? sg_lo : sg_hi) >> (3 * (t & 7))) & 7u;
-      w |= (ex | sg << 11) << (16 * h);
+  if (c.obstacle_probability > 0) {
+    // obstacles draw tile by tile, a lane-dependent number of words each: a rolled loop, one 32-bit store per tile pair
+    for (int k = 0; 2 * k < c.T; k++) {
+      uint32_t w = 0;
+      for (int h = 0; h < 2; h++) {
+        const int t = 2 * k + h;
+        const uint32_t ex = ((Sn >> t) & 1u) | ((E >> t) & 1u) << 1 | ((S >> t) & 1u) << 2 | ((Ew >> t) & 1u) << 3 | ((uint32_t)(border >> (4 * t)) & 15u);
+        const uint32_t sg = (uint32_t)(v >> (3 * t)) & 7u;
+        w |= (ex | obstacle_draw<RNG>(c, rng, (int)ex) | sg << 11) << (16 * h);
+      }
+      dst[k] = w;
     }
-    out[k] = w;
+  } else {
+    const uint32_t sg_lo = (uint32_t)v, sg_hi = (uint32_t)(v >> 24);  // tiles 0-7 in bits 0-23, tiles 8-15 in bits 24-47
+    const uint32_t bd_lo = (uint32_t)border, bd_hi = (uint32_t)(border >> 32);
+    uint32_t out[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int t = 2 * k + h;
+        const uint32_t ex = ((Sn >> t) & 1u) | ((E >> t) & 1u) << 1 | ((S >> t) & 1u) << 2 | ((Ew >> t) & 1u) << 3 | (((t < 8 ? bd_lo : bd_hi) >> (4 * (t & 7))) & 15u);
+        const uint32_t sg = ((t < 8 ? sg_lo : sg_hi) >> (3 * (t & 7))) & 7u;
+        w |= (ex | sg << 11) << (16 * h);
+      }
+      out[k] = w;
+    }
+    { uint4 q; q.x = out[0]; q.y = out[1]; q.z = out[2]; q.w = out[3]; ((uint4*)dst)[0] = q; }
+    if (c.T == 16) { uint4 q; q.x = out[4]; q.y = out[5]; q.z = out[6]; q.w = out[7]; ((uint4*)dst)[1] = q; }
   }
   if (v >> 63) e.err |= 8;
   e.plan = plan_pack(c.start_x, c.start_y, c.start_dir, c.goal_x, c.goal_y, c.goal_dir, 0) | (unsigned)((v >> 48) & 0x1FFu) << 20;

@@ -19,6 +19,9 @@ namespace pgtg {
 #ifndef PGTG_LEAN_MIN_BLOCKS
 #define PGTG_LEAN_MIN_BLOCKS 8
 #endif
+// bytes of the per-thread edge array of the register-resident map generation: 7 words, an odd stride, so that the lanes of
+// a warp reading the same index hit 32 different banks
+#define PGTG_EDGE_ROW 28
 #ifndef PGTG_MAPGEN_MIN_BLOCKS
 #define PGTG_MAPGEN_MIN_BLOCKS 12
 #endif
@@ -220,24 +223,32 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
 // (PGTG_MAPGEN_CTAS_PER_SM); the default is one request per thread. TABLED: see generate_map.
 template <int RNG, int TMAX, bool TABLED = false>
 __global__ void __launch_bounds__(128, TABLED ? PGTG_MAPGEN_TABLED_MIN_BLOCKS : PGTG_MAPGEN_MIN_BLOCKS) pgtg_mapgen_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity,
-                                                                                const __grid_constant__ SharedLayout layout, bool in_registers) {
+                                                                                const __grid_constant__ SharedLayout layout) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t count = p.regen_count[parity];
   if (blockIdx.x * blockDim.x >= count) return;
   const uint2* list = p.regen_list + (size_t)parity * 2 * c.N;
-  if (RNG == PGTG_RNG_PHILOX && TABLED && in_registers) {  // the headline configuration: no tables, no shared memory, no barrier
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-      const uint2 r = list[i];
-      phase_pregenerate_in_registers<RNG>(c, p, (int)r.x, r.y);
-    }
-    return;
-  }
   BlockShared sh = carve_layout(smem, layout);
   stage_tables(c, p, sh, threadIdx.x, blockDim.x);
   __syncthreads();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     uint2 r = list[i];
     phase_pregenerate<RNG, TMAX, TABLED>(c, p, sh, threadIdx.x, (int)r.x, r.y);
+  }
+}
+
+// The same for configurations whose map is assembled in registers (map_in_registers -- the headline configuration): no
+// staged tables, no barrier; shared memory holds only each thread's edge array. Its own kernel so that the register
+// allocation is not the staged path's (MINB CTAs of 128 threads per SM; measured).
+template <int RNG, int MINB>
+__global__ void __launch_bounds__(128, MINB) pgtg_mapgen_registers_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, int parity) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t count = p.regen_count[parity];
+  if (blockIdx.x * blockDim.x >= count) return;
+  const uint2* list = p.regen_list + (size_t)parity * 2 * c.N;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const uint2 r = list[i];
+    phase_pregenerate_in_registers<RNG>(c, p, smem + threadIdx.x * PGTG_EDGE_ROW, (int)r.x, r.y);
   }
 }
 
@@ -272,25 +283,41 @@ static int launch_sized(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, 
   return launch_one<RNG, MODE, 256, PREGEN>(e, mask, seeds, actions, action_bytes, st);
 }
 
+template <int RNG, int MINB>
+static int launch_mapgen_registers(pgtg_env* e, cudaStream_t st, int grid, int carveout) {
+  auto kern = pgtg::pgtg_mapgen_registers_kernel<RNG, MINB>;
+  static bool carve_set = false;
+  if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout); carve_set = true; }
+  kern<<<grid, 128, 128 * PGTG_EDGE_ROW, st>>>(e->dc, e->dp, e->dp.parity);
+  return lk(cudaGetLastError());
+}
+
 template <int RNG, int TMAX, bool TABLED = false>
 static int launch_mapgen(pgtg_env* e, cudaStream_t st) {
   const int B = 128;
   size_t smem = pgtg::mapgen_shared_bytes(e->dc, B);
-  auto kern = pgtg::pgtg_mapgen_kernel<RNG, TMAX, TABLED>;
-  const bool in_registers = TABLED && pgtg::map_in_registers(e->dc) && !getenv("PGTG_NO_MAP_IN_REGISTERS");
-  if (in_registers) smem = 0;
-  static bool carve_set = false;
-  if (!carve_set) {
-    const char* cv = getenv("PGTG_MAPGEN_CARVEOUT");  // experiment: L1-sized carveout for the connectivity-table lookups
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : cudaSharedmemCarveoutMaxShared);
-    carve_set = true;
-  }
-  if (smem > 48 * 1024) { int rc = lk(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); if (rc) return rc; }
   int full = (2 * e->dc.N + B - 1) / B;
   int grid = e->mapgen_grid > 0 && e->mapgen_grid < full ? e->mapgen_grid : full;
+  if constexpr (RNG == PGTG_RNG_PHILOX && TABLED) {
+    if (pgtg::map_in_registers(e->dc) && !getenv("PGTG_NO_MAP_IN_REGISTERS")) {
+      const char* mb = getenv("PGTG_MAPGEN_MINB");   // tuning knobs
+      const char* cv = getenv("PGTG_MAPGEN_CARVEOUT");
+      // 48 registers; 45 KB shared and the rest L1 (the connectivity lookups of the first trips hit it) -- except next to the
+      // traffic tick, which leaves SMs free for this kernel only if both ask for the same carveout (measured)
+      const int minb = mb ? atoi(mb) : 10, carve = cv ? atoi(cv) : (e->traffic_G > 0 ? (int)cudaSharedmemCarveoutMaxShared : 25);
+      if (minb >= 16) return launch_mapgen_registers<RNG, 16>(e, st, grid, carve);
+      if (minb >= 12) return launch_mapgen_registers<RNG, 12>(e, st, grid, carve);
+      if (minb >= 10) return launch_mapgen_registers<RNG, 10>(e, st, grid, carve);
+      return launch_mapgen_registers<RNG, 8>(e, st, grid, carve);
+    }
+  }
+  auto kern = pgtg::pgtg_mapgen_kernel<RNG, TMAX, TABLED>;
+  static bool carve_set = false;
+  if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve_set = true; }
+  if (smem > 48 * 1024) { int rc = lk(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); if (rc) return rc; }
   unsigned char* const origin = (unsigned char*)4096;
   const pgtg::SharedLayout layout = pgtg::layout_of(pgtg::carve_mapgen(origin, e->dc, B), origin);
-  kern<<<grid, B, smem, st>>>(e->dc, e->dp, e->dp.parity, layout, in_registers);
+  kern<<<grid, B, smem, st>>>(e->dc, e->dp, e->dp.parity, layout);
   return lk(cudaGetLastError());
 }
 

@@ -125,7 +125,8 @@ static void run_mapgen(pgtg_env* h) {
   uint32_t count = p.regen_count[p.parity];
   const uint2* list = p.regen_list + (size_t)p.parity * 2 * c.N;
   if (RNG == PGTG_RNG_PHILOX && TABLED && map_in_registers(c) && !getenv("PGTG_NO_MAP_IN_REGISTERS")) {  // as the kernel dispatches
-    for (uint32_t i = 0; i < count; i++) phase_pregenerate_in_registers<RNG>(c, p, (int)list[i].x, list[i].y);
+    alignas(4) uint8_t arr[32];
+    for (uint32_t i = 0; i < count; i++) phase_pregenerate_in_registers<RNG>(c, p, arr, (int)list[i].x, list[i].y);
     free(smem);
     return;
   }

@@ -79,6 +79,8 @@ CONFIGS = {
     # 8-tile grids: the emulation build has the connectivity / path tables up to 13 edges, so these run the tabled edge
     # removal and the register-resident map assembly the headline configuration uses on the device (map_in_registers)
     "tabled_2x4_registers": (dict(random_map_width=2, random_map_height=4), 300, 40),
+    "tabled_2x4_registers_obstacles": (dict(random_map_width=2, random_map_height=4, random_map_obstacle_probability=0.6,
+                                            random_map_traffic_light_probability_weight=3, traffic_density=0.1), 200, 40),
     "tabled_4x2_registers_sparse": (dict(random_map_width=4, random_map_height=2, random_map_percentage_of_connections=0.2,
                                          max_episode_steps=12), 300, 40),
     "tabled_3x3_shared": (dict(random_map_width=3, random_map_height=3, random_map_obstacle_probability=0.3), 200, 40),
