@@ -131,6 +131,14 @@ def test_specialised_kernels_match_general(kw, monkeypatch):
     assert fast_stats.keys() == slow_stats.keys()
     for k in fast_stats:
         assert fast_stats[k] == pytest.approx(slow_stats[k], rel=1e-12), k
+    # third leg: lean tick, tabled map generation through the staged kernel instead of the register-resident one
+    monkeypatch.delenv("PGTG_NO_LEAN")
+    monkeypatch.delenv("PGTG_NO_TABLED")
+    monkeypatch.setenv("PGTG_NO_MAP_IN_REGISTERS", "1")
+    staged, _ = run()
+    for t, (a, b) in enumerate(zip(fast, staged)):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), f"tick {t} (staged map generation)"
 
 
 @pytest.mark.gpu
