@@ -127,8 +127,10 @@ static void build_direction_lut(int R, std::vector<uint8_t>& lut) {
 // The plain configuration the LEAN tick instantiation promises (pgtg_logic.cuh, env_step): decided at
 // pgtg_create and again whenever something it depends on changes (pgtg_update_rules, pgtg_set_state).
 static int lean_predicate(const pgtg_config& c, const DevCfg& d) {
-  return (d.pregen && !(c.traffic_density > 0) && !d.rules_without_traffic && !c.sliding && d.obs_fast && d.kind_channel[PGTG_CH_CAR_SPAWNER] < 0 &&
-          !d.use_nsd && !d.vis_words && !c.separate_reward_cost) ? 1 : 0;  // (terminal observations: the lean FINAL instantiation)
+  const bool plain = d.pregen && !(c.traffic_density > 0) && !d.rules_without_traffic && d.kind_channel[PGTG_CH_CAR_SPAWNER] < 0 && !d.vis_words &&
+                     !c.separate_reward_cost && (c.sliding || d.obs_fast);
+  if (!plain) return 0;
+  return (c.sliding || d.use_nsd) ? 2 : 1;  // 2: the lean SLIDE instantiation (terminal observations: the FINAL ones)
 }
 
 // The LUT block the kernels stage into shared memory: the generated tables plus everything derived from them.
@@ -481,7 +483,7 @@ extern "C" int pgtg_update_rules(pgtg_env* e, const pgtg_rule* rules, int num_ru
   e->cfg.num_rules = num_rules;
   for (int i = 0; i < num_rules; i++) e->cfg.rules[i] = rules[i];
   // a rule that can fire without traffic needs apply_braking, which the lean tick does not contain
-  e->dc.lean = lean_predicate(e->cfg, e->dc) && !e->cars_injected;
+  e->dc.lean = e->cars_injected ? 0 : lean_predicate(e->cfg, e->dc);
   return PGTG_OK;
 }
 
@@ -1033,7 +1035,7 @@ extern "C" int pgtg_kernel_info(pgtg_env* e, char* out, int out_bytes) {
   if (!e || !out || out_bytes < 1) return fail(PGTG_ERR_INVALID, "null argument");
   const char* rng = e->cfg.rng_mode == PGTG_RNG_TAPE ? "tape" : e->cfg.rng_mode == PGTG_RNG_NUMPY ? "numpy" : "philox";
   if (e->traffic_G > 0) snprintf(out, (size_t)out_bytes, "tick=traffic(G=%d,NT=%d) mapgen=%s rng=%s", e->traffic_G, e->traffic_NT, e->dc.pregen ? (e->dc.conn_bits && e->dc.path_tab ? "tabled" : "general") : "none", rng);
-  else snprintf(out, (size_t)out_bytes, "tick=%s(B=%d) mapgen=%s rng=%s", e->dc.lean && e->dc.pregen && e->cfg.rng_mode != PGTG_RNG_TAPE && !getenv("PGTG_NO_LEAN") ? (e->dc.write_final_obs ? "lean+final" : "lean") : "general", e->block,
+  else snprintf(out, (size_t)out_bytes, "tick=%s(B=%d) mapgen=%s rng=%s", e->dc.lean && e->dc.pregen && e->cfg.rng_mode != PGTG_RNG_TAPE && !getenv("PGTG_NO_LEAN") ? (e->dc.lean == 2 ? (e->dc.write_final_obs ? "lean+slide+final" : "lean+slide") : e->dc.write_final_obs ? "lean+final" : "lean") : "general", e->block,
                 e->dc.pregen ? (e->dc.conn_bits && e->dc.path_tab ? "tabled" : "general") : "in-tick", rng);
   return PGTG_OK;
 }

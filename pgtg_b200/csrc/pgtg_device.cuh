@@ -160,7 +160,7 @@ struct DevCfg {
   int C, P, sliding, window_k, use_nsd;
   int channel_kind[PGTG_MAX_CHANNELS];
   int kind_channel[16];          // kind -> its channel (-1: not observed); valid when obs_fast
-  int lean;                     // plain configuration: the tick runs the LEAN instantiation (see env_step)
+  int lean;                     // plain configuration: the tick runs the LEAN instantiation (see env_step); 2 = its SLIDE variant (sliding window / nsd)
   int obs_fast;                 // fixed window and no kind listed twice: the observation is written kind by kind
   int fixed_map, edges_to_keep, n_edge_tab, border_connections, n_border_slots;
   int start_mode, goal_mode, start_x, start_y, start_dir, goal_x, goal_y, goal_dir, min_sg_dist;

@@ -1237,9 +1237,41 @@ PG_HD uint32_t sliding_column_bits(const DevCfg& c, const MapView& m, int kind, 
   return col;
 }
 
+// The same planes tile by tile instead of column by column (the lean SLIDE tick, one env per thread): the window covers at
+// most ceil((P + 8) / 9)^2 tiles; a tile's 81-bit plane of a kind is built ONCE and its columns are cut into the window, and
+// a tile that has nothing of the kind (most kinds on most tiles) costs a descriptor test. Same bits as the column loop.
+PG_HD void sliding_planes_by_tile(const DevCfg& c, const MapView& m, int phase, int x0, int y0, uint32_t* bits, uint32_t base) {
+  const int P = c.P, PP = P * P;
+  const int tx_lo = (x0 + 9 * 64) / TILE - 64, tx_hi = (x0 + P - 1 + 9 * 64) / TILE - 64;  // floor division (x0 >= -window_k)
+  const int ty_lo = (y0 + 9 * 64) / TILE - 64, ty_hi = (y0 + P - 1 + 9 * 64) / TILE - 64;
+  for (int ch = 0; ch < c.C; ch++) {
+    const int kind = c.channel_kind[ch];
+    if (kind == PGTG_CH_ZERO || kind == PGTG_CH_TRAFFIC) continue;  // (no cars in the lean tick)
+    const uint32_t off = base + ch * PP;
+    for (int ttx = tx_lo; ttx <= tx_hi; ttx++) {
+      const int ix_lo = ttx * TILE - x0 > 0 ? ttx * TILE - x0 : 0, ix_hi = ttx * TILE + TILE - x0 < P ? ttx * TILE + TILE - x0 : P;
+      for (int tty = ty_lo; tty <= ty_hi; tty++) {
+        const int iy_lo = tty * TILE - y0 > 0 ? tty * TILE - y0 : 0, iy_hi = tty * TILE + TILE - y0 < P ? tty * TILE + TILE - y0 : P;
+        const uint32_t rows = (1u << (iy_hi - iy_lo)) - 1u;  // <= 9 rows of this tile
+        if (ttx < 0 || ttx >= c.W || tty < 0 || tty >= c.H) {  // outside the map: walls and nothing else (:1384)
+          if (kind == PGTG_CH_WALLS)
+            for (int ix = ix_lo; ix < ix_hi; ix++) emit_bits(bits, off + ix * P + iy_lo, rows);
+          continue;
+        }
+        uint32_t w[3];
+        tile_plane(c, m, kind, tty * c.W + ttx, phase, w);
+        if (!(w[0] | w[1] | w[2])) continue;
+        const int ly = y0 + iy_lo - tty * TILE;
+        for (int ix = ix_lo; ix < ix_hi; ix++) emit_bits(bits, off + ix * P + iy_lo, (col9(w, x0 + ix - ttx * TILE) >> ly) & rows);
+      }
+    }
+  }
+}
+
 // writes env's C*P*P observation bits at bit offset `base` of `bits`, plus position/velocity/nsd
 // (planes = false: only the scalars -- the caller writes the planes itself, e.g. one window column per thread)
-template <bool LEAN = false>
+// (SLIDE: the lean instantiation that keeps the sliding window and next_subgoal_direction -- still no cars, no rules)
+template <bool LEAN = false, bool SLIDE = false>
 PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, const EnvRegs& e, int env, uint32_t* bits,
                         uint32_t base, int32_t* pos, int32_t* vel, int32_t* nsd, bool planes = true) {
   int pix = e.x < 0 ? 0 : (e.x > c.WS - 1 ? c.WS - 1 : e.x);  // :1352-1356
@@ -1251,7 +1283,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
   int PP = c.P * c.P;
   if (!LEAN && !planes && !c.sliding) {
     pos[0] = pix - tx * TILE; pos[1] = piy - ty * TILE;
-  } else if (LEAN || (!c.sliding && c.obs_fast)) {
+  } else if ((LEAN && !SLIDE) || (!c.sliding && c.obs_fast)) {
     // Fixed window, kind by kind: a tile has walls, at most ONE obstacle / light plane, goal-ish
     // lines only on path tiles; everything else stays zero and costs nothing (same bits as the
     // channel loop below, which remains for feature lists that name a kind twice).
@@ -1299,7 +1331,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
       emit_bits(bits, off, w[0]); emit_bits(bits, off + 32, w[1]); emit_bits(bits, off + 64, w[2]);
     }
     pos[0] = pix - tx * TILE; pos[1] = piy - ty * TILE;  // :1448-1461
-  } else if (!c.sliding) {
+  } else if (!LEAN && !c.sliding) {  // (the lean predicate asks for obs_fast with the fixed window)
     int t = ty * c.W + tx;
     for (int ch = 0; ch < c.C; ch++) {
       int kind = c.channel_kind[ch];
@@ -1319,6 +1351,8 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
     pos[0] = pix - tx * TILE; pos[1] = piy - ty * TILE;  // :1448-1461
   } else {
     int k = c.window_k, x0 = e.x - k, y0 = e.y - k;  // window around the UNCLAMPED position (:1370-1377)
+    if (LEAN) { if (planes) sliding_planes_by_tile(c, m, phase, x0, y0, bits, base); }
+    else
     for (int ch = 0; planes && ch < c.C; ch++) {
       int kind = c.channel_kind[ch];
       if (kind == PGTG_CH_ZERO) continue;
@@ -1337,7 +1371,7 @@ PG_HD void env_observe(const DevCfg& c, const DevPtrs& p, const MapView& m, cons
   }
   vel[0] = e.vx; vel[1] = e.vy;
   int d = -1;
-  if (!LEAN && c.use_nsd) {  // :1466-1504
+  if ((!LEAN || SLIDE) && c.use_nsd) {  // :1466-1504
     int sg = td_sg(m.tiles[ty * c.W + tx]);  // map.py:120-141
     d = sg ? sg - 1 : -1;
     if (d == -1 || c.sliding) {

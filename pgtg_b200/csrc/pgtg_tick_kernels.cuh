@@ -43,8 +43,9 @@ __device__ unsigned long long g_phase_clk[16];
 #define PG_CLK(i)
 #endif
 
-// (FINAL: the lean instantiation that also writes the terminal observation of the finished envs, gymnasium's final_observation)
-template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false>
+// (FINAL: the lean instantiation that also writes the terminal observation of the finished envs, gymnasium's final_observation;
+//  SLIDE: the lean instantiation for the sliding window and / or next_subgoal_direction -- the observation of train.py without cars)
+template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false, bool SLIDE = false>
 __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
                                                         const void* __restrict__ actions, int action_bytes, StatsArgs sa,
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
       PG_CLK(3)
       if (LEAN && FINAL) {  // terminal observation first: emit the finished envs' planes, expand their rows, clear the bitstring
         if (lane == 0) sh.counters[16 + warp] = (int)any;
-        if (done) phase_emit_regs<true>(c, p, sh, tid, env, true, er);
+        if (done) phase_emit_regs<true, SLIDE>(c, p, sh, tid, env, true, er);
         __syncthreads();
         phase_expand_final_vec(c, p.f_obs_map, sh, tid, B, env0, nvalid, sh.counters + 16);
         __syncthreads();
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
         else { k = sh.regs[tid].episode + 1u; phase_reset<RNG, TMAX, true, false>(c, p, sh, tid, env); }  // k: the episode this env is about to start
       }
       PG_CLK(4)
-      if (valid) { if (LEAN) phase_emit_regs<true>(c, p, sh, tid, env, false, er); else phase_emit<false>(c, p, sh, tid, env, false); }
+      if (valid) { if (LEAN) phase_emit_regs<true, SLIDE>(c, p, sh, tid, env, false, er); else phase_emit<false>(c, p, sh, tid, env, false); }
       PG_CLK(5)
       if (any) {
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
@@ -257,9 +258,9 @@ __global__ void __launch_bounds__(128, MINB) pgtg_mapgen_registers_kernel(const 
 // launch code: returns the cudaError_t of the launch (0 = ok)
 static inline int lk(cudaError_t e) { return (int)e; }
 
-template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false>
+template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false, bool SLIDE = false>
 static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
-  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN, LEAN, FINAL>;
+  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN, LEAN, FINAL, SLIDE>;
   // same L1/shared carveout as the map-generation kernel: an SM cannot host CTAs of two kernels with
   // different carveouts, which would serialise the two (measured: no overlap at all without this)
   static bool carve_set = false;
@@ -327,9 +328,14 @@ static int launch_mode(pgtg_env* e, int mode, const uint8_t* mask, const int64_t
     case MODE_STEP:
       // plain configuration: the lean instantiation (the ring-fed reset does not depend on the board size)
       if (RNG != PGTG_RNG_TAPE && e->dc.pregen && e->dc.lean && !getenv("PGTG_NO_LEAN")) {
-        if (e->dc.write_final_obs)
-          return launch_one<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, MODE_STEP, 16, RNG != PGTG_RNG_TAPE, RNG != PGTG_RNG_TAPE, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
-        return launch_one<RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG, MODE_STEP, 16, RNG != PGTG_RNG_TAPE, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
+        constexpr int R = RNG == PGTG_RNG_TAPE ? PGTG_RNG_PHILOX : RNG;
+        constexpr bool L = RNG != PGTG_RNG_TAPE;  // (never launched for the tape: keeps that translation unit from instantiating it)
+        if (e->dc.lean == 2) {  // sliding window and / or next_subgoal_direction
+          if (e->dc.write_final_obs) return launch_one<R, MODE_STEP, 16, L, L, L, L>(e, mask, seeds, actions, action_bytes, st);
+          return launch_one<R, MODE_STEP, 16, L, L, false, L>(e, mask, seeds, actions, action_bytes, st);
+        }
+        if (e->dc.write_final_obs) return launch_one<R, MODE_STEP, 16, L, L, L>(e, mask, seeds, actions, action_bytes, st);
+        return launch_one<R, MODE_STEP, 16, L, L>(e, mask, seeds, actions, action_bytes, st);
       }
       if (RNG != PGTG_RNG_TAPE && e->dc.pregen) return launch_sized<RNG, MODE_STEP, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);
       return launch_sized<RNG, MODE_STEP, false>(e, mask, seeds, actions, action_bytes, st);

@@ -47,7 +47,7 @@ static void bk_traffic_geometry(const pgtg::DevCfg&, int* G, int* NT) { *G = 32;
 
 #include "../../pgtg_b200/csrc/pgtg_api_impl.hpp"
 
-template <int RNG, int TMAX, bool PREGEN, bool LEAN = false>
+template <int RNG, int TMAX, bool PREGEN, bool LEAN = false, bool SLIDE = false>
 static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes,
                       int blk, unsigned char* smem) {
   const DevCfg& c = h->dc;
@@ -70,7 +70,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
       }
     }
     if (c.write_final_obs && n_done) {
-      for (int k = 0; k < n_done; k++) phase_emit(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true);
+      for (int k = 0; k < n_done; k++) { if (LEAN) phase_emit<LEAN, SLIDE>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true); else phase_emit(c, p, sh, sh.done_list[k], env0 + sh.done_list[k], true); }
       if (LEAN) {  // the lean FINAL instantiation expands the finished envs' rows 32 bytes at a time
         int words[8] = {0};
         for (int k = 0; k < n_done; k++) words[sh.done_list[k] >> 5] |= (int)(1u << (sh.done_list[k] & 31));
@@ -110,7 +110,7 @@ static void run_block(pgtg_env* h, int mode, const uint8_t* mask, const int64_t*
     if (PREGEN && mode == MODE_STEP) phase_reset<RNG, TMAX, true, LEAN>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
     else phase_reset<RNG, TMAX, false>(c, p, sh, sh.done_list[k], env0 + sh.done_list[k]);
   }
-  for (int t = 0; t < nvalid; t++) phase_emit<LEAN>(c, p, sh, t, env0 + t, false);
+  for (int t = 0; t < nvalid; t++) phase_emit<LEAN, SLIDE>(c, p, sh, t, env0 + t, false);
   for (int t = 0; t < B; t++) phase_expand(c, p.obs_map, sh, t, B, env0, nvalid, p.obs_packed);
   for (int k = 0; k < 8; k++) p.stats[k] += st[k];
 }
@@ -244,7 +244,8 @@ static int bk_launch(pgtg_env* h, int mode, const uint8_t* mask, const int64_t* 
     bool tape = h->cfg.rng_mode == PGTG_RNG_TAPE;
 #define RUN(R, M, G) run_block<R, M, G>(h, mode, mask, seeds, actions, action_bytes, b, smem)
 // the lean instantiation is a step-mode specialisation, as in the CUDA launch code
-#define RUNL(R, M) run_block<R, M, true, true>(h, mode, mask, seeds, actions, action_bytes, b, smem)
+#define RUNL(R, M) do { if (h->dc.lean == 2) run_block<R, M, true, true, true>(h, mode, mask, seeds, actions, action_bytes, b, smem); \
+                        else run_block<R, M, true, true>(h, mode, mask, seeds, actions, action_bytes, b, smem); } while (0)
     const bool lean = h->dc.lean && mode == MODE_STEP;
 #define RUN3(M) do { bool np = h->cfg.rng_mode == PGTG_RNG_NUMPY; if (tape) RUN(PGTG_RNG_TAPE, M, false); \
     else if (np) { if (h->dc.pregen && lean) RUNL(PGTG_RNG_NUMPY, M); else if (h->dc.pregen) RUN(PGTG_RNG_NUMPY, M, true); else RUN(PGTG_RNG_NUMPY, M, false); } \

@@ -97,11 +97,15 @@ def test_results_do_not_depend_on_sharding():
         e.close()
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(random_map_obstacle_probability=0.4), dict(random_map_width=3, random_map_height=3)],
-                         ids=["default", "obstacles", "3x3"])
+@pytest.mark.parametrize("kw", [dict(), dict(random_map_obstacle_probability=0.4), dict(random_map_width=3, random_map_height=3),
+                                dict(use_sliding_observation_window=True, sliding_observation_window_size=5, use_next_subgoal_direction=True,
+                                     random_map_obstacle_probability=0.3),
+                                dict(use_next_subgoal_direction=True), dict(use_sliding_observation_window=True, final_observation=True)],
+                         ids=["default", "obstacles", "3x3", "sliding5+nsd", "nsd", "sliding9+final"])
 def test_specialised_kernels_match_general(kw, monkeypatch):
-    """The lean tick and the tabled map generation are compile-time specialisations of the general
-    kernels (same source, cold code not emitted): switching them off must not change one bit."""
+    """The lean tick (plain, and its SLIDE variant for the sliding window / next_subgoal_direction) and the tabled map
+    generation are compile-time specialisations of the general kernels (same source, cold code not emitted): switching
+    them off must not change one bit."""
     import torch
 
     from pgtg_b200 import PGTGVectorEnv
@@ -117,7 +121,14 @@ def test_specialised_kernels_match_general(kw, monkeypatch):
         out = []
         for a in actions:
             obs, rew, term, trunc, info = env.step(a)
-            out.append((env._t["obs_map"].clone(), obs["position"].clone(), obs["velocity"].clone(), rew.clone(), term.clone(), trunc.clone()))
+            row = [env._t["obs_map"].clone(), obs["position"].clone(), obs["velocity"].clone(), rew.clone(), term.clone(), trunc.clone()]
+            if "next_subgoal_direction" in obs:
+                row.append(obs["next_subgoal_direction"].clone())
+            if kw.get("final_observation"):
+                fin = info["_final_observation"]
+                row.append(fin.clone())
+                row.append(env._t["final_obs_map"][fin].clone())
+            out.append(tuple(row))
         return out, env.episode_stats()
 
     fast, fast_stats = run()
