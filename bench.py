@@ -53,12 +53,12 @@ WORKLOADS = {
     "train-py": (TRAIN_PY, 262144, 1024, dict(max_episode_steps=100, flat=True)),
     # gymnasium's vector contract: terminal observations of auto-reset envs are written too
     "default-2M+final_observation": (dict(), 2 * 1024 * 1024, 16384, dict(final_observation=True)),
-    # a car-free configuration outside the lean tick's promise (general tick): sliding window + next_subgoal_direction
+    # the observation of train.py without cars: 11x11 sliding window + next_subgoal_direction (the lean SLIDE tick)
     "sliding-nsd-1M": (dict(use_sliding_observation_window=True, sliding_observation_window_size=5, use_next_subgoal_direction=True), 1024 * 1024, 8192, {}),
     # small smoke-sized run
     "default-64k": (dict(), 65536, 8192, {}),
 }
-EXTRA = ["traffic-64k", "large-1M", "train-py", "default-2M+final_observation"]
+EXTRA = ["traffic-64k", "large-1M", "train-py", "default-2M+final_observation", "sliding-nsd-1M"]
 
 
 def mean_cars(kw: dict) -> float:

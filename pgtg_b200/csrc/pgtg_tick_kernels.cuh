@@ -264,7 +264,11 @@ static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, co
   // same L1/shared carveout as the map-generation kernel: an SM cannot host CTAs of two kernels with
   // different carveouts, which would serialise the two (measured: no overlap at all without this)
   static bool carve_set = false;
-  if (!carve_set) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve_set = true; }
+  if (!carve_set) {
+    const char* cv = getenv("PGTG_TICK_CARVEOUT");  // tuning knob
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
+    carve_set = true;
+  }
   const size_t smem = LEAN ? pgtg::block_shared_bytes(e->dc, e->block, true) : e->smem;
   if (smem > 48 * 1024) {
     { int rc = lk(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); if (rc) return rc; }
