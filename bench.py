@@ -331,6 +331,11 @@ def main():
 
     N = n_gpu_envs
     flat = bool(extras.get("flat"))
+    # host threads and the pinned buffers allocated below on the GPU's own NUMA node (the e2e legs are host-copy bound)
+    from pgtg_b200.distributed import bind_to_gpu_numa_node
+
+    full_affinity = os.sched_getaffinity(0)
+    numa = None if os.environ.get("PGTG_NO_NUMA_BIND") else bind_to_gpu_numa_node(local)
     env = make_env(args.workload, N, dev, rank, args.final_observation)
     env.reset()
     pool = action_pool(N, dev, rank)
@@ -412,6 +417,7 @@ def main():
             pout = env.packed_host_buffers(pinned=True)
             packed_bytes = sum(v.nbytes for v in pout.values())
             e2e_packed = timed_host_loop(lambda a: env.step_host_packed(a, pout), args.e2e_steps * 4)
+    os.sched_setaffinity(0, full_affinity)  # the CPU baselines below use every core the process was given
     if sampler:
         sampler.end()
     clocks = sampler.stop() if sampler else None
@@ -465,6 +471,7 @@ def main():
             "e2e_packed": {"value": e2e_packed, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": packed_bytes,
                            "path": "pgtg_step_host_packed: observation planes as bits (pgtg_unpack_obs restores the int8 planes on the host), double-buffered"},
             "gpu_launches": int(launches),
+            "numa": numa,  # what bind_to_gpu_numa_node did for this rank (None: topology not exposed)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg, "kernel_ms": kernel_ms,
                          "kernel": info,

@@ -30,7 +30,42 @@ def all_reduce_stats(stats):
     return stats
 
 
-def make_sharded(total_envs: int, device=None, **kwargs):
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int, sysfs: str = "/sys/bus/pci/devices") -> dict | None:
+    """Pin this process to the CPUs next to its GPU (the PCI device's `local_cpulist`), so that the pinned host buffers it
+    allocates afterwards -- and the threads that read them -- live on the GPU's own NUMA node: the host-buffer entry
+    points (`pgtg_step_host*`) are bounded by device->host copies, and on a two-socket node a buffer on the far socket
+    sends every copy across the socket interconnect. Call it before allocating pinned memory. Returns what it did
+    ({"numa_node", "cpus"}), or None when the topology is not exposed (single node, container without sysfs)."""
+    import torch
+
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        addr = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs, addr, "local_cpulist")) as fh:
+            cpus = _parse_cpulist(fh.read())
+        with open(os.path.join(sysfs, addr, "numa_node")) as fh:
+            node = int(fh.read().strip())
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return {"numa_node": node, "cpus": len(allowed), "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "bound": True}
+    except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):
+        return None
+
+
+def make_sharded(total_envs: int, device=None, bind_numa: bool = True, **kwargs):
     """A `PGTGVectorEnv` over this rank's shard of `total_envs` global envs (one process per GPU,
     launched with torchrun)."""
     import torch
@@ -40,4 +75,6 @@ def make_sharded(total_envs: int, device=None, **kwargs):
     base, n = shard(total_envs)
     if device is None:
         device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    if bind_numa and torch.device(device).type == "cuda":
+        bind_to_gpu_numa_node(torch.device(device).index or 0)
     return PGTGVectorEnv(n, device=device, env_id_base=base, **kwargs)

@@ -63,3 +63,16 @@ def test_two_ranks_equal_one_process(tmp_path):
         assert np.array_equal(z["rewards"], ref_rewards[:, b:b + n])
         assert np.array_equal(z["obs"], ref_obs[:, b:b + n])
         assert np.allclose(z["total"], ref_stats)
+
+
+def test_numa_binding_helper_is_safe_without_topology(tmp_path):
+    """bind_to_gpu_numa_node: cpulist parsing, and no effect (None) where the GPU / its sysfs entry is not visible."""
+    import os
+
+    from pgtg_b200.distributed import _parse_cpulist, bind_to_gpu_numa_node
+
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    assert os.sched_getaffinity(0) == before
