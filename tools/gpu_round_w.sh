@@ -17,3 +17,7 @@ tools/ncu_capture.sh r02_ncu_large1M traffic_tick 4 --workload large-1M --steps 
 tools/ncu_capture.sh r02_ncu_trainpy traffic_tick 4 --workload train-py --steps 3 --warmup 3 $B
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,driver_version --format=csv > gpurun_out/r02_gpu.txt
 tail -2 gpurun_out/r02_pytest_gpu.log
+tools/ncu_capture.sh r02_ncu_lean_slide_tick pgtg_tick_kernel 6 --workload sliding-nsd-1M --steps 3 --warmup 3 $B
+python bench.py --workload sliding-nsd-1M --steps 30 --warmup 5 --cpu-seconds 3 --python-seconds 3 --e2e-steps 0 --no-extra > gpurun_out/r02_bench_sliding-nsd-1M.json 2> gpurun_out/r02_bench_sliding-nsd-1M.err
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_smoke.log 2>&1
+tail -2 gpurun_out/r02_smoke.log
