@@ -13,6 +13,7 @@
 //   const char* bk_error();  int bk_dl_device_type();
 //   int bk_conn_table_max_bits();  int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
 //   int bk_build_path_table(pgtg_env*, uint64_t* table_dev);
+//   bool bk_inline_mapgen();   whether the backend has the tick instantiation that generates maps itself (PGTG_INLINE_MAPGEN)
 //   int bk_side_create(void** stream, void** ev_tick, void** ev_map0, void** ev_map1, int* sm_count);
 //   void bk_side_destroy(void*, void*, void*, void*);  int bk_stream_wait(void* stream, void* ev);
 //   void* bk_event_create();  void bk_event_destroy(void*);  int bk_event_record(void* ev, void* stream);
@@ -249,7 +250,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
   e->cars_injected = false;
   e->timing = false; e->tev_used = 0;
   e->side_stream = e->ev_tick = e->ev_map[0] = e->ev_map[1] = nullptr;
-  e->launch_index = 0; e->mapgen_grid = 0;
+  e->launch_index = 0; e->mapgen_grid = 0; e->inline_mapgen = false;
   e->flat = nullptr; e->flat_dim = 0;
   e->info_dev = nullptr;
   e->packed_dev = nullptr; e->stage_dev[0] = e->stage_dev[1] = nullptr; e->stage_bytes = 0; e->copy_stream = nullptr;
@@ -391,6 +392,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     int per_sm = env_ctas ? atoi(env_ctas) : 0;  // 0 = full grid (best with the connectivity table)
     e->mapgen_grid = per_sm > 0 ? sms * per_sm : 0;
     e->mapgen_grid_overlap = e->mapgen_grid; e->overlap = !getenv("PGTG_NO_OVERLAP");
+    e->inline_mapgen = bk_inline_mapgen() && getenv("PGTG_INLINE_MAPGEN") != nullptr && cfg->rng_mode == PGTG_RNG_PHILOX && !getenv("PGTG_NO_LEAN");  // (and map_in_registers: below)
   }
   if (e->dc.conn_bits) {
     size_t words = ((size_t)1 << e->dc.conn_bits) / 32 + 1;
@@ -419,6 +421,7 @@ extern "C" int pgtg_create(const pgtg_config* cfg, int device, pgtg_env** out) {
     if (!t || bk_build_path_table(e, t)) { pgtg_destroy(e); return fail(PGTG_ERR_CUDA, std::string("path table: ") + bk_error()); }
     p.path_table = t;
   }
+  if (!pgtg::map_in_registers(e->dc)) e->inline_mapgen = false;  // (needs both tables, decided just above)
   bk_sync(nullptr);
   *out = e;
   return PGTG_OK;
@@ -506,6 +509,7 @@ extern "C" int pgtg_load_draws(pgtg_env* e, const double* values, const uint8_t*
   return PGTG_OK;
 }
 
+static int join_side(pgtg_env* e, void* stream);
 // One launch of the pregen pipeline. Launch L appends its map requests to queue L&1 and
 // reads only ring slots filled by map generations <= L-2, so the map generation of launch L-1 (side
 // stream, small persistent grid) runs concurrently with the tick of launch L. `join` makes the caller's
@@ -514,6 +518,16 @@ static int run_pipeline(pgtg_env* e, int mode, const uint8_t* mask, const int64_
   if (!e->dc.pregen) {
     if (bk_launch(e, mode, mask, seeds, actions, action_bytes, stream)) return -1;
     e->launches++;
+    return 0;
+  }
+  if (mode == MODE_STEP && inline_mapgen_now(e)) {  // no requests, no second kernel; maps of a reset may still be in flight
+    if (join_side(e, stream)) return -1;
+    const bool timed1 = e->timing && e->tev_used + 4 <= (int)e->tev.size();
+    if (timed1) bk_event_record(e->tev[e->tev_used], stream);
+    if (bk_launch(e, mode, mask, seeds, actions, action_bytes, stream)) return -1;
+    e->launches++;
+    if (timed1) { for (int i = 1; i < 4; i++) bk_event_record(e->tev[e->tev_used + i], stream); e->tev_used += 4; }
+    e->launch_index++;
     return 0;
   }
   int par = (int)(e->launch_index & 1);

@@ -33,6 +33,7 @@ struct pgtg_env {
   // pregen pipeline: the persistent map-generation kernel runs on a side stream and overlaps the next tick
   void* side_stream; void* ev_tick; void* ev_map[2];
   uint64_t launch_index;
+  bool inline_mapgen;   // experiment (PGTG_INLINE_MAPGEN): the lean tick rebuilds consumed ring slots itself
   int mapgen_grid;      // CTAs of the persistent map-generation kernel (0 = one per 128 requests)
   int mapgen_grid_overlap; bool overlap;  // overlap on: side stream + small grid; off: same stream, full grid
   // optional per-kernel timing (CUDA events on the launching stream around each kernel of a tick)
@@ -51,3 +52,5 @@ struct pgtg_env {
   std::vector<uint16_t> edge_tab, edge_rev, border_slots;
 };
 
+// the lean tick generates the maps itself (experiment, PGTG_INLINE_MAPGEN): plain lean configuration only
+static inline bool inline_mapgen_now(const pgtg_env* e) { return e->inline_mapgen && e->dc.pregen && e->dc.lean == 1 && !e->dc.write_final_obs; }

@@ -60,6 +60,7 @@ static int bk_flatten(pgtg_env*, void* stream);
 static int bk_info(pgtg_env*, int32_t* out_dev);
 static int bk_error_or(pgtg_env*, uint32_t* out_dev);
 static int bk_conn_table_max_bits() { return 24; }
+static bool bk_inline_mapgen() { return true; }
 static int bk_build_conn_table(pgtg_env*, uint32_t* table_dev);
 static int bk_build_path_table(pgtg_env*, uint64_t* table_dev);
 int pgtg_traffic_geometry(const pgtg::DevCfg& c, int* G, int* NT, size_t* smem);  // pgtg_traffic.cu

@@ -45,7 +45,9 @@ __device__ unsigned long long g_phase_clk[16];
 
 // (FINAL: the lean instantiation that also writes the terminal observation of the finished envs, gymnasium's final_observation;
 //  SLIDE: the lean instantiation for the sliding window and / or next_subgoal_direction -- the observation of train.py without cars)
-template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false, bool SLIDE = false>
+//  INLINE: a finished env's thread rebuilds the ring slot it has just consumed right here, after the expansion, instead of queueing
+//  a request for the map-generation kernel (register-resident generator; experiment)
+template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false, bool SLIDE = false, bool INLINE = false>
 __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BLOCKS) pgtg_tick_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p,
                                                         const uint8_t* __restrict__ mask, const int64_t* __restrict__ seeds,
                                                         const void* __restrict__ actions, int action_bytes, StatsArgs sa,
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
       // needs one barrier only, the one in front of the byte expansion. Map requests are queued
       // per warp; the atomic's round trip hides behind the observation emit.
       uint32_t k = 0, qbase = 0;
-      if (any && lane == 0) qbase = atomicAdd(p.regen_count + p.parity, (uint32_t)__popc(any));
+      if (!INLINE && any && lane == 0) qbase = atomicAdd(p.regen_count + p.parity, (uint32_t)__popc(any));
       PG_CLK(3)
       if (LEAN && FINAL) {  // terminal observation first: emit the finished envs' planes, expand their rows, clear the bitstring
         if (lane == 0) sh.counters[16 + warp] = (int)any;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
       PG_CLK(4)
       if (valid) { if (LEAN) phase_emit_regs<true, SLIDE>(c, p, sh, tid, env, false, er); else phase_emit<false>(c, p, sh, tid, env, false); }
       PG_CLK(5)
-      if (any) {
+      if (!INLINE && any) {
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
         if (done) {
           uint2 q; q.x = (uint32_t)env; q.y = k + 2u;
@@ -147,6 +149,8 @@ __global__ void __launch_bounds__(128, LEAN ? PGTG_LEAN_MIN_BLOCKS : PGTG_MIN_BL
       }
       phase_expand(c, p.obs_map, sh, tid, B, env0, nvalid, p.obs_packed);
       PG_CLK(8)
+      if (INLINE && LEAN && done)  // (the thread's tile row is dead after the emit: it serves as the generator's edge array)
+        phase_pregenerate_in_registers<RNG>(c, p, (uint8_t*)(sh.tiles + tid * c.tile_stride), env, k + 2u);
       return;
     }
   } else if (MODE == MODE_RESET) {
@@ -258,9 +262,9 @@ __global__ void __launch_bounds__(128, MINB) pgtg_mapgen_registers_kernel(const 
 // launch code: returns the cudaError_t of the launch (0 = ok)
 static inline int lk(cudaError_t e) { return (int)e; }
 
-template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false, bool SLIDE = false>
+template <int RNG, int MODE, int TMAX, bool PREGEN, bool LEAN = false, bool FINAL = false, bool SLIDE = false, bool INLINE = false>
 static int launch_one(pgtg_env* e, const uint8_t* mask, const int64_t* seeds, const void* actions, int action_bytes, cudaStream_t st) {
-  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN, LEAN, FINAL, SLIDE>;
+  auto kern = pgtg::pgtg_tick_kernel<RNG, MODE, TMAX, PREGEN, LEAN, FINAL, SLIDE, INLINE>;
   // same L1/shared carveout as the map-generation kernel: an SM cannot host CTAs of two kernels with
   // different carveouts, which would serialise the two (measured: no overlap at all without this)
   static bool carve_set = false;
@@ -339,6 +343,7 @@ static int launch_mode(pgtg_env* e, int mode, const uint8_t* mask, const int64_t
           return launch_one<R, MODE_STEP, 16, L, L, false, L>(e, mask, seeds, actions, action_bytes, st);
         }
         if (e->dc.write_final_obs) return launch_one<R, MODE_STEP, 16, L, L, L>(e, mask, seeds, actions, action_bytes, st);
+        if constexpr (RNG == PGTG_RNG_PHILOX) { if (inline_mapgen_now(e)) return launch_one<R, MODE_STEP, 16, L, L, false, false, L>(e, mask, seeds, actions, action_bytes, st); }
         return launch_one<R, MODE_STEP, 16, L, L>(e, mask, seeds, actions, action_bytes, st);
       }
       if (RNG != PGTG_RNG_TAPE && e->dc.pregen) return launch_sized<RNG, MODE_STEP, RNG != PGTG_RNG_TAPE>(e, mask, seeds, actions, action_bytes, st);

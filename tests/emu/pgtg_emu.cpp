@@ -40,6 +40,7 @@ static int bk_stats_reset(pgtg_env*, void*);
 static int bk_flatten(pgtg_env*, void*);
 static int bk_info(pgtg_env*, int32_t*);
 static int bk_error_or(pgtg_env*, uint32_t*);
+static bool bk_inline_mapgen() { return false; }
 static int bk_conn_table_max_bits() { return 13; }  // CPU tests: tables up to 8192 entries (e.g. 3x3 maps)
 static int bk_build_conn_table(pgtg_env*, uint32_t*);
 static int bk_build_path_table(pgtg_env*, uint64_t*);

@@ -188,3 +188,39 @@ def test_lean_final_observation_matches_general(monkeypatch):
             assert torch.equal(x, y), f"tick {t}"
         finished += int(a[2].sum())
     assert finished > 100000
+
+
+@pytest.mark.gpu
+def test_inline_map_generation_matches_the_pipeline(monkeypatch):
+    """PGTG_INLINE_MAPGEN: the lean tick rebuilds consumed ring slots itself instead of queueing requests for the
+    map-generation kernel (faster below ~100 k envs, where the step is launch-bound; slower at the headline size --
+    DESIGN.md section 7). Same maps, same everything."""
+    import torch
+
+    from pgtg_b200 import PGTGVectorEnv
+
+    n, ticks = 30000, 30
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(3)
+    actions = [torch.randint(0, 9, (n,), device="cuda:0", dtype=torch.int32, generator=g) for _ in range(ticks)]
+
+    def run():
+        env = PGTGVectorEnv(n, device="cuda:0", seed=9)
+        env.reset()
+        out = []
+        for a in actions:
+            obs, rew, term, trunc, _ = env.step(a)
+            out.append((env._t["obs_map"].clone(), obs["position"].clone(), rew.clone(), term.clone()))
+        launches = env.launch_count()
+        st = env.episode_stats()
+        env.close()
+        return out, st, launches
+
+    a, sa, la = run()
+    monkeypatch.setenv("PGTG_INLINE_MAPGEN", "1")
+    b, sb, lb = run()
+    assert lb < la  # no map-generation launches after the reset
+    for t, (x, y) in enumerate(zip(a, b)):
+        for u, v in zip(x, y):
+            assert torch.equal(u, v), f"tick {t}"
+    assert sa["episodes"] == sb["episodes"] > 0
