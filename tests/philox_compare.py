@@ -84,6 +84,11 @@ CONFIGS = {
     "tabled_4x2_registers_sparse": (dict(random_map_width=4, random_map_height=2, random_map_percentage_of_connections=0.2,
                                          max_episode_steps=12), 300, 40),
     "tabled_3x3_shared": (dict(random_map_width=3, random_map_height=3, random_map_obstacle_probability=0.3), 200, 40),
+    # 16-tile strips and slabs: other edge / border-slot counts through the register-resident generator on the device
+    # (1x16: 15 edges, 32 border slots, no grid faces; 8x2: 22 edges, 18 slots)
+    "strip_1x16": (dict(random_map_width=1, random_map_height=16, random_map_obstacle_probability=0.2), 200, 40),
+    "strip_16x1_traffic": (dict(random_map_width=16, random_map_height=1, traffic_density=0.1), 120, 40),
+    "slab_8x2": (dict(random_map_width=8, random_map_height=2, random_map_percentage_of_connections=0.3), 200, 40),
     # car-free configurations outside the lean tick's promise (they run the traffic tick's parallel observation phases)
     "carfree_sliding_nsd": (dict(use_sliding_observation_window=True, sliding_observation_window_size=5, use_next_subgoal_direction=True,
                                  random_map_obstacle_probability=0.5), 200, 40),
