@@ -116,19 +116,36 @@ __global__ void __launch_bounds__(128) pgtg_build_path_table_kernel(const __grid
     table[g] = path_table_entry(c, *sh.lut, g, sh.tiles + threadIdx.x * c.tile_stride);
 }
 
-// FlattenObservation view: one warp per env, plane by plane (no per-element divisions), coalesced float32 stores;
-// reads the int8 planes through L2 (they were just written by the tick).
-__global__ void __launch_bounds__(256) pgtg_flatten_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, FlatOrder order,
-                                                          float* __restrict__ out, int dim) {
-  const int PP = c.P * c.P, lane = threadIdx.x & 31;
+// FlattenObservation view: one warp per env; the C*P*P plane cells are one flat index space (cell -> plane by a multiply-high,
+// no division), a lane takes eight cells 32 apart per round and issues the eight byte loads before the first store, so a
+// warp keeps eight sectors in flight instead of one (the one-load-at-a-time loop this replaces was bound by that latency:
+// 0.51 ms for 262 144 envs of the train.py configuration; now 0.33 ms = 4.3 TB/s of reads + float32 stores, 66 % of the
+// measured HBM bandwidth). Measured and no faster: sixteen loads per round, a plane-uniform chunk loop, reading the packed
+// bits instead of the int8 planes -- what is left is the 4.5 KB of 32-bit stores per env. Reads go through L2.
+__global__ void __launch_bounds__(256) pgtg_flatten_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevPtrs p, const __grid_constant__ FlatOrder order,
+                                                          float* __restrict__ out, int dim, uint32_t inv_pp /* ceil(2^32 / (P*P)) */) {
+  const int PP = c.P * c.P, total = c.C * PP, lane = threadIdx.x & 31;
   for (int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); env < c.N; env += gridDim.x * (blockDim.x >> 5)) {
     float* o = out + (size_t)env * dim;
-    const int8_t* m = p.obs_map + (size_t)env * c.C * PP;
-    for (int k = 0; k < c.C; k++) {
-      const int8_t* src = m + order.plane[k] * PP;
-      for (int cell = lane; cell < PP; cell += 32) o[k * PP + cell] = (float)src[cell];
+    const int8_t* m = p.obs_map + (size_t)env * total;
+    for (int base = lane; base < total; base += 32 * 8) {
+      int8_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int idx = base + 32 * u;
+        v[u] = 0;
+        if (idx < total) {
+          const int k = PP == 1 ? idx : (int)__umulhi((uint32_t)idx, inv_pp);  // idx / PP (exact: idx < 2^16; 2^32 / 1 does not fit)
+          v[u] = __ldg(m + order.plane[k] * PP + (idx - k * PP));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int idx = base + 32 * u;
+        if (idx < total) o[idx] = (float)v[u];
+      }
     }
-    o += c.C * PP;
+    o += total;
     if (c.use_nsd) {  // Discrete(9, start=-1) one-hot
       if (lane < 9) o[lane] = (p.obs_nsd[env] + 1 == lane) ? 1.0f : 0.0f;
       o += 9;
@@ -223,7 +240,8 @@ static int bk_flatten(pgtg_env* e, void* stream) {
   for (int i = 0; i < PGTG_MAX_CHANNELS; i++) order.plane[i] = e->flat_order[i];
   const int warps = 8, want = (e->dc.N + warps - 1) / warps;
   const int blocks = want < 148 * 32 ? want : 148 * 32;
-  pgtg::pgtg_flatten_kernel<<<blocks, 32 * warps, 0, (cudaStream_t)stream>>>(e->dc, e->dp, order, e->flat, e->flat_dim);
+  const uint32_t pp = (uint32_t)(e->dc.P * e->dc.P), inv_pp = (uint32_t)((0x100000000ull + pp - 1) / pp);
+  pgtg::pgtg_flatten_kernel<<<blocks, 32 * warps, 0, (cudaStream_t)stream>>>(e->dc, e->dp, order, e->flat, e->flat_dim, inv_pp);
   return ck(cudaGetLastError());
 }
 static int bk_stats_reset(pgtg_env* e, void* stream) {

@@ -80,3 +80,21 @@ def test_flatten_cuda_and_save_map(tmp_path):
     o2, _ = again.reset()
     assert torch.equal(o2["map"]["walls"][0], venv._observation()["map"]["walls"][3])
     venv.close(); again.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [0, 2, 5, 8])
+def test_flatten_cuda_sliding_windows(k):
+    """the flat index space of the flatten kernel (cell -> plane by a multiply-high) over window sizes 1, 5, 11 and 17
+    (the position space stays MultiDiscrete([9, 9]), environment.py:428, so gymnasium itself cannot flatten windows beyond k = 8)"""
+    from native_env import NativeAdapter
+
+    n = 70
+    env = NativeAdapter("cuda", num_envs=n, seed=5, traffic_density=0.1, random_map_obstacle_probability=0.5, use_next_subgoal_direction=True,
+                        use_sliding_observation_window=True, sliding_observation_window_size=k)
+    env.reset()
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        env.step(rng.integers(0, 9, n).astype(np.int32))
+        _check(env, True)
+    env.close()
