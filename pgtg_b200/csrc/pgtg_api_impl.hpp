@@ -148,7 +148,7 @@ static void derive_lut(Lut& L) {
   for (int w = 0; w < 3; w++) L.exit_any[w] = L.exit_line[0][w] | L.exit_line[1][w] | L.exit_line[2][w] | L.exit_line[3][w];
   for (int d = 0; d < 4; d++) {
     int n = 0;
-    for (int sq = 0; sq < 81; sq++) if (((L.exit_line[d][sq >> 5] >> (sq & 31)) & 1u) && n < 4) L.line_sq[d][n++] = (uint8_t)sq;
+    for (int sq = 0; sq < 81; sq++) if (((L.exit_line[d][sq >> 5] >> (sq & 31)) & 1u) && n < 4) { L.line_xy[d][n] = (uint8_t)((sq / TILE) | (sq % TILE) << 4); L.line_sq[d][n++] = (uint8_t)sq; }
   }
   for (int e = 0; e < 16; e++) {
     L.lane_count[e] = (uint8_t)(__builtin_popcount(L.lane_any[e][0]) + __builtin_popcount(L.lane_any[e][1]) + __builtin_popcount(L.lane_any[e][2]));

@@ -269,6 +269,7 @@ struct Lut {
   uint32_t spawner_cols;  // local columns that can hold a car_spawner
   uint32_t exit_any[3];   // union of the four exit lines
   uint8_t line_sq[4][4];  // the three squares of each exit line in ascending order
+  uint8_t line_xy[4][4];  // the same as local x | y << 4
   uint8_t lane_count[16]; // lane squares of a tile type
   uint8_t entry_ok[16];   // per tile type, bit k: the border spawner of slot k + 1 exists (spawner slots, pgtg_logic.cuh)
 };
@@ -639,7 +640,8 @@ struct MapView {
   // nearest remaining subgoal / final-goal square: first strict minimum of the Manhattan distance
   // in the x-major scan (environment.py:1047-1053, 1474-1480) == lexicographic min of (d, x, y), i.e. the minimum of the
   // key d << 16 | x << 8 | y. tile_goal_key = the best key among the goal-line squares of tile t (0xFFFFFFFF: none).
-  PG_MEMBER uint32_t tile_goal_key(int t, int px, int py) const {
+  PG_MEMBER uint32_t tile_goal_key(int t, int px, int py) const { return tile_goal_key(t, (t % c.W) * TILE, (t / c.W) * TILE, px, py); }
+  PG_MEMBER uint32_t tile_goal_key(int t, int ox, int oy, int px, int py) const {  // (ox, oy): the tile's origin square
     const unsigned td = tiles[t];
     const int sg = td_sg(td);
     if (!sg) return 0xFFFFFFFFu;
@@ -649,12 +651,11 @@ struct MapView {
     // claimed earlier by start? (only possible on degenerate fixed maps) -- labels decide
     const unsigned lab = (line_labels(t, td) >> (4 * d)) & 15;
     if (lab != 1 && lab != 4) return 0xFFFFFFFFu;
-    const int ox = (t % c.W) * TILE, oy = (t / c.W) * TILE;
     uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < 3; k++) {  // the 3 squares of exit line d (north (3..5,0) east (8,3..5) ...), from the derived LUT
-      const int sq = L.line_sq[d][k];
-      const int X = ox + sq / TILE, Y = oy + sq % TILE;
+      const int xy = L.line_xy[d][k];
+      const int X = ox + (xy & 15), Y = oy + (xy >> 4);
       const uint32_t key = (uint32_t)(abs(X - px) + abs(Y - py)) << 16 | (uint32_t)X << 8 | (uint32_t)Y;
       best = key < best ? key : best;
     }
@@ -664,7 +665,13 @@ struct MapView {
     uint32_t best = ng_key;  // (the traffic tick computes the key beforehand, one tile per thread)
     if (!ng_pre) {
       best = 0xFFFFFFFFu;
-      for (int t = 0; t < c.T; t++) { const uint32_t k = tile_goal_key(t, px, py); best = k < best ? k : best; }
+      int ox = 0, oy = 0;  // tile origins walked row by row (no division per tile)
+      for (int t = 0; t < c.T; t++) {
+        const uint32_t k = tile_goal_key(t, ox, oy, px, py);
+        best = k < best ? k : best;
+        ox += TILE;
+        if (ox == c.WS) { ox = 0; oy += TILE; }
+      }
     }
     gx = (int)((best >> 8) & 255u); gy = (int)(best & 255u);
     return best != 0xFFFFFFFFu;
