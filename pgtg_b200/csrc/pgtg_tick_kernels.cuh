@@ -14,7 +14,7 @@ namespace pgtg {
 #define PGTG_MIN_BLOCKS 8
 #endif
 #ifndef PGTG_MAPGEN_TABLED_MIN_BLOCKS
-#define PGTG_MAPGEN_TABLED_MIN_BLOCKS 16  /* 32 registers, no spills: the tabled generator has no flood fill / BFS state */
+#define PGTG_MAPGEN_TABLED_MIN_BLOCKS 12  /* 40 registers (the staged tabled generator: numpy-exact mode, 9-tile maps); at 16 CTAs/SM it spills */
 #endif
 #ifndef PGTG_LEAN_MIN_BLOCKS
 #define PGTG_LEAN_MIN_BLOCKS 8
