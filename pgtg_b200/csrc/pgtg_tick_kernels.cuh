@@ -311,9 +311,10 @@ static int launch_mapgen(pgtg_env* e, cudaStream_t st) {
     if (pgtg::map_in_registers(e->dc) && !getenv("PGTG_NO_MAP_IN_REGISTERS")) {
       const char* mb = getenv("PGTG_MAPGEN_MINB");   // tuning knobs
       const char* cv = getenv("PGTG_MAPGEN_CARVEOUT");
-      // 48 registers; 45 KB shared and the rest L1 (the connectivity lookups of the first trips hit it) -- except next to the
-      // traffic tick, which leaves SMs free for this kernel only if both ask for the same carveout (measured)
-      const int minb = mb ? atoi(mb) : 10, carve = cv ? atoi(cv) : (e->traffic_G > 0 ? (int)cudaSharedmemCarveoutMaxShared : 25);
+      // 12 CTAs/SM at 40 registers (sweep of 8 / 10 / 12 / 16 on the final kernel: 12 is 1-2 % ahead); 54 KB shared and the rest
+      // L1 (the connectivity lookups of the first trips hit it) -- except next to the traffic tick, which leaves SMs free for
+      // this kernel only if both ask for the same carveout (measured)
+      const int minb = mb ? atoi(mb) : 12, carve = cv ? atoi(cv) : (e->traffic_G > 0 ? (int)cudaSharedmemCarveoutMaxShared : 30);
       if (minb >= 16) return launch_mapgen_registers<RNG, 16>(e, st, grid, carve);
       if (minb >= 12) return launch_mapgen_registers<RNG, 12>(e, st, grid, carve);
       if (minb >= 10) return launch_mapgen_registers<RNG, 10>(e, st, grid, carve);
